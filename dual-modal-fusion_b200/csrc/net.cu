@@ -1,0 +1,761 @@
+// GMFNet on sm_100a: weight packing, the two CUDA-core stems (fused with the patch gather), the
+// tcgen05 conv layers (conv_tc.cuh), the head (GAP + 2 linears + argmax + confusion matrix) and the
+// chunked whole-scene driver.  Replaces model.gmfnet.Net behind solver/mainsolver.py:30-38,52,109,169
+// and the loops of Solver.test()/color() (solver/mainsolver.py:104-141, 167-185).
+//
+// Data flow for a chunk of NB pixels (activations in the C8-planar bf16 layout, see conv_tc.cuh):
+//   scene --stem_ms--> A1[NB][8][p][p][8]   --conv ms2 (+pool)--> CAT[NB][0..15][p/2][p/2][8]
+//   scene --stem_pan-> B1[NB][4][2p][2p][8] --conv pan2 (+pool)-> B2[NB][8][p][p][8]
+//                                            --conv pan3 (+pool)-> CAT[NB][16..31][p/2][p/2][8]
+//   CAT --conv 1x1 fuse--> F[NB][16][p/2][p/2][8] --head--> logits / pred / confusion matrix
+// The stems read the patch windows straight from the padded scene (K1 is never materialised on the
+// inference path).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace dmf {
+
+constexpr int C_MS1 = 64, C_MS2 = 128, C_PAN1 = 32, C_PAN2 = 64, C_PAN3 = 128, C_CAT = 256, C_FUSE = 128, C_HID = 64;
+constexpr float BN_EPS = 1e-5f;
+constexpr int kSmemLimit = 227 * 1024;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+struct LayerGeom {
+    int S, taps, cin, cout, pool;
+    int NP, TH, tiles_x, tiles_y, PX, tiles_per_group, a_plane, a_stage, sbo_a, n_stage, smem;
+};
+
+static int make_geom(LayerGeom& g, int S, int taps, int cin, int cout, int pool) {
+    g.S = S; g.taps = taps; g.cin = cin; g.cout = cout; g.pool = pool;
+    const int kch = cin / 8;
+    if (taps == 9) {
+        DMF_REQUIRE(S % 8 == 0, "conv3x3 map size %d is not a multiple of 8", S);
+        g.TH = (S % 16 == 0) ? 16 : 8;
+        g.NP = 16 / g.TH;
+        g.tiles_x = S / 8; g.tiles_y = S / g.TH; g.PX = 0;
+        g.tiles_per_group = g.tiles_x * g.tiles_y;
+        g.sbo_a = tc::kPitch * 16;
+        g.a_plane = (g.TH + 2) * g.NP * tc::kPitch * 16;
+    } else {
+        const int px = S * S;
+        DMF_REQUIRE(px % 128 == 0 || 128 % px == 0, "conv1x1 map %dx%d does not tile into 128 pixels", S, S);
+        g.PX = std::min(px, 128); g.NP = 128 / g.PX; g.TH = 0; g.tiles_x = g.tiles_y = 0;
+        g.tiles_per_group = px / g.PX;
+        g.sbo_a = 128;
+        g.a_plane = 128 * 16;
+    }
+    g.a_stage = kch * g.a_plane;
+    DMF_REQUIRE(g.a_stage % 128 == 0, "A stage not 128-byte aligned");
+    const int fixed = taps * cin * cout * 2 + 2 * cout * 4 + 256;
+    g.n_stage = std::min(6, (kSmemLimit - fixed) / g.a_stage);
+    DMF_REQUIRE(g.n_stage >= 1, "layer does not fit in shared memory");
+    g.smem = fixed + g.n_stage * g.a_stage;
+    return DMF_OK;
+}
+
+// tensor map over an activation tensor [N][C/8][S][S][8] bf16 for a layer's A-tile box
+static int make_map(CUtensorMap* m, const LayerGeom& g, const void* base, int64_t N) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DMF_ERR_CUDA; }
+    const int kch = g.cin / 8, S = g.S;
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], es[4] = {1, 1, 1, 1};
+    if (g.taps == 9) {
+        dims[0] = 8ull * S; dims[1] = (cuuint64_t)N; dims[2] = S; dims[3] = kch;
+        strides[0] = (cuuint64_t)kch * S * S * 16; strides[1] = (cuuint64_t)S * 16; strides[2] = (cuuint64_t)S * S * 16;
+        box[0] = 8 * tc::kPitch; box[1] = g.NP; box[2] = g.TH + 2; box[3] = kch;
+    } else {
+        dims[0] = 8; dims[1] = (cuuint64_t)S * S; dims[2] = (cuuint64_t)N; dims[3] = kch;
+        strides[0] = 16; strides[1] = (cuuint64_t)kch * S * S * 16; strides[2] = (cuuint64_t)S * S * 16;
+        box[0] = 8; box[1] = g.PX; box[2] = g.NP; box[3] = kch;
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return DMF_ERR_CUDA; }
+    return DMF_OK;
+}
+
+struct ConvLayer {
+    LayerGeom g;
+    __nv_bfloat16* w = nullptr;   // packed [tap][cin/8][cout][8]
+    float* scale = nullptr;
+    float* shift = nullptr;
+    CUtensorMap map;              // over the workspace input buffer
+};
+
+}  // namespace dmf
+
+using namespace dmf;
+
+struct dmf_net {
+    int p = 0, C = 0, NB = 0;
+    std::map<std::string, std::vector<float>> params;
+    bool ready = false;
+    bool timing = false;
+    // stems / head weights
+    float *w_ms1 = nullptr, *sc_ms1 = nullptr, *sh_ms1 = nullptr;      // [36][64]
+    float *w_pan1 = nullptr, *sc_pan1 = nullptr, *sh_pan1 = nullptr;   // [32][12]
+    float *fc1t = nullptr, *fc1b = nullptr, *fc2t = nullptr, *fc2b = nullptr;
+    ConvLayer L[4];   // ms2, pan2, pan3, fuse
+    __nv_bfloat16 *A1 = nullptr, *B1 = nullptr, *B2 = nullptr, *CAT = nullptr, *F = nullptr;
+    cudaEvent_t ev[8] = {};
+    float stage_ms[8] = {};
+};
+
+namespace dmf {
+
+// ------------------------------------------------------------------------------------ stems
+struct PatchSrc {
+    // either windows of a scene (idx == null -> consecutive pixels from `first`) ...
+    dmf_scene scene;
+    const int64_t* idx;
+    int64_t first;
+    // ... or materialised patches [N][4][p][p] / [N][1][4p][4p]
+    const float* patches;
+};
+
+// MS stem: conv3x3 4->64 (zero padding at the PATCH border) + BN + ReLU, fp32 on CUDA cores, one CTA
+// per patch, one thread per pixel; output bf16 C8-planar.
+template <bool FROM_SCENE>
+__global__ void __launch_bounds__(256) stem_ms_kernel(PatchSrc src, int p, int64_t N, const float* __restrict__ wt,
+                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    float4* tile = reinterpret_cast<float4*>(sm);                 // (p+2) x (p+2) pixels, zero border
+    float* w_s = sm + 4 * (p + 2) * (p + 2);                       // [36][64]
+    float* sc_s = w_s + 36 * C_MS1;
+    float* sh_s = sc_s + C_MS1;
+    const int T = p + 2;
+    for (int i = threadIdx.x; i < 36 * C_MS1; i += blockDim.x) w_s[i] = wt[i];
+    for (int i = threadIdx.x; i < C_MS1; i += blockDim.x) { sc_s[i] = scale[i]; sh_s[i] = shift[i]; }
+    const int64_t n = blockIdx.x;
+    int x = 0, y = 0;
+    if (FROM_SCENE) {
+        const int64_t k = src.idx ? src.idx[n] : src.first + n;
+        x = (int)(k / src.scene.W); y = (int)(k % src.scene.W);
+    }
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+        const int r = i / T - 1, c = i % T - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r >= 0 && r < p && c >= 0 && c < p) {
+            if (FROM_SCENE) {
+                v = __ldg(reinterpret_cast<const float4*>(src.scene.ms) + (int64_t)(x + r) * src.scene.Wp + y + c);
+            } else {
+                const float* b = src.patches + n * 4 * p * p + r * p + c;
+                v = make_float4(b[0], b[p * p], b[2 * p * p], b[3 * p * p]);
+            }
+        }
+        tile[i] = v;
+    }
+    __syncthreads();
+    for (int px = threadIdx.x; px < p * p; px += blockDim.x) {
+        const int h = px / p, w = px % p;
+        float in[36];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 v = tile[(h + t / 3) * T + w + t % 3];
+            in[4 * t] = v.x; in[4 * t + 1] = v.y; in[4 * t + 2] = v.z; in[4 * t + 3] = v.w;
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < C_MS1 / 8; ++ch) {
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 36; ++k) {
+                const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * C_MS1 + ch * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * C_MS1 + ch * 8 + 4);
+                acc[0] = fmaf(in[k], w0.x, acc[0]); acc[1] = fmaf(in[k], w0.y, acc[1]);
+                acc[2] = fmaf(in[k], w0.z, acc[2]); acc[3] = fmaf(in[k], w0.w, acc[3]);
+                acc[4] = fmaf(in[k], w1.x, acc[4]); acc[5] = fmaf(in[k], w1.y, acc[5]);
+                acc[6] = fmaf(in[k], w1.z, acc[6]); acc[7] = fmaf(in[k], w1.w, acc[7]);
+            }
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = fmaxf(fmaf(acc[2 * k], sc_s[ch * 8 + 2 * k], sh_s[ch * 8 + 2 * k]), 0.f);
+                const float b = fmaxf(fmaf(acc[2 * k + 1], sc_s[ch * 8 + 2 * k + 1], sh_s[ch * 8 + 2 * k + 1]), 0.f);
+                pk[k] = tc::pack_bf16x2(a, b);
+            }
+            *reinterpret_cast<uint4*>(out + (((n * (C_MS1 / 8) + ch) * p + h) * p + w) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+// PAN stem: conv3x3 1->32 + BN + ReLU + maxpool2, fp32 on CUDA cores; one CTA per patch, one thread
+// per POOLED pixel (4x4 input window in registers); output bf16 C8-planar [N][4][2p][2p][8].
+template <bool FROM_SCENE>
+__global__ void __launch_bounds__(256) stem_pan_kernel(PatchSrc src, int p, int64_t N, const float* __restrict__ wt,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    const int P = 4 * p, T = P + 2, S = 2 * p;
+    float* tile = sm;                            // T x T, zero border
+    float* w_s = sm + ((T * T + 3) & ~3);        // [32][12] (9 taps + 3 pad)
+    float* sc_s = w_s + C_PAN1 * 12;
+    float* sh_s = sc_s + C_PAN1;
+    for (int i = threadIdx.x; i < C_PAN1 * 12; i += blockDim.x) w_s[i] = wt[i];
+    for (int i = threadIdx.x; i < C_PAN1; i += blockDim.x) { sc_s[i] = scale[i]; sh_s[i] = shift[i]; }
+    const int64_t n = blockIdx.x;
+    int x = 0, y = 0;
+    if (FROM_SCENE) {
+        const int64_t k = src.idx ? src.idx[n] : src.first + n;
+        x = (int)(k / src.scene.W); y = (int)(k % src.scene.W);
+    }
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+        const int r = i / T - 1, c = i % T - 1;
+        float v = 0.f;
+        if (r >= 0 && r < P && c >= 0 && c < P)
+            v = FROM_SCENE ? __ldg(src.scene.pan + (int64_t)(4 * x + r) * src.scene.pan_pitch + 4 * y + c)
+                           : src.patches[n * P * P + r * P + c];
+        tile[i] = v;
+    }
+    __syncthreads();
+    for (int px = threadIdx.x; px < S * S; px += blockDim.x) {
+        const int ph = px / S, pw = px % S;
+        float in[16];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) in[4 * r + c] = tile[(2 * ph + r) * T + 2 * pw + c];
+#pragma unroll 1
+        for (int ch = 0; ch < C_PAN1 / 8; ++ch) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+                float res[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int co = ch * 8 + 2 * k2 + e;
+                    const float4 wa = *reinterpret_cast<const float4*>(w_s + co * 12);
+                    const float4 wb = *reinterpret_cast<const float4*>(w_s + co * 12 + 4);
+                    const float w8 = w_s[co * 12 + 8];
+                    const float wv[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, w8};
+                    float best = -INFINITY;
+#pragma unroll
+                    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+                        for (int ox = 0; ox < 2; ++ox) {
+                            float a = 0.f;
+#pragma unroll
+                            for (int t = 0; t < 9; ++t) a = fmaf(in[(oy + t / 3) * 4 + ox + t % 3], wv[t], a);
+                            best = fmaxf(best, fmaf(a, sc_s[co], sh_s[co]));
+                        }
+                    res[e] = fmaxf(best, 0.f);
+                }
+                pk[k2] = tc::pack_bf16x2(res[0], res[1]);
+            }
+            *reinterpret_cast<uint4*>(out + (((n * (C_PAN1 / 8) + ch) * S + ph) * S + pw) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ head
+// F[N][16][px][8] bf16 -> global average pool -> Linear 128->64 + ReLU -> Linear 64->C -> logits,
+// argmax (first maximum), confusion matrix, prediction map.  128 threads, persistent over patches.
+__global__ void __launch_bounds__(128) head_kernel(const __nv_bfloat16* __restrict__ F, int64_t N, int npx, int C,
+                                                   const float* __restrict__ fc1t, const float* __restrict__ fc1b,
+                                                   const float* __restrict__ fc2t, const float* __restrict__ fc2b,
+                                                   const dmf_scene scene, const int64_t* __restrict__ idx, int64_t first,
+                                                   float* __restrict__ logits_out, uint8_t* __restrict__ pred_out,
+                                                   unsigned long long* __restrict__ cm, uint8_t* __restrict__ pred_map) {
+    extern __shared__ __align__(16) float hs[];
+    float* w1 = hs;                       // [128][64]
+    float* w2 = w1 + C_FUSE * C_HID;      // [64][C]
+    float* b1 = w2 + C_HID * C;
+    float* b2 = b1 + C_HID;
+    float* g = b2 + ((C + 3) & ~3);       // [128]
+    float* hid = g + C_FUSE;              // [64]
+    float* lg = hid + C_HID;              // [C]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(lg + ((C + 3) & ~3));   // [C*C]
+    for (int i = threadIdx.x; i < C_FUSE * C_HID; i += 128) w1[i] = fc1t[i];
+    for (int i = threadIdx.x; i < C_HID * C; i += 128) w2[i] = fc2t[i];
+    if (threadIdx.x < C_HID) b1[threadIdx.x] = fc1b[threadIdx.x];
+    if (threadIdx.x < C) b2[threadIdx.x] = fc2b[threadIdx.x];
+    for (int i = threadIdx.x; i < C * C; i += 128) hist[i] = 0;
+    __syncthreads();
+    const int t = threadIdx.x, chunk = t >> 3, sub = t & 7;
+    const float inv = 1.0f / (float)npx;
+    for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
+        // thread (chunk, sub): pixels sub, sub+8, ... of its 8-channel chunk, 16 bytes per load
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const uint4* base = reinterpret_cast<const uint4*>(F) + (n * 16 + chunk) * npx;
+        for (int px = sub; px < npx; px += 8) {
+            const uint4 v = __ldg(base + px);
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[k]));
+                s[2 * k] += f.x; s[2 * k + 1] += f.y;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s[k] += __shfl_xor_sync(0xffffffffu, s[k], 1);
+            s[k] += __shfl_xor_sync(0xffffffffu, s[k], 2);
+            s[k] += __shfl_xor_sync(0xffffffffu, s[k], 4);
+        }
+        if (sub == 0)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[chunk * 8 + k] = s[k] * inv;
+        __syncthreads();
+        if (t < C_HID) {
+            float a = b1[t];
+#pragma unroll 8
+            for (int k = 0; k < C_FUSE; ++k) a = fmaf(g[k], w1[k * C_HID + t], a);
+            hid[t] = fmaxf(a, 0.f);
+        }
+        __syncthreads();
+        if (t < C) {
+            float a = b2[t];
+#pragma unroll 8
+            for (int k = 0; k < C_HID; ++k) a = fmaf(hid[k], w2[k * C + t], a);
+            lg[t] = a;
+            if (logits_out) logits_out[n * C + t] = a;
+        }
+        __syncthreads();
+        if (t == 0) {
+            int best = 0;
+            float bv = lg[0];
+            for (int c = 1; c < C; ++c)
+                if (lg[c] > bv) { bv = lg[c]; best = c; }
+            if (pred_out) pred_out[n] = (uint8_t)best;
+            if (cm || pred_map) {
+                const int64_t k = idx ? idx[n] : first + n;
+                if (pred_map) pred_map[k] = (uint8_t)best;
+                if (cm) {
+                    const int lab = scene.label[k];
+                    if (lab < C) hist[best * C + lab] += 1;
+                }
+            }
+        }
+        // the next iteration's first __syncthreads orders these reads/writes against the reuse of g/hid/lg
+    }
+    __syncthreads();
+    if (cm)
+        for (int i = threadIdx.x; i < C * C; i += 128)
+            if (hist[i]) atomicAdd(&cm[i], (unsigned long long)hist[i]);
+}
+
+// ------------------------------------------------------------------------------------ device-side debug conv
+// Plain CUDA-core convolution over the same layouts and packed weights; fp32 accumulation, same
+// epilogue.  Exists only so tests can localise a fault to one layer on the GPU; the product path
+// never calls it.
+__global__ void direct_conv_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ w,
+                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                   __nv_bfloat16* __restrict__ out, int64_t N, int S, int cin, int cout, int taps,
+                                   int pool, int out_chunks, int out_chunk0) {
+    const int So = pool ? S / 2 : S;
+    const int64_t total = N * So * So * cout;
+    const int kch = cin / 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i % cout);
+        int64_t r = i / cout;
+        const int ow = (int)(r % So); r /= So;
+        const int oh = (int)(r % So);
+        const int64_t n = r / So;
+        float best = -INFINITY;
+        const int reps = pool ? 2 : 1;
+        for (int oy = 0; oy < reps; ++oy)
+            for (int ox = 0; ox < reps; ++ox) {
+                const int h = pool ? 2 * oh + oy : oh, wv = pool ? 2 * ow + ox : ow;
+                float acc = 0.f;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int dy = taps == 9 ? tap / 3 - 1 : 0, dx = taps == 9 ? tap % 3 - 1 : 0;
+                    const int hh = h + dy, ww = wv + dx;
+                    if (hh < 0 || hh >= S || ww < 0 || ww >= S) continue;
+                    for (int ci = 0; ci < cin; ++ci) {
+                        const float a = __bfloat162float(in[(((n * kch + ci / 8) * S + hh) * S + ww) * 8 + ci % 8]);
+                        const float b = __bfloat162float(w[(((int64_t)tap * kch + ci / 8) * cout + co) * 8 + ci % 8]);
+                        acc = fmaf(a, b, acc);
+                    }
+                }
+                const float yv = fmaxf(fmaf(acc, scale[co], shift[co]), 0.f);
+                best = fmaxf(best, __bfloat162float(__float2bfloat16_rn(yv)));
+            }
+        out[(((n * out_chunks + out_chunk0 + co / 8) * So + oh) * So + ow) * 8 + co % 8] = __float2bfloat16_rn(best);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static const std::vector<float>* param(const dmf_net* n, const std::string& k, size_t numel) {
+    auto it = n->params.find(k);
+    if (it == n->params.end()) { set_error("net: parameter '%s' was not loaded", k.c_str()); return nullptr; }
+    if (it->second.size() != numel) {
+        set_error("net: parameter '%s' has %zu elements, expected %zu", k.c_str(), it->second.size(), numel);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+// eval-mode BatchNorm folded with the conv bias: y = acc*scale + shift
+static int fold_bn(const dmf_net* n, const std::string& blk, int cout, std::vector<float>& scale, std::vector<float>& shift) {
+    auto *cb = param(n, blk + ".0.bias", cout), *gw = param(n, blk + ".1.weight", cout), *gb = param(n, blk + ".1.bias", cout),
+         *mu = param(n, blk + ".1.running_mean", cout), *var = param(n, blk + ".1.running_var", cout);
+    if (!cb || !gw || !gb || !mu || !var) return DMF_ERR_STATE;
+    scale.resize(cout); shift.resize(cout);
+    for (int c = 0; c < cout; ++c) {
+        const float s = (*gw)[c] / sqrtf((*var)[c] + BN_EPS);
+        scale[c] = s;
+        shift[c] = (*gb)[c] + ((*cb)[c] - (*mu)[c]) * s;
+    }
+    return DMF_OK;
+}
+
+template <typename T>
+static int to_device(T** dst, const std::vector<T>& v) {
+    if (*dst) cudaFree(*dst);
+    *dst = nullptr;
+    DMF_CUDA(cudaMalloc(dst, sizeof(T) * v.size()));
+    DMF_CUDA(cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    return DMF_OK;
+}
+
+static int pack_conv(dmf_net* n, ConvLayer& L, const std::string& blk) {
+    const int cin = L.g.cin, cout = L.g.cout, taps = L.g.taps, kch = cin / 8;
+    auto* w = param(n, blk + ".0.weight", (size_t)cout * cin * taps);
+    if (!w) return DMF_ERR_STATE;
+    std::vector<__nv_bfloat16> pk((size_t)taps * cin * cout);
+    for (int tap = 0; tap < taps; ++tap)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int co = 0; co < cout; ++co)
+                pk[(((size_t)tap * kch + ci / 8) * cout + co) * 8 + ci % 8] =
+                    __float2bfloat16_rn((*w)[((size_t)co * cin + ci) * taps + tap]);
+    std::vector<float> sc, sh;
+    DMF_TRY(fold_bn(n, blk, cout, sc, sh));
+    DMF_TRY(to_device(&L.w, pk));
+    DMF_TRY(to_device(&L.scale, sc));
+    DMF_TRY(to_device(&L.shift, sh));
+    return DMF_OK;
+}
+
+template <int CI, int CO, int TAPS, bool POOL>
+static int launch_conv(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16* out, int out_chunks, int out_chunk0,
+                       int64_t N, cudaStream_t st) {
+    tc::ConvParams P;
+    const LayerGeom& g = L.g;
+    P.S = g.S; P.NP = g.NP; P.TH = g.TH; P.tiles_x = g.tiles_x; P.tiles_y = g.tiles_y; P.PX = g.PX;
+    P.tiles_per_group = g.tiles_per_group;
+    P.N = (int)N;
+    P.n_tiles = (int)((N + g.NP - 1) / g.NP) * g.tiles_per_group;
+    P.a_plane = g.a_plane; P.a_stage = g.a_stage; P.n_stage = g.n_stage; P.sbo_a = g.sbo_a;
+    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0;
+    P.w = L.w; P.scale = L.scale; P.shift = L.shift; P.out = out;
+    auto kern = tc::conv_tc_kernel<CI, CO, TAPS, POOL>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr_set = true;
+    }
+    const int grid = std::min(P.n_tiles, num_sms());
+    kern<<<grid, tc::kThreads, g.smem, st>>>(map, P);
+    DMF_LAUNCHED();
+    return DMF_OK;
+}
+
+static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat16* out, int64_t N, cudaStream_t st) {
+    const int ocat = C_CAT / 8;
+    switch (layer) {
+        case 0: return launch_conv<C_MS1, C_MS2, 9, true>(n->L[0], map, out, ocat, 0, N, st);
+        case 1: return launch_conv<C_PAN1, C_PAN2, 9, true>(n->L[1], map, out, C_PAN2 / 8, 0, N, st);
+        case 2: return launch_conv<C_PAN2, C_PAN3, 9, true>(n->L[2], map, out, ocat, C_MS2 / 8, N, st);
+        case 3: return launch_conv<C_CAT, C_FUSE, 1, false>(n->L[3], map, out, C_FUSE / 8, 0, N, st);
+    }
+    return DMF_ERR_ARG;
+}
+
+static size_t stem_ms_smem(int p) { return sizeof(float) * (4 * (p + 2) * (p + 2) + 36 * C_MS1 + 2 * C_MS1); }
+static size_t stem_pan_smem(int p) {
+    const int T = 4 * p + 2;
+    return sizeof(float) * (((T * T + 3) & ~3) + C_PAN1 * 12 + 2 * C_PAN1);
+}
+static size_t head_smem(int C) {
+    return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + C_FUSE + C_HID + ((C + 3) & ~3)) +
+           sizeof(unsigned int) * C * C;
+}
+
+static int launch_stems(dmf_net* n, const PatchSrc& src, bool from_scene, int64_t N, __nv_bfloat16* A1, __nv_bfloat16* B1,
+                        int which, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMF_CUDA(cudaFuncSetAttribute(stem_pan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        DMF_CUDA(cudaFuncSetAttribute(stem_pan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    if (which & 1) {
+        if (from_scene) stem_ms_kernel<true><<<(unsigned)N, 256, stem_ms_smem(n->p), st>>>(src, n->p, N, n->w_ms1, n->sc_ms1, n->sh_ms1, A1);
+        else stem_ms_kernel<false><<<(unsigned)N, 256, stem_ms_smem(n->p), st>>>(src, n->p, N, n->w_ms1, n->sc_ms1, n->sh_ms1, A1);
+        DMF_LAUNCHED();
+    }
+    if (which & 2) {
+        if (from_scene) stem_pan_kernel<true><<<(unsigned)N, 256, stem_pan_smem(n->p), st>>>(src, n->p, N, n->w_pan1, n->sc_pan1, n->sh_pan1, B1);
+        else stem_pan_kernel<false><<<(unsigned)N, 256, stem_pan_smem(n->p), st>>>(src, n->p, N, n->w_pan1, n->sc_pan1, n->sh_pan1, B1);
+        DMF_LAUNCHED();
+    }
+    return DMF_OK;
+}
+
+// one chunk (N <= NB patches) through the whole network
+static int forward_chunk(dmf_net* n, const PatchSrc& src, bool from_scene, int64_t N, float* logits, uint8_t* pred,
+                         int64_t* cm, uint8_t* pred_map, cudaStream_t st) {
+    const bool tm = n->timing;
+    if (tm) cudaEventRecord(n->ev[0], st);
+    DMF_TRY(launch_stems(n, src, from_scene, N, n->A1, n->B1, 1, st));
+    if (tm) cudaEventRecord(n->ev[1], st);
+    DMF_TRY(run_layer(n, 0, n->L[0].map, n->CAT, N, st));
+    if (tm) cudaEventRecord(n->ev[2], st);
+    DMF_TRY(launch_stems(n, src, from_scene, N, n->A1, n->B1, 2, st));
+    if (tm) cudaEventRecord(n->ev[3], st);
+    DMF_TRY(run_layer(n, 1, n->L[1].map, n->B2, N, st));
+    if (tm) cudaEventRecord(n->ev[4], st);
+    DMF_TRY(run_layer(n, 2, n->L[2].map, n->CAT, N, st));
+    if (tm) cudaEventRecord(n->ev[5], st);
+    DMF_TRY(run_layer(n, 3, n->L[3].map, n->F, N, st));
+    if (tm) cudaEventRecord(n->ev[6], st);
+    const int npx = (n->p / 2) * (n->p / 2);
+    const int grid = (int)std::min<int64_t>(N, (int64_t)num_sms() * 4);
+    head_kernel<<<grid, 128, head_smem(n->C), st>>>(n->F, N, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, src.scene,
+                                                    src.idx, src.first, logits, pred, (unsigned long long*)cm, pred_map);
+    DMF_LAUNCHED();
+    if (tm) {
+        cudaEventRecord(n->ev[7], st);
+        DMF_CUDA(cudaEventSynchronize(n->ev[7]));
+        for (int i = 0; i < 7; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, n->ev[i], n->ev[i + 1]);
+            n->stage_ms[i] += ms;
+        }
+        float tot = 0.f;
+        cudaEventElapsedTime(&tot, n->ev[0], n->ev[7]);
+        n->stage_ms[7] += tot;
+    }
+    return DMF_OK;
+}
+
+}  // namespace dmf
+
+extern "C" {
+
+int dmf_net_create(dmf_net** out, int p, int num_classes, int max_batch) {
+    DMF_REQUIRE(out, "net_create: null");
+    DMF_REQUIRE(p == 8 || p == 16 || p == 32, "net_create: patch_size must be 8, 16 or 32 (got %d)", p);
+    DMF_REQUIRE(num_classes >= 2 && num_classes <= 64, "net_create: 2 <= Categories_Number <= 64");
+    DMF_REQUIRE(max_batch >= 1 && max_batch <= (1 << 20), "net_create: bad max_batch");
+    dmf_net* n = new dmf_net();
+    n->p = p; n->C = num_classes; n->NB = max_batch;
+    int rc = make_geom(n->L[0].g, p, 9, C_MS1, C_MS2, 1);
+    if (rc == DMF_OK) rc = make_geom(n->L[1].g, 2 * p, 9, C_PAN1, C_PAN2, 1);
+    if (rc == DMF_OK) rc = make_geom(n->L[2].g, p, 9, C_PAN2, C_PAN3, 1);
+    if (rc == DMF_OK) rc = make_geom(n->L[3].g, p / 2, 1, C_CAT, C_FUSE, 0);
+    if (rc != DMF_OK) { delete n; return rc; }
+    *out = n;
+    return DMF_OK;
+}
+
+int dmf_net_destroy(dmf_net* n) {
+    if (!n) return DMF_OK;
+    float* fs[] = {n->w_ms1, n->sc_ms1, n->sh_ms1, n->w_pan1, n->sc_pan1, n->sh_pan1, n->fc1t, n->fc1b, n->fc2t, n->fc2b};
+    for (float* f : fs) cudaFree(f);
+    for (auto& L : n->L) { cudaFree(L.w); cudaFree(L.scale); cudaFree(L.shift); }
+    __nv_bfloat16* bs[] = {n->A1, n->B1, n->B2, n->CAT, n->F};
+    for (auto* b : bs) cudaFree(b);
+    for (auto& e : n->ev) if (e) cudaEventDestroy(e);
+    delete n;
+    return DMF_OK;
+}
+
+int dmf_net_load_param(dmf_net* n, const char* name, const float* data_host, int64_t numel) {
+    DMF_REQUIRE(n && name && data_host && numel > 0, "net_load_param: bad argument");
+    n->params[name].assign(data_host, data_host + numel);
+    n->ready = false;
+    return DMF_OK;
+}
+
+int64_t dmf_net_flops_per_patch(const dmf_net* n) {
+    if (!n) return 0;
+    const int64_t p = n->p;
+    auto conv = [](int64_t cin, int64_t cout, int64_t k, int64_t h) { return 2 * cin * cout * k * k * h * h; };
+    return conv(4, C_MS1, 3, p) + conv(C_MS1, C_MS2, 3, p) + conv(1, C_PAN1, 3, 4 * p) + conv(C_PAN1, C_PAN2, 3, 2 * p) +
+           conv(C_PAN2, C_PAN3, 3, p) + conv(C_CAT, C_FUSE, 1, p / 2) + 2 * C_FUSE * C_HID + 2 * C_HID * n->C;
+}
+
+int dmf_net_finalize(dmf_net* n, void* stream) {
+    DMF_REQUIRE(n, "net_finalize: null");
+    (void)stream;
+    const int p = n->p, C = n->C;
+    // --- stems
+    {
+        auto* w = param(n, "ms1.0.weight", (size_t)C_MS1 * 4 * 9);
+        if (!w) return DMF_ERR_STATE;
+        std::vector<float> wt(36 * C_MS1), sc, sh;   // [tap][cin][cout]
+        for (int co = 0; co < C_MS1; ++co)
+            for (int ci = 0; ci < 4; ++ci)
+                for (int t = 0; t < 9; ++t) wt[(t * 4 + ci) * C_MS1 + co] = (*w)[(co * 4 + ci) * 9 + t];
+        DMF_TRY(fold_bn(n, "ms1", C_MS1, sc, sh));
+        DMF_TRY(to_device(&n->w_ms1, wt)); DMF_TRY(to_device(&n->sc_ms1, sc)); DMF_TRY(to_device(&n->sh_ms1, sh));
+    }
+    {
+        auto* w = param(n, "pan1.0.weight", (size_t)C_PAN1 * 9);
+        if (!w) return DMF_ERR_STATE;
+        std::vector<float> wt(C_PAN1 * 12, 0.f), sc, sh;
+        for (int co = 0; co < C_PAN1; ++co)
+            for (int t = 0; t < 9; ++t) wt[co * 12 + t] = (*w)[co * 9 + t];
+        DMF_TRY(fold_bn(n, "pan1", C_PAN1, sc, sh));
+        DMF_TRY(to_device(&n->w_pan1, wt)); DMF_TRY(to_device(&n->sc_pan1, sc)); DMF_TRY(to_device(&n->sh_pan1, sh));
+    }
+    // --- tensor-core layers
+    DMF_TRY(pack_conv(n, n->L[0], "ms2"));
+    DMF_TRY(pack_conv(n, n->L[1], "pan2"));
+    DMF_TRY(pack_conv(n, n->L[2], "pan3"));
+    DMF_TRY(pack_conv(n, n->L[3], "fuse"));
+    // --- head
+    {
+        auto *w1 = param(n, "fc1.weight", (size_t)C_HID * C_FUSE), *b1 = param(n, "fc1.bias", C_HID),
+             *w2 = param(n, "fc2.weight", (size_t)C * C_HID), *b2 = param(n, "fc2.bias", C);
+        if (!w1 || !b1 || !w2 || !b2) return DMF_ERR_STATE;
+        std::vector<float> t1((size_t)C_FUSE * C_HID), t2((size_t)C_HID * C);
+        for (int o = 0; o < C_HID; ++o)
+            for (int k = 0; k < C_FUSE; ++k) t1[(size_t)k * C_HID + o] = (*w1)[(size_t)o * C_FUSE + k];
+        for (int o = 0; o < C; ++o)
+            for (int k = 0; k < C_HID; ++k) t2[(size_t)k * C + o] = (*w2)[(size_t)o * C_HID + k];
+        DMF_TRY(to_device(&n->fc1t, t1)); DMF_TRY(to_device(&n->fc1b, *b1));
+        DMF_TRY(to_device(&n->fc2t, t2)); DMF_TRY(to_device(&n->fc2b, *b2));
+    }
+    // --- workspace + tensor maps (once)
+    if (!n->A1) {
+        const size_t NB = n->NB;
+        DMF_CUDA(cudaMalloc(&n->A1, NB * C_MS1 * p * p * 2));
+        DMF_CUDA(cudaMalloc(&n->B1, NB * C_PAN1 * 4 * p * p * 2));
+        DMF_CUDA(cudaMalloc(&n->B2, NB * C_PAN2 * p * p * 2));
+        DMF_CUDA(cudaMalloc(&n->CAT, NB * C_CAT * (p / 2) * (p / 2) * 2));
+        DMF_CUDA(cudaMalloc(&n->F, NB * C_FUSE * (p / 2) * (p / 2) * 2));
+        DMF_TRY(make_map(&n->L[0].map, n->L[0].g, n->A1, n->NB));
+        DMF_TRY(make_map(&n->L[1].map, n->L[1].g, n->B1, n->NB));
+        DMF_TRY(make_map(&n->L[2].map, n->L[2].g, n->B2, n->NB));
+        DMF_TRY(make_map(&n->L[3].map, n->L[3].g, n->CAT, n->NB));
+        for (auto& e : n->ev) DMF_CUDA(cudaEventCreate(&e));
+        DMF_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    }
+    DMF_CUDA(cudaDeviceSynchronize());
+    n->ready = true;
+    return DMF_OK;
+}
+
+int dmf_net_set_timing(dmf_net* n, int enabled) {
+    DMF_REQUIRE(n, "net_set_timing: null");
+    n->timing = enabled != 0;
+    memset(n->stage_ms, 0, sizeof(n->stage_ms));
+    return DMF_OK;
+}
+int dmf_net_get_timing(dmf_net* n, float out_ms[8]) {
+    DMF_REQUIRE(n && out_ms, "net_get_timing: null");
+    memcpy(out_ms, n->stage_ms, sizeof(n->stage_ms));
+    return DMF_OK;
+}
+
+#define DMF_NET_READY(n)                                                                             \
+    do {                                                                                             \
+        if (!(n) || !(n)->ready) { dmf::set_error("net: call dmf_net_finalize after loading all parameters"); return DMF_ERR_STATE; } \
+    } while (0)
+
+int dmf_net_forward_patches(dmf_net* n, const float* ms_dev, const float* pan_dev, int64_t N, float* logits_out_dev,
+                            void* stream) {
+    DMF_NET_READY(n);
+    DMF_REQUIRE(ms_dev && pan_dev && logits_out_dev && N >= 0, "net_forward_patches: bad argument");
+    const int p = n->p;
+    for (int64_t o = 0; o < N; o += n->NB) {
+        const int64_t nb = std::min<int64_t>(n->NB, N - o);
+        // the two stems read different tensors: run them with their own sources
+        PatchSrc sm{}; sm.patches = ms_dev + o * 4 * p * p;
+        PatchSrc sp{}; sp.patches = pan_dev + o * 16 * p * p;
+        cudaStream_t st = (cudaStream_t)stream;
+        DMF_TRY(launch_stems(n, sm, false, nb, n->A1, n->B1, 1, st));
+        DMF_TRY(launch_stems(n, sp, false, nb, n->A1, n->B1, 2, st));
+        DMF_TRY(run_layer(n, 0, n->L[0].map, n->CAT, nb, st));
+        DMF_TRY(run_layer(n, 1, n->L[1].map, n->B2, nb, st));
+        DMF_TRY(run_layer(n, 2, n->L[2].map, n->CAT, nb, st));
+        DMF_TRY(run_layer(n, 3, n->L[3].map, n->F, nb, st));
+        const int npx = (p / 2) * (p / 2);
+        const int grid = (int)std::min<int64_t>(nb, (int64_t)num_sms() * 4);
+        dmf_scene none{};
+        head_kernel<<<grid, 128, head_smem(n->C), st>>>(n->F, nb, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, none, nullptr,
+                                                        0, logits_out_dev + o * n->C, nullptr, nullptr, nullptr);
+        DMF_LAUNCHED();
+    }
+    return DMF_OK;
+}
+
+int dmf_net_forward_scene(dmf_net* n, const dmf_scene* s, const int64_t* flat_idx_dev, int64_t first, int64_t N,
+                          float* logits_out_dev, uint8_t* pred_out_dev, int64_t* cm_dev, uint8_t* pred_map_dev, void* stream) {
+    DMF_NET_READY(n);
+    DMF_REQUIRE(s && N >= 0, "net_forward_scene: bad argument");
+    DMF_REQUIRE(s->p == n->p, "net_forward_scene: scene patch size %d != net patch size %d", s->p, n->p);
+    DMF_REQUIRE(!cm_dev || s->label, "net_forward_scene: confusion matrix needs dmf_scene_set_labels");
+    DMF_REQUIRE(flat_idx_dev || (first >= 0 && first + N <= (int64_t)s->H * s->W), "net_forward_scene: pixel range outside the scene");
+    for (int64_t o = 0; o < N; o += n->NB) {
+        const int64_t nb = std::min<int64_t>(n->NB, N - o);
+        PatchSrc src{};
+        src.scene = *s;
+        src.idx = flat_idx_dev ? flat_idx_dev + o : nullptr;
+        src.first = first + o;
+        DMF_TRY(forward_chunk(n, src, true, nb, logits_out_dev ? logits_out_dev + o * n->C : nullptr,
+                              pred_out_dev ? pred_out_dev + o : nullptr, cm_dev, pred_map_dev, (cudaStream_t)stream));
+    }
+    return DMF_OK;
+}
+
+int dmf_infer_scene(dmf_net* n, const dmf_scene* s, int row0, int row1, uint8_t* pred_map_dev, int64_t* cm_dev, void* stream) {
+    DMF_REQUIRE(s && row0 >= 0 && row1 >= row0 && row1 <= s->H, "infer_scene: bad row band [%d,%d)", row0, row1);
+    return dmf_net_forward_scene(n, s, nullptr, (int64_t)row0 * s->W, (int64_t)(row1 - row0) * s->W, nullptr, nullptr, cm_dev,
+                                 pred_map_dev, stream);
+}
+
+int dmf_net_debug_layer(dmf_net* n, int layer, int impl, const void* in_dev, void* out_dev, int64_t N, void* stream) {
+    DMF_NET_READY(n);
+    DMF_REQUIRE(layer >= 0 && layer < 4 && in_dev && out_dev && N > 0, "net_debug_layer: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ConvLayer& L = n->L[layer];
+    const int och = layer == 0 || layer == 2 ? C_CAT / 8 : L.g.cout / 8;
+    const int oc0 = layer == 2 ? C_MS2 / 8 : 0;
+    if (impl == 1) {
+        const int So = L.g.pool ? L.g.S / 2 : L.g.S;
+        const int64_t total = N * So * So * L.g.cout;
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+        direct_conv_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in_dev, L.w, L.scale, L.shift, (__nv_bfloat16*)out_dev, N,
+                                                 L.g.S, L.g.cin, L.g.cout, L.g.taps, L.g.pool, och, oc0);
+        DMF_LAUNCHED();
+        return DMF_OK;
+    }
+    CUtensorMap map;
+    DMF_TRY(make_map(&map, L.g, in_dev, N));
+    return run_layer(n, layer, map, (__nv_bfloat16*)out_dev, N, st);
+}
+
+int dmf_net_debug_stem(dmf_net* n, int which, const float* patches_dev, void* out_dev, int64_t N, void* stream) {
+    DMF_NET_READY(n);
+    DMF_REQUIRE((which == 0 || which == 1) && patches_dev && out_dev && N > 0, "net_debug_stem: bad argument");
+    PatchSrc src{};
+    src.patches = patches_dev;
+    return launch_stems(n, src, false, N, (__nv_bfloat16*)out_dev, (__nv_bfloat16*)out_dev, which == 0 ? 1 : 2, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+"""Python face of the C-ABI: thin object wrappers (Scene, NetHandle) and tensor-level helpers.
+
+torch is used only for device memory, streams and (in solver/) torch.distributed.  Everything that
+computes goes through libdmf_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, F64, U8, U16, check, lib
+
+_NP2DT = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.float32): F32, np.dtype(np.float64): F64}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('dual-modal-fusion_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def np_dtype_code(a):
+    try:
+        return _NP2DT[np.dtype(a.dtype)]
+    except KeyError:
+        raise TypeError('raster dtype %s is not supported (uint8, uint16, float32, float64)' % a.dtype)
+
+
+def launch_count():
+    return int(lib.dmf_launch_count())
+
+
+def _as_dev(a, device):
+    """numpy / torch, host or device -> contiguous tensor on `device`."""
+    if isinstance(a, np.ndarray):
+        if a.dtype == np.uint16:   # torch has limited uint16 support: move the bytes
+            t = torch.from_numpy(np.ascontiguousarray(a).view(np.int16))
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+    else:
+        t = a.contiguous()
+    return t.to(device, non_blocking=True)
+
+
+class Scene:
+    """Normalised, reflect-padded MS/PAN rasters resident in HBM
+    (data_padding of function/function.py:99-117 for both rasters + the dataset's float32 cast)."""
+
+    def __init__(self, handle, H, W, p, device):
+        self._h, self.H, self.W, self.p, self.device = handle, H, W, p, device
+        self.Hp, self.Wp = H + p - 1, W + p - 1
+        self.H4p, self.W4p = 4 * H + 4 * p - 1, 4 * W + 4 * p - 1
+        self.has_labels = False
+        self.has_mspan = False
+
+    @classmethod
+    def from_raw(cls, ms, pan, p, device='cuda:0'):
+        """ms [H,W,4], pan [4H,4W]: numpy arrays (host, copied) or CUDA tensors."""
+        _require_cuda()
+        H, W = int(ms.shape[0]), int(ms.shape[1])
+        assert tuple(ms.shape) == (H, W, 4) and tuple(pan.shape) == (4 * H, 4 * W), 'MS must be [H,W,4], PAN [4H,4W]'
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            if isinstance(ms, np.ndarray):
+                ms_c, pan_c = np.ascontiguousarray(ms), np.ascontiguousarray(pan)
+                check(lib.dmf_scene_create_raw(C.byref(h), ms_c.ctypes.data_as(C.c_void_p), np_dtype_code(ms_c),
+                                               pan_c.ctypes.data_as(C.c_void_p), np_dtype_code(pan_c), H, W, p, 0, _stream()))
+                torch.cuda.current_stream().synchronize()   # host buffers may be pageable
+            else:
+                code = {torch.uint8: U8, torch.int16: U16, torch.uint16: U16, torch.float32: F32, torch.float64: F64}
+                ms_c, pan_c = ms.contiguous(), pan.contiguous()
+                check(lib.dmf_scene_create_raw(C.byref(h), _ptr(ms_c), code[ms_c.dtype], _ptr(pan_c), code[pan_c.dtype],
+                                               H, W, p, 1, _stream()))
+        return cls(h, H, W, p, device)
+
+    @classmethod
+    def from_padded(cls, ms_pad, pan_pad, p, device='cuda:0'):
+        """ms_pad / pan_pad exactly as data_padding() returns them (float64 or float32 ndarrays)."""
+        _require_cuda()
+        H, W = ms_pad.shape[0] - p + 1, ms_pad.shape[1] - p + 1
+        assert tuple(pan_pad.shape) == (4 * H + 4 * p - 1, 4 * W + 4 * p - 1), 'PAN padded shape mismatch'
+        assert ms_pad.dtype == pan_pad.dtype
+        h = C.c_void_p()
+        a, b = np.ascontiguousarray(ms_pad), np.ascontiguousarray(pan_pad)
+        with torch.cuda.device(device):
+            check(lib.dmf_scene_create_padded(C.byref(h), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                              np_dtype_code(a), H, W, p, 0, _stream()))
+            torch.cuda.current_stream().synchronize()
+        return cls(h, H, W, p, device)
+
+    def set_labels(self, label):
+        lab = np.ascontiguousarray(label, dtype=np.uint8)
+        assert lab.shape == (self.H, self.W)
+        with torch.cuda.device(self.device):
+            check(lib.dmf_scene_set_labels(self._h, lab.ctypes.data_as(C.c_void_p), 0, _stream()))
+            torch.cuda.current_stream().synchronize()
+        self.has_labels = True
+
+    def set_mspan(self, mspan_pad):
+        a = np.ascontiguousarray(mspan_pad)
+        assert a.shape == (self.H4p, self.W4p)
+        with torch.cuda.device(self.device):
+            check(lib.dmf_scene_set_mspan(self._h, a.ctypes.data_as(C.c_void_p), np_dtype_code(a), 0, _stream()))
+            torch.cuda.current_stream().synchronize()
+        self.has_mspan = True
+
+    def export(self, which):
+        """0 -> MS [Hp,Wp,4], 1 -> PAN [H4p,W4p], 2 -> MSPAN; float32 CUDA tensors."""
+        shape = (self.Hp, self.Wp, 4) if which == 0 else (self.H4p, self.W4p)
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.dmf_scene_export(self._h, which, _ptr(out), _stream()))
+        return out
+
+    def gather(self, flat_idx, tri=False, want_target=None):
+        """K1: flat_idx int64 (tensor / ndarray / list) -> (ms [N,4,p,p], pan [N,1,4p,4p][, mspan], target [N])."""
+        idx = torch.as_tensor(flat_idx, dtype=torch.int64).to(self.device)
+        N, p = idx.numel(), self.p
+        want_target = self.has_labels if want_target is None else want_target
+        ms = torch.empty((N, 4, p, p), dtype=torch.float32, device=self.device)
+        pan = torch.empty((N, 1, 4 * p, 4 * p), dtype=torch.float32, device=self.device)
+        mspan = torch.empty_like(pan) if tri else None
+        tgt = torch.empty((N,), dtype=torch.float32, device=self.device) if want_target else None
+        with torch.cuda.device(self.device):
+            check(lib.dmf_gather(self._h, _ptr(idx), N, _ptr(ms), _ptr(pan), _ptr(mspan), _ptr(tgt), _stream()))
+        return (ms, pan, mspan, tgt) if tri else (ms, pan, tgt)
+
+    def close(self):
+        if self._h:
+            lib.dmf_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def normalize_pad(array, P, out_dtype=np.float64, device='cuda:0'):
+    """data_padding()'s arithmetic for one raster on the GPU; returns a CUDA tensor."""
+    _require_cuda()
+    a = np.ascontiguousarray(array)
+    H, W = a.shape[0], a.shape[1]
+    bands = a.shape[2] if a.ndim == 3 else 1
+    with torch.cuda.device(device):
+        src = _as_dev(a, device)
+        shape = (H + P - 1, W + P - 1) + ((bands,) if a.ndim == 3 else ())
+        out = torch.empty(shape, dtype=torch.float64 if out_dtype == np.float64 else torch.float32, device=device)
+        check(lib.dmf_normalize_pad(_ptr(src), np_dtype_code(a), H, W, bands, P, _ptr(out),
+                                    F64 if out_dtype == np.float64 else F32, _stream()))
+    return out
+
+
+def ihs_tran(ms, pan, offsets, device='cuda:0'):
+    """K2: ms f64 [H,W,4], pan f64 [4H,4W], offsets int8 [4,H,W,2] -> f64 CUDA tensor [4H,4W]."""
+    _require_cuda()
+    H, W = ms.shape[0], ms.shape[1]
+    with torch.cuda.device(device):
+        a = _as_dev(np.asarray(ms, dtype=np.float64) if isinstance(ms, np.ndarray) else ms.double(), device)
+        b = _as_dev(np.asarray(pan, dtype=np.float64) if isinstance(pan, np.ndarray) else pan.double(), device)
+        o = _as_dev(np.asarray(offsets, dtype=np.int8) if isinstance(offsets, np.ndarray) else offsets, device)
+        out = torch.empty((4 * H, 4 * W), dtype=torch.float64, device=device)
+        check(lib.dmf_ihs_tran(_ptr(a), _ptr(b), _ptr(o), _ptr(out), H, W, _stream()))
+    return out
+
+
+def pan2ms(pan, device='cuda:0'):
+    """K2: pan [4H,4W] (u8/u16/f32/f64 ndarray) -> f64 CUDA tensor [H,W,4]."""
+    _require_cuda()
+    a = np.ascontiguousarray(pan)
+    H4, W4 = a.shape
+    with torch.cuda.device(device):
+        src = _as_dev(a, device)
+        out = torch.empty((H4 // 4, W4 // 4, 4), dtype=torch.float64, device=device)
+        check(lib.dmf_pan2ms(_ptr(src), np_dtype_code(a), H4, W4, _ptr(out), _stream()))
+    return out
+
+
+def argmax_confusion(logits, target, C_, cm=None, want_pred=True):
+    """K4: logits f32 [N,C] CUDA, target f32 or u8 [N] CUDA -> (pred int64 [N] | None, cm int64 [C,C])."""
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and logits.shape[1] == C_
+    logits = logits.contiguous()
+    N = logits.shape[0]
+    if cm is None:
+        cm = torch.zeros((C_, C_), dtype=torch.int64, device=logits.device)
+    pred = torch.empty((N,), dtype=torch.int64, device=logits.device) if want_pred else None
+    tcode = F32
+    if target is not None:
+        target = target.contiguous()
+        tcode = {torch.float32: F32, torch.uint8: U8}[target.dtype]
+    with torch.cuda.device(logits.device):
+        check(lib.dmf_argmax_confusion(_ptr(logits), _ptr(target), tcode, N, C_, _ptr(pred),
+                                       _ptr(cm) if target is not None else C.c_void_p(0), _stream()))
+    return pred, cm
+
+
+def scatter_labels(label_map, x, y, pred):
+    """K5a: label_map u8 [H,W] CUDA; x, y, pred int64 [N] (moved to the device if needed)."""
+    dev = label_map.device
+    x, y, pred = (torch.as_tensor(v, dtype=torch.int64).to(dev).contiguous() for v in (x, y, pred))
+    with torch.cuda.device(dev):
+        check(lib.dmf_scatter_labels(_ptr(x), _ptr(y), _ptr(pred), x.numel(), _ptr(label_map), label_map.shape[1], _stream()))
+    return label_map
+
+
+def paint_labels(label_map, colors):
+    """K5b: label_map u8 [H,W] CUDA, colors [[r,g,b],...] -> u8 [H,W,3] CUDA."""
+    pal = np.ascontiguousarray(np.asarray(colors, dtype=np.uint8))
+    lm = label_map.contiguous()
+    out = torch.empty(tuple(lm.shape) + (3,), dtype=torch.uint8, device=lm.device)
+    with torch.cuda.device(lm.device):
+        check(lib.dmf_paint_labels(_ptr(lm), lm.numel(), pal.ctypes.data_as(C.c_void_p), pal.shape[0], _ptr(out), _stream()))
+    return out
+
+
+class NetHandle:
+    """GMFNet weights packed for the sm_100a kernels + activation workspace for `max_batch` patches."""
+
+    def __init__(self, p, num_classes, max_batch=4096, device='cuda:0'):
+        _require_cuda()
+        self.p, self.C, self.max_batch, self.device = p, num_classes, max_batch, device
+        self._h = C.c_void_p()
+        check(lib.dmf_net_create(C.byref(self._h), p, num_classes, max_batch))
+        self.flops_per_patch = int(lib.dmf_net_flops_per_patch(self._h))
+
+    def load_state_dict(self, sd):
+        with torch.cuda.device(self.device):
+            for k, v in sd.items():
+                if not torch.is_floating_point(v):
+                    continue                      # num_batches_tracked
+                a = np.ascontiguousarray(v.detach().to('cpu', torch.float32).numpy())
+                check(lib.dmf_net_load_param(self._h, k.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+            check(lib.dmf_net_finalize(self._h, _stream()))
+
+    def forward_patches(self, ms, pan):
+        assert ms.is_cuda and pan.is_cuda and ms.dtype == torch.float32 and pan.dtype == torch.float32
+        ms, pan = ms.contiguous(), pan.contiguous()
+        N = ms.shape[0]
+        assert tuple(ms.shape[1:]) == (4, self.p, self.p) and tuple(pan.shape) == (N, 1, 4 * self.p, 4 * self.p)
+        out = torch.empty((N, self.C), dtype=torch.float32, device=ms.device)
+        with torch.cuda.device(ms.device):
+            check(lib.dmf_net_forward_patches(self._h, _ptr(ms), _ptr(pan), N, _ptr(out), _stream()))
+        return out
+
+    def forward_scene(self, scene, flat_idx=None, first=0, count=None, want_logits=True, want_pred=False, cm=None,
+                      pred_map=None):
+        idx = None
+        if flat_idx is not None:
+            idx = torch.as_tensor(flat_idx, dtype=torch.int64).to(self.device).contiguous()
+            count = idx.numel()
+        logits = torch.empty((count, self.C), dtype=torch.float32, device=self.device) if want_logits else None
+        pred = torch.empty((count,), dtype=torch.uint8, device=self.device) if want_pred else None
+        with torch.cuda.device(self.device):
+            check(lib.dmf_net_forward_scene(self._h, scene._h, _ptr(idx), first, count, _ptr(logits), _ptr(pred),
+                                            _ptr(cm), _ptr(pred_map), _stream()))
+        return logits, pred
+
+    def infer_scene(self, scene, row0=0, row1=None, pred_map=None, cm=None):
+        """Fused whole-band inference: returns (pred_map u8 [H,W], cm int64 [C,C])."""
+        row1 = scene.H if row1 is None else row1
+        if pred_map is None:
+            pred_map = torch.zeros((scene.H, scene.W), dtype=torch.uint8, device=self.device)
+        if cm is None and scene.has_labels:
+            cm = torch.zeros((self.C, self.C), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.dmf_infer_scene(self._h, scene._h, row0, row1, _ptr(pred_map), _ptr(cm), _stream()))
+        return pred_map, cm
+
+    def set_timing(self, on):
+        check(lib.dmf_net_set_timing(self._h, 1 if on else 0))
+
+    def get_timing(self):
+        buf = (C.c_float * 8)()
+        check(lib.dmf_net_get_timing(self._h, buf))
+        names = ['stem_ms', 'conv_ms2', 'stem_pan', 'conv_pan2', 'conv_pan3', 'conv_fuse', 'head', 'total']
+        return dict(zip(names, [float(v) for v in buf]))
+
+    def debug_layer(self, layer, impl, x, out_shape):
+        out = torch.zeros(out_shape, dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.dmf_net_debug_layer(self._h, layer, impl, _ptr(x.contiguous()), _ptr(out), x.shape[0], _stream()))
+        return out
+
+    def debug_stem(self, which, patches, out_shape):
+        out = torch.zeros(out_shape, dtype=torch.bfloat16, device=patches.device)
+        with torch.cuda.device(patches.device):
+            check(lib.dmf_net_debug_stem(self._h, which, _ptr(patches.contiguous()), _ptr(out), patches.shape[0], _stream()))
+        return out
+
+    def close(self):
+        if self._h:
+            lib.dmf_net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
