@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — scene pixels classified / second on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3]
+
+One "step" = one whole-scene classification pass (every pixel: co-registered MS/PAN window ->
+GMFNet -> argmax -> confusion matrix + label map) over the synthetic scene of the workload:
+  N = 1 : C2  Xi'an-scale   MS 4x1000x1000 / PAN 4000x4000, 12 classes (+background = 13)
+  N > 1 : C3  Hohhot-scale  MS 4x2001x2101 / PAN 8004x8404, 11 classes, row-band sharded,
+          one int64 C*C all-reduce per step (strong scaling: the scene is fixed).
+`value` is timed with CUDA events with the scene resident in HBM; `e2e` goes through the public API
+from pinned HOST rasters (H2D + normalise/pad + inference + D2H of label map and matrix + OA/AA/Kappa).
+`--impl reference` times the reference's CPU path (oracle/ref_pipeline.py port) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, 'dual-modal-fusion_b200'))
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    'c1': dict(name='C1 synthetic MS 4x128x128 / PAN 512x512, p=16, 7 classes', H=128, W=128, classes=7),
+    'c2': dict(name="C2 Xi'an-scale synthetic MS 4x1000x1000 / PAN 4000x4000, p=16, 12 classes", H=1000, W=1000, classes=12),
+    'c3': dict(name='C3 Hohhot-scale synthetic MS 4x2001x2101 / PAN 8004x8404, p=16, 11 classes', H=2001, W=2101, classes=11),
+}
+P = 16
+METRIC, UNIT = 'scene pixels classified/sec', 'px/s'
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json'))), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled every 100 ms during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.index = index
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40,
+                     'hw_power_brake': 0x80}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.reasons.update(k for k, bit in names.items() if r & bit)
+                time.sleep(0.1)
+        except Exception as e:               # clocks are evidence, not a dependency
+            self.reasons.add('unavailable: %s' % type(e).__name__)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=2)
+
+    def summary(self):
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+def cpu_reference_run(wl, budget_s, steps=1, warmup=0):
+    """The reference's CPU path on the host cores; returns (px/s, cores, description, per-step ms)."""
+    from oracle import dmf_oracle as orc
+    from oracle.ref_pipeline import RefPipeline
+    ms, pan, label = orc.synthetic_scene(wl['H'], wl['W'], wl['classes'], seed=0, label_seed=1)
+    pipe = RefPipeline(ms, pan, label, P, wl['classes'] + 1)
+    order = np.arange(wl['H'] * wl['W'])
+    per_step_px = 0
+    times = []
+    cursor = 0
+    for s in range(warmup + steps):
+        idx = order[cursor:cursor + 200000]
+        _, _, done, secs = pipe.classify(idx, batch_size=300, budget_s=budget_s if s >= warmup else min(budget_s, 3.0))
+        cursor = (cursor + done) % (order.size - 200000 if order.size > 200000 else 1)
+        if s >= warmup:
+            per_step_px += done
+            times.append(secs)
+    total = float(sum(times))
+    desc = ('%d px (row-major prefix, DataLoader bs=300 num_workers=0, per-item __getitem__, fp32 Net on CPU, per-sample '
+            'confusion loop) in %.1f s; scene prep %.1f s not counted' % (per_step_px, total, pipe.prep_s))
+    return per_step_px / total, torch.get_num_threads(), desc, 1e3 * total / max(1, steps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default=None, choices=list(WORKLOADS))
+    ap.add_argument('--max-batch', type=int, default=4096)
+    ap.add_argument('--cpu-budget-s', type=float, default=15.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    wl_key = args.workload or ('c2' if max(world, args.gpus) == 1 else 'c3')
+    wl = WORKLOADS[wl_key]
+    config = {'workload': wl['name'], 'patch_size': P, 'sharding': 'row bands, scene replicated per rank',
+              'l2': 'explicit 256 MiB L2 flush between timed steps; per-step activations (0.7 GB) exceed L2 too'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        per_step = max(2.0, min(args.cpu_budget_s, 120.0 / max(1, args.steps + args.warmup)))
+        v, cores, desc, ms_step = cpu_reference_run(wl, per_step, steps=args.steps, warmup=min(args.warmup, 1))
+        print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+                          'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                          'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+                          'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch.distributed as dist
+    import dmf
+    from oracle import dmf_oracle as orc          # synthetic scene generator + cpu_baseline only
+    from model.gmfnet import Net
+    from indicators.kappa import aa_oa
+    from solver.mainsolver import row_band
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = 'cuda:%d' % local_rank
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    C = wl['classes'] + 1
+    H, W = wl['H'], wl['W']
+    ms, pan, label = orc.synthetic_scene(H, W, wl['classes'], seed=0, label_seed=1)
+    torch.manual_seed(3407)
+    net = Net({'Categories_Number': C, 'patch_size': P, 'schedule': {'activate': 'Relu'}, 'b200': {'max_batch': args.max_batch}})
+    net = net.to(dev).eval()
+    handle = net.native()
+    r0, r1 = row_band(H, rank, world)
+    npix_total = H * W
+
+    # ---- resident scene for the device-timed arm
+    scene = dmf.Scene.from_raw(ms, pan, P, dev)
+    scene.set_labels(label)
+    pred_map = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        cm.zero_()
+        handle.infer_scene(scene, r0, r1, pred_map=pred_map, cm=cm)
+        if world > 1:
+            dist.all_reduce(cm)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = dmf.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        for a, b in ev:
+            flush.fill_(1)                      # L2 flush, outside the event pair
+            a.record()
+            step()
+            b.record()
+        barrier()
+    launches = dmf.launch_count() - launches0
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    value = npix_total * args.steps / (total_ms / 1e3)
+    cm_host = cm.cpu().numpy().astype(np.float64)
+    assert cm_host.sum() == npix_total, 'confusion matrix does not cover the scene'
+
+    # ---- e2e: public API from pinned host rasters, copies inside the timed region
+    ms_pin = torch.from_numpy(ms.view(np.int16)).pin_memory()
+    pan_pin = torch.from_numpy(pan.view(np.int16)).pin_memory()
+    pm_host = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+    cm_pin = torch.empty((C, C), dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        sc = dmf.Scene.from_raw(ms_pin, pan_pin, P, dev)
+        sc.set_labels(label)
+        pm, m = handle.infer_scene(sc, r0, r1)
+        if world > 1:
+            dist.all_reduce(m)
+        pm_host[r0:r1].copy_(pm[r0:r1], non_blocking=True)
+        cm_pin.copy_(m, non_blocking=True)
+        torch.cuda.synchronize()
+        sc.close()
+        with open(os.devnull, 'w') as null, _redirect(null):
+            return aa_oa(cm_pin.numpy().astype(np.float64))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        result = e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = npix_total * args.steps / float(e2e_s)
+    h2d = ms.nbytes + pan.nbytes + label.nbytes
+    d2h = (r1 - r0) * W + C * C * 8
+
+    # ---- roofline of the dominant kernel: per-stage device events inside the library (one extra pass)
+    handle.set_timing(True)
+    handle.infer_scene(scene, r0, r1)
+    stage = handle.get_timing()
+    handle.set_timing(False)
+    pk, pk_src = peaks()
+    n_local = (r1 - r0) * W
+    n_chunks = -(-n_local // args.max_batch)
+    conv = lambda cin, cout, k, h: 2 * cin * cout * k * k * h * h
+    kernels = {   # kernel instance -> (stage keys, algorithmic FLOPs per pixel, launches per chunk)
+        'conv_tc_kernel<64,128,9,pool> (ms2 + pan3)': (['conv_ms2', 'conv_pan3'], 2 * conv(64, 128, 3, P), 2),
+        'conv_tc_kernel<32,64,9,pool> (pan2)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
+        'conv_tc_kernel<256,128,1> (fuse)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
+    }
+    name, (keys, fl_px, per_chunk) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
+    k_ms = sum(stage[k] for k in keys)
+    achieved = fl_px * n_local / (k_ms / 1e3) / 1e12
+    roofline = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+                'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
+                'avg_launch_ms': k_ms / (n_chunks * per_chunk), 'launches': n_chunks * per_chunk,
+                'flops_per_launch': fl_px * n_local / (n_chunks * per_chunk),
+                'stage_ms': {k: round(v, 3) for k, v in stage.items()},
+                'whole_net_tflops': handle.flops_per_patch * n_local / (stage['total'] / 1e3) / 1e12}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, desc, _ = cpu_reference_run(wl, args.cpu_budget_s)
+        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc}
+
+    if rank == 0:
+        config.update({'global_pixels': npix_total, 'chunk_pixels': args.max_batch, 'row_band_rank0': [r0, r1],
+                       'flops_per_pixel': handle.flops_per_patch, 'OA_AA_Kappa': [float(result[1]), float(result[0]), float(result[2])]})
+        print(json.dumps({'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                          'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                          'dtype': 'bf16', 'data': 'synthetic', 'config': config, 'clocks': clk.summary(),
+                          'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+                          'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _redirect:
+    def __init__(self, f):
+        self.f = f
+
+    def __enter__(self):
+        self.old = sys.stdout
+        sys.stdout = self.f
+
+    def __exit__(self, *a):
+        sys.stdout = self.old
+
+
+if __name__ == '__main__':
+    main()

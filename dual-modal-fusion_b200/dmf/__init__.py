@@ -74,11 +74,14 @@ class Scene:
                 check(lib.dmf_scene_create_raw(C.byref(h), ms_c.ctypes.data_as(C.c_void_p), np_dtype_code(ms_c),
                                                pan_c.ctypes.data_as(C.c_void_p), np_dtype_code(pan_c), H, W, p, 0, _stream()))
                 torch.cuda.current_stream().synchronize()   # host buffers may be pageable
-            else:
+            else:                                  # torch tensors: CUDA, or (pinned) host memory
                 code = {torch.uint8: U8, torch.int16: U16, torch.uint16: U16, torch.float32: F32, torch.float64: F64}
                 ms_c, pan_c = ms.contiguous(), pan.contiguous()
+                assert ms_c.is_cuda == pan_c.is_cuda
                 check(lib.dmf_scene_create_raw(C.byref(h), _ptr(ms_c), code[ms_c.dtype], _ptr(pan_c), code[pan_c.dtype],
-                                               H, W, p, 1, _stream()))
+                                               H, W, p, 1 if ms_c.is_cuda else 0, _stream()))
+                if not ms_c.is_cuda and not (ms_c.is_pinned() and pan_c.is_pinned()):
+                    torch.cuda.current_stream().synchronize()
         return cls(h, H, W, p, device)
 
     @classmethod

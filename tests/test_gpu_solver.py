@@ -1,0 +1,89 @@
+"""GPU test of the drop-in boundary: the Solver / dataset / model objects with the reference's names,
+driven the way test.py drives them, must reproduce what the reference's own Solver produced on the C1
+synthetic scene (tests/golden/solver_c1.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dmf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def c1_cfg(tmp, ms, pan, label, train=0, color=1):
+    ncls = 7
+    colors = [[(37 * i) % 256, (91 * i) % 256, (53 * i) % 256] for i in range(ncls + 1)]
+    return {'task': 'classification', 'time': 1, 'index': 0, 'epoch': 1, 'device': 'cuda:0', 'gpu_mode': False,
+            'data_new': 0, 'data_address': str(tmp) + '/', 'use_h5': False, 'nohup': 1, 'model_name': 'gmfnet',
+            'batchsize': 256, 'test_batchsize': 300, 'color_batchsize': 300, 'train_rate': 0.02, 'verify_rate': 0.02,
+            'patch_size': 16, 'Categories_Number': ncls + 1, 'data_city': 'c1',
+            'DATA_DICT': {'c1': {'size': [128, 128, 4], 'color': colors}},
+            'schedule': {'loss': 'Criterion', 'optimizer': 'ADAM', 'if_scheduler': 0, 'scheduler': 'ExponentialLR',
+                         'activate': 'Relu', 'lr': 1e-3, 'base_lr': 5e-4},
+            'train': {'index': train, 'pretrained': 0, 'save_best': True}, 'test': {'index': 1, 'save_matrix': 1},
+            'color': {'index': color, 'supervised': 1, 'unsupervised': 1},
+            'RESULT_output': str(tmp) + '/out/', 'RESULT_excel': str(tmp) + '/result.xlsx',
+            'rasters': {'ms': ms, 'pan': pan, 'label': label}}
+
+
+def test_solver_reproduces_the_reference_run(tmp_path, golden):
+    from solver.mainsolver import Solver
+    g = golden('solver_c1')
+    ms, pan, label = orc.synthetic_scene(128, 128, 7, seed=0, label_seed=1)
+    torch.manual_seed(3407)                                     # test.py:8
+    s = Solver(c1_cfg(tmp_path, ms, pan, label))
+    assert len(s.matrix_[1]) + len(s.matrix_[0]) == 128 * 128
+    s.dataloader()
+    assert np.array_equal(s.train_loader.indices, g['train_idx'])
+    assert np.array_equal(s.test_loader.indices, g['test_idx'])
+    assert np.array_equal(s.valid_loader.indices, g['valid_idx'])
+    d1, d2, tgt, x, y = next(iter(s.train_loader))
+    assert np.array_equal(x.numpy(), g['train_batch0_x']) and np.array_equal(y.numpy(), g['train_batch0_y'])
+    assert d1.is_cuda and d1.shape == (256, 4, 16, 16) and d2.shape == (256, 1, 64, 64) and tgt.dtype == torch.float32
+    MS, PAN = orc.data_padding(ms, 16), orc.data_padding(pan, 16)
+    a, b = orc.gather_dual(MS, PAN, x.numpy(), y.numpy(), 16)
+    assert np.array_equal(d1.cpu().numpy(), a) and np.array_equal(d2.cpu().numpy(), b)
+    assert np.array_equal(tgt.cpu().numpy(), label[x.numpy(), y.numpy()].astype(np.float32))
+    # dataset item contract of train/dataset.py:185
+    item = s.dataset[777]
+    assert item[0].shape == (4, 16, 16) and item[1].shape == (1, 64, 64) and item[2].dim() == 0
+    assert (item[3], item[4]) == (777 // 128, 777 % 128) and not item[0].is_cuda
+    # lazily materialised reference attributes
+    assert np.array_equal(s.MS, MS) and s.PAN.shape == PAN.shape
+
+    s.init_model()                                              # same RNG position as the reference run
+    assert list(s.model.state_dict().keys()) == list(g['state_keys'])
+    pred_map, M = s.classify_scene()
+    pm = pred_map.cpu().numpy()
+    assert (pm == g['label_map']).mean() >= 0.999
+    assert np.array_equal(M, orc.confusion(pm.reshape(-1), label.reshape(-1), 8))
+    if np.array_equal(pm, g['label_map']):
+        assert np.array_equal(M, g['M'])
+    s.test()                                                    # full test loader through K4
+    assert s.test_matrix.sum() == len(g['test_idx'])
+    want = orc.confusion(pm.reshape(-1)[g['test_idx']], label.reshape(-1)[g['test_idx']], 8)
+    assert np.array_equal(s.test_matrix, want)
+    s.color()
+    assert (tmp_path / 'out' / '0_pic_1.png').exists() and (tmp_path / 'out' / '0_pic_2.png').exists()
+    assert np.array_equal(s.label_np2, pm.astype(np.float64))
+    assert np.array_equal(s.label_np1, np.where(label != 0, pm, 0).astype(np.float64))
+
+
+def test_train_epoch_then_eval_uses_updated_weights(tmp_path):
+    from solver.mainsolver import Solver
+    ms, pan, label = orc.synthetic_scene(64, 64, 7, seed=4, label_seed=5, blocky=True)
+    cfg = c1_cfg(tmp_path, ms, pan, label, train=1, color=0)
+    cfg['DATA_DICT']['c1']['size'] = [64, 64, 4]
+    cfg['train_rate'], cfg['verify_rate'] = 0.2, 0.05
+    torch.manual_seed(0)
+    s = Solver(cfg)
+    s.run()
+    assert s.train_time > 0 and (tmp_path / 'out' / '0_weights.pth').exists() and (tmp_path / 'out' / '0_curweights.pth').exists()
+    assert s.test_matrix.sum() == len(s.test_loader.indices)
+    # native inference must track the trained parameters: compare with the autograd graph in eval mode
+    net = s.cur_model.eval()
+    d1, d2, _, _, _ = next(iter(s.test_loader))
+    with torch.no_grad():
+        native = net(d1, d2)
+        graph = net._graph(d1, d2)
+    assert torch.allclose(native, graph, rtol=2e-2, atol=5e-3), float((native - graph).abs().max())
