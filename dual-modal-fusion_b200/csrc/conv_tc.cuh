@@ -14,27 +14,30 @@
 //
 // GEMM view per tile: D[128 pixels, C_out] += A_tap[128 pixels, 16 ch] * W_tap[C_out, 16 ch]^T,
 // M = 128, N = C_out, K = 16 per tcgen05.mma, 9*C_in/16 MMAs per tile, fp32 accumulate in TMEM.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (tcgen05.ld -> BN affine -> ReLU -> bf16 -> 2x2 max-pool via warp shuffles
-// -> 16-byte stores in the next layer's layout).  TMEM holds two accumulators so the epilogue of tile
-// i overlaps the MMAs of tile i+1; the A halo ring has 2..6 stages.
+// Warp roles (64 + 128*G threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), then G
+// epilogue groups of 4 warps (tcgen05.ld -> BN affine -> ReLU -> bf16 -> 2x2 max-pool via warp
+// shuffles -> 16-byte stores in the next layer's layout).  TMEM holds G accumulators; group g drains
+// the tiles with (tile % G == g), so G epilogues overlap the MMAs of the following tiles.  (The ncu
+// profile of the first version, one group, showed the tensor pipe 52 % active: a single epilogue warp
+// per scheduler is latency-bound at ~1400 dependent instructions per tile.)  The A halo ring has
+// 2..6 stages.
 #pragma once
 #include "common.cuh"
 
 namespace dmf {
 namespace tc {
 
-constexpr int kThreads = 192;
 constexpr int kPitch = 10;                 // halo row pitch in pixels (8 + 2)
 constexpr uint64_t kSpinLimit = 4000000000ull;   // ~2 s of SM clocks, then trap instead of hanging the GPU
 
 struct ConvParams {
-    int S;            // input map is S x S
-    int NP;           // patches per tile
+    // every geometric quantity is a power of two (p in {8,16,32}); *_l2 are the exponents
+    int S, S_l2;      // input map is S x S
+    int NP, NP_l2;    // patches per tile
     int TH;           // output rows per tile (3x3 path)
-    int tiles_x, tiles_y;
-    int PX;           // 1x1 path: pixels of one patch per tile
-    int tiles_per_group;
+    int tiles_x_l2;
+    int PX, PX_l2;    // 1x1 path: pixels of one patch per tile
+    int tpg_l2;       // tiles per patch group
     int n_tiles;
     int N;            // patches
     int a_plane;      // bytes of one channel-chunk plane inside an A stage
@@ -43,6 +46,7 @@ struct ConvParams {
     int sbo_a;        // bytes between 8-pixel row groups of A
     int out_chunks;   // channel chunks of the output tensor
     int out_chunk0;   // first chunk this layer writes
+    int dbg;          // diagnostics only: bit0 = skip the A-tile TMA loads, bit1 = skip the epilogue math/stores
     const __nv_bfloat16* w;     // packed [tap][C_in/8][C_out][8]
     const float* scale;         // folded BatchNorm scale  [C_out]
     const float* shift;         // folded BatchNorm shift  [C_out]
@@ -113,6 +117,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -139,14 +153,21 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int C_IN, int C_OUT, int TAPS, bool POOL>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams P) {
+template <int C_IN, int C_OUT, int TAPS, bool POOL, int G, int NP>
+__global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams P) {
+    constexpr int kThreads = 64 + 128 * G;
     constexpr int KCH = C_IN / 8;
     constexpr int KSTEPS = C_IN / 16;
     constexpr uint32_t WBYTES = (uint32_t)TAPS * C_IN * C_OUT * 2;
-    constexpr uint32_t TMEM_COLS = 2 * C_OUT;          // two accumulators; power of two >= 32
-    static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
+    constexpr uint32_t TMEM_USED = G * C_OUT;          // G accumulators ...
+    constexpr uint32_t TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    static_assert(G >= 1 && G <= 4 && TMEM_USED <= 512, "epilogue groups / TMEM columns");   // ... in a power-of-two allocation
     static_assert(C_IN % 16 == 0 && C_OUT % 32 == 0 && C_OUT <= 256, "channel counts");
+    // A-tile geometry is compile-time so that every UMMA descriptor is "base + immediate"
+    constexpr int TH = TAPS == 9 ? 16 / NP : 0;
+    constexpr uint32_t A_PLANE = TAPS == 9 ? (uint32_t)(TH + 2) * NP * kPitch * 16 : 128u * 16u;
+    constexpr uint32_t SBO_A = TAPS == 9 ? (uint32_t)kPitch * 16 : 128u;
+    constexpr uint32_t A_STAGE = KCH * A_PLANE;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
@@ -154,8 +175,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     float* scale_s = reinterpret_cast<float*>(a_s + (size_t)P.n_stage * P.a_stage);
     float* shift_s = scale_s + C_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
-    // bars: [0,8) full, [8,16) empty, 16 weights, 17..18 tmem_full, 19..20 tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    // bars: [0,8) full, [8,16) empty, 16 weights, 17..20 tmem_full, 21..24 tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -163,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
     const uint32_t w_bar = bar0 + 8u * 16;
     auto tfull_bar = [&](int a) { return bar0 + 8u * (17 + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (19 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (21 + a); };
 
     for (int i = threadIdx.x; i < C_OUT; i += kThreads) {
         scale_s[i] = P.scale[i];
@@ -172,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < G; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -187,125 +208,146 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
     if (warp == 0) {
-        // ------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // ------------------------------------------------ TMA producer (whole warp converged, one lane issues)
+        const bool leader = elect_one();
+        if (leader) {
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
             mbar_expect_tx(w_bar, WBYTES);
             constexpr uint32_t CH = 16384;
             for (uint32_t off = 0; off < WBYTES; off += CH)
                 bulk_load(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(P.w) + off, min(CH, WBYTES - off), w_bar);
-            for (int i = 0; i < n_local; ++i) {
-                const int tile = blockIdx.x + i * gridDim.x;
-                const int st = i % P.n_stage;
-                mbar_wait(empty_bar(st), ((i / P.n_stage) & 1) ^ 1);
-                mbar_expect_tx(full_bar(st), P.a_stage);
-                const int grp = tile / P.tiles_per_group, t = tile - grp * P.tiles_per_group;
-                const uint32_t dst = smem_u32(a_s + (size_t)st * P.a_stage);
-                if (TAPS == 9) {
-                    const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
-                    tma_load_4d(dst, &in_map, full_bar(st), (tx * 8 - 1) * 8, grp * P.NP, ty * P.TH - 1, 0);
-                } else {
-                    tma_load_4d(dst, &in_map, full_bar(st), 0, t * P.PX, grp * P.NP, 0);
-                }
-            }
         }
         __syncwarp();
+        int st = 0;
+        uint32_t ph = 1;                          // parity to wait on for "stage free"; flips when the ring wraps
+        for (int i = 0; i < n_local; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            mbar_wait(empty_bar(st), ph);
+            if (leader) {
+                if (P.dbg & 1) {
+                    mbar_arrive(full_bar(st));
+                } else {
+                    mbar_expect_tx(full_bar(st), A_STAGE);
+                    const int grp = tile >> P.tpg_l2, t = tile & ((1 << P.tpg_l2) - 1);
+                    const uint32_t dst = smem_u32(a_s) + (uint32_t)st * A_STAGE;
+                    if (TAPS == 9) {
+                        const int ty = t >> P.tiles_x_l2, tx = t & ((1 << P.tiles_x_l2) - 1);
+                        tma_load_4d(dst, &in_map, full_bar(st), (tx * 8 - 1) * 8, grp * NP, ty * TH - 1, 0);
+                    } else {
+                        // dims: (8 ch x 32 px merged, 32-px block, patch, chunk)
+                        tma_load_4d(dst, &in_map, full_bar(st), 0, (t << P.PX_l2) >> 5, grp << P.NP_l2, 0);
+                    }
+                }
+            }
+            __syncwarp();
+            if (++st == P.n_stage) { st = 0; ph ^= 1; }
+        }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, C_OUT);
-            mbar_wait(w_bar, 0);
-            const uint32_t w_addr = smem_u32(w_s);
-            for (int i = 0; i < n_local; ++i) {
-                const int st = i % P.n_stage, acc = i & 1;
-                mbar_wait(tempty_bar(acc), ((i >> 1) & 1) ^ 1);
-                mbar_wait(full_bar(st), (i / P.n_stage) & 1);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(a_s + (size_t)st * P.a_stage);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C_OUT);
+        // ------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+        constexpr uint32_t idesc = umma_idesc_bf16(128, C_OUT);
+        const bool leader = elect_one();
+        mbar_wait(w_bar, 0);
+        // descriptor = base + (byte offset >> 4): the offsets below are compile-time immediates
+        const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < n_local; ++i) {
+            const int acc = i % G;
+            mbar_wait(tempty_bar(acc), ((i / G) & 1) ^ 1);
+            mbar_wait(full_bar(st), ph);
+            tc_fence_after();
+            const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * A_STAGE, A_PLANE, SBO_A);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C_OUT);
+            if (leader) {
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
-                    const int dy = tap / 3, dx = tap - dy * 3;
-                    const uint32_t tap_off = TAPS == 9 ? (uint32_t)((dy * P.NP * kPitch + dx) * 16) : 0u;
+                    const uint32_t tap_off = TAPS == 9 ? (uint32_t)(((tap / 3) * NP * kPitch + (tap % 3)) * 16) : 0u;
 #pragma unroll
                     for (int j = 0; j < KSTEPS; ++j) {
-                        const uint64_t ad = umma_desc(a_addr + (uint32_t)(2 * j) * P.a_plane + tap_off, P.a_plane, P.sbo_a);
-                        const uint64_t bd = umma_desc(w_addr + (uint32_t)((tap * KCH + 2 * j) * C_OUT * 16), C_OUT * 16, 128);
+                        const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(2 * j) * A_PLANE + tap_off) >> 4);
+                        const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((tap * KCH + 2 * j) * C_OUT * 16) >> 4);
                         umma_bf16(d_tmem, ad, bd, idesc, (tap | j) ? 1u : 0u);
                     }
                 }
                 umma_commit(empty_bar(st));      // halo stage reusable once these MMAs retire
                 umma_commit(tfull_bar(acc));     // accumulator ready for the epilogue
             }
+            __syncwarp();
+            if (++st == P.n_stage) { st = 0; ph ^= 1; }
         }
-        __syncwarp();
     } else {
-        // ------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------ epilogue (G groups of 4 warps)
+        const int eg = (warp - 2) >> 2;          // epilogue group = accumulator this warp drains
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
         const int m = q * 32 + lane;             // accumulator row = pixel of the tile
-        const int So = POOL ? P.S / 2 : P.S;
-        for (int i = 0; i < n_local; ++i) {
+        const int So_l2 = POOL ? P.S_l2 - 1 : P.S_l2;
+        constexpr int hx = 8 * NP;               // lane distance of the vertical pooling neighbour
+        const int sub = (lane & 1) | (((lane / hx) & 1) << 1);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * C_OUT);
+        for (int i = eg; i < n_local; i += G) {
             const int tile = blockIdx.x + i * gridDim.x;
-            const int acc = i & 1;
-            const int grp = tile / P.tiles_per_group, t = tile - grp * P.tiles_per_group;
+            const int grp = tile >> P.tpg_l2, t = tile & ((1 << P.tpg_l2) - 1);
             int n, h, w;
             if (TAPS == 9) {
-                const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+                const int ty = t >> P.tiles_x_l2, tx = t & ((1 << P.tiles_x_l2) - 1);
                 const int g = m >> 3;
-                n = grp * P.NP + g % P.NP;
-                h = ty * P.TH + g / P.NP;
+                n = grp * NP + (g % NP);
+                h = ty * TH + (g / NP);
                 w = tx * 8 + (m & 7);
             } else {
-                const int px = t * P.PX + m % P.PX;
-                n = grp * P.NP + m / P.PX;
-                h = px / P.S;
-                w = px - h * P.S;
+                const int px = (t << P.PX_l2) + (m & (P.PX - 1));
+                n = (grp << P.NP_l2) + (m >> P.PX_l2);
+                h = px >> P.S_l2;
+                w = px & (P.S - 1);
             }
             const bool valid = n < P.N;
-            mbar_wait(tfull_bar(acc), (i >> 1) & 1);
+            // element offset of (n, chunk 0, h', w', 0); one channel chunk is So*So*8 elements further
+            const int64_t chunk0 = (int64_t)n * P.out_chunks + P.out_chunk0;
+            const int hh = POOL ? h >> 1 : h, ww = POOL ? w >> 1 : w;
+            __nv_bfloat16* const obase = P.out + (((chunk0 << So_l2) + hh) << So_l2) * 8 + ww * 8;
+            const int64_t cstride = (int64_t)8 << (2 * So_l2);
+            mbar_wait(tfull_bar(eg), (i / G) & 1);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C_OUT);
 #pragma unroll 1
-            for (int c0 = 0; c0 < C_OUT; c0 += 32) {
+            for (int c0 = 0; c0 < ((P.dbg & 2) ? 0 : C_OUT); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(t_row + c0, v);
                 uint32_t pk[16];
+                const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
+                const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    float a = fmaf(__uint_as_float(v[2 * k]), scale_s[c0 + 2 * k], shift_s[c0 + 2 * k]);
-                    float b = fmaf(__uint_as_float(v[2 * k + 1]), scale_s[c0 + 2 * k + 1], shift_s[c0 + 2 * k + 1]);
-                    pk[k] = pack_bf16x2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+                for (int k = 0; k < 8; ++k) {
+                    const float4 sc = sc4[k], sh = sh4[k];
+                    const float a0 = fmaxf(fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x), 0.f);
+                    const float a1 = fmaxf(fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y), 0.f);
+                    const float a2 = fmaxf(fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z), 0.f);
+                    const float a3 = fmaxf(fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w), 0.f);
+                    pk[2 * k] = pack_bf16x2(a0, a1);
+                    pk[2 * k + 1] = pack_bf16x2(a2, a3);
                 }
                 if (POOL) {
-                    const int hx = 8 * P.NP;     // lane distance of the vertical neighbour
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         pk[k] = max_bf16x2(pk[k], __shfl_xor_sync(0xffffffffu, pk[k], 1));
                         pk[k] = max_bf16x2(pk[k], __shfl_xor_sync(0xffffffffu, pk[k], hx));
                     }
                     // the 4 lanes of a 2x2 window now hold the same 32 pooled channels: each stores one 8-channel chunk
-                    const int sub = (lane & 1) | (((lane / hx) & 1) << 1);
                     uint4 o;
                     o.x = sub == 0 ? pk[0] : sub == 1 ? pk[4] : sub == 2 ? pk[8] : pk[12];
                     o.y = sub == 0 ? pk[1] : sub == 1 ? pk[5] : sub == 2 ? pk[9] : pk[13];
                     o.z = sub == 0 ? pk[2] : sub == 1 ? pk[6] : sub == 2 ? pk[10] : pk[14];
                     o.w = sub == 0 ? pk[3] : sub == 1 ? pk[7] : sub == 2 ? pk[11] : pk[15];
-                    if (valid) {
-                        const int64_t chunk = (int64_t)n * P.out_chunks + P.out_chunk0 + (c0 >> 3) + sub;
-                        *reinterpret_cast<uint4*>(P.out + ((chunk * So + (h >> 1)) * So + (w >> 1)) * 8) = o;
-                    }
+                    if (valid) *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + sub) * cstride) = o;
                 } else if (valid) {
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4) {
-                        const int64_t chunk = (int64_t)n * P.out_chunks + P.out_chunk0 + (c0 >> 3) + s4;
-                        *reinterpret_cast<uint4*>(P.out + ((chunk * So + h) * So + w) * 8) =
+                    for (int s4 = 0; s4 < 4; ++s4)
+                        *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + s4) * cstride) =
                             make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
-                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) mbar_arrive(tempty_bar(eg));
         }
     }
 

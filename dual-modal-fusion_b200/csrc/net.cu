@@ -43,6 +43,7 @@ static EncodeTiledFn get_encode() {
 struct LayerGeom {
     int S, taps, cin, cout, pool;
     int NP, TH, tiles_x, tiles_y, PX, tiles_per_group, a_plane, a_stage, sbo_a, n_stage, smem;
+    int S_l2, NP_l2, tiles_x_l2, PX_l2, tpg_l2;
 };
 
 static int make_geom(LayerGeom& g, int S, int taps, int cin, int cout, int pool) {
@@ -66,6 +67,12 @@ static int make_geom(LayerGeom& g, int S, int taps, int cin, int cout, int pool)
     }
     g.a_stage = kch * g.a_plane;
     DMF_REQUIRE(g.a_stage % 128 == 0, "A stage not 128-byte aligned");
+    auto l2 = [](int v) { int e = 0; while ((1 << e) < v) ++e; return e; };
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    DMF_REQUIRE(pow2(S) && pow2(g.NP) && pow2(g.tiles_per_group) && (taps == 1 || pow2(g.tiles_x)) && (taps == 9 || pow2(g.PX)),
+                "layer geometry must be powers of two");
+    g.S_l2 = l2(S); g.NP_l2 = l2(g.NP); g.tiles_x_l2 = taps == 9 ? l2(g.tiles_x) : 0; g.PX_l2 = taps == 1 ? l2(g.PX) : 0;
+    g.tpg_l2 = l2(g.tiles_per_group);
     const int fixed = taps * cin * cout * 2 + 2 * cout * 4 + 256;
     g.n_stage = std::min(6, (kSmemLimit - fixed) / g.a_stage);
     DMF_REQUIRE(g.n_stage >= 1, "layer does not fit in shared memory");
@@ -85,9 +92,11 @@ static int make_map(CUtensorMap* m, const LayerGeom& g, const void* base, int64_
         strides[0] = (cuuint64_t)kch * S * S * 16; strides[1] = (cuuint64_t)S * 16; strides[2] = (cuuint64_t)S * S * 16;
         box[0] = 8 * tc::kPitch; box[1] = g.NP; box[2] = g.TH + 2; box[3] = kch;
     } else {
-        dims[0] = 8; dims[1] = (cuuint64_t)S * S; dims[2] = (cuuint64_t)N; dims[3] = kch;
-        strides[0] = 16; strides[1] = (cuuint64_t)kch * S * S * 16; strides[2] = (cuuint64_t)S * S * 16;
-        box[0] = 8; box[1] = g.PX; box[2] = g.NP; box[3] = kch;
+        // inner dimension = 8 channels x IB pixels merged (contiguous in memory): 512-byte TMA rows
+        const int IB = std::min(g.PX, 32);
+        dims[0] = 8ull * IB; dims[1] = (cuuint64_t)S * S / IB; dims[2] = (cuuint64_t)N; dims[3] = kch;
+        strides[0] = (cuuint64_t)IB * 16; strides[1] = (cuuint64_t)kch * S * S * 16; strides[2] = (cuuint64_t)S * S * 16;
+        box[0] = 8 * IB; box[1] = g.PX / IB; box[2] = g.NP; box[3] = kch;
     }
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -448,37 +457,41 @@ static int pack_conv(dmf_net* n, ConvLayer& L, const std::string& blk) {
     return DMF_OK;
 }
 
-template <int CI, int CO, int TAPS, bool POOL>
+template <int CI, int CO, int TAPS, bool POOL, int G, int NP>
 static int launch_conv(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16* out, int out_chunks, int out_chunk0,
-                       int64_t N, cudaStream_t st) {
+                       int64_t N, cudaStream_t st, int dbg = 0) {
     tc::ConvParams P;
     const LayerGeom& g = L.g;
-    P.S = g.S; P.NP = g.NP; P.TH = g.TH; P.tiles_x = g.tiles_x; P.tiles_y = g.tiles_y; P.PX = g.PX;
-    P.tiles_per_group = g.tiles_per_group;
+    P.S = g.S; P.S_l2 = g.S_l2; P.NP = g.NP; P.NP_l2 = g.NP_l2; P.TH = g.TH; P.tiles_x_l2 = g.tiles_x_l2;
+    P.PX = g.PX; P.PX_l2 = g.PX_l2; P.tpg_l2 = g.tpg_l2;
     P.N = (int)N;
     P.n_tiles = (int)((N + g.NP - 1) / g.NP) * g.tiles_per_group;
     P.a_plane = g.a_plane; P.a_stage = g.a_stage; P.n_stage = g.n_stage; P.sbo_a = g.sbo_a;
-    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0;
+    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0; P.dbg = dbg;
     P.w = L.w; P.scale = L.scale; P.shift = L.shift; P.out = out;
-    auto kern = tc::conv_tc_kernel<CI, CO, TAPS, POOL>;
+    if (TAPS == 9 && (g.NP != NP || g.TH != 16 / NP)) { set_error("conv geometry/template mismatch"); return DMF_ERR_STATE; }
+    auto kern = tc::conv_tc_kernel<CI, CO, TAPS, POOL, G, NP>;
     static bool attr_set = false;
     if (!attr_set) {
         DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
     const int grid = std::min(P.n_tiles, num_sms());
-    kern<<<grid, tc::kThreads, g.smem, st>>>(map, P);
+    kern<<<grid, 64 + 128 * G, g.smem, st>>>(map, P);
     DMF_LAUNCHED();
     return DMF_OK;
 }
 
-static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat16* out, int64_t N, cudaStream_t st) {
+static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat16* out, int64_t N, cudaStream_t st, int dbg = 0) {
     const int ocat = C_CAT / 8;
+    const bool np2 = n->L[layer].g.NP == 2;       // 8x8 maps (p = 8): two patches per 128-pixel tile
     switch (layer) {
-        case 0: return launch_conv<C_MS1, C_MS2, 9, true>(n->L[0], map, out, ocat, 0, N, st);
-        case 1: return launch_conv<C_PAN1, C_PAN2, 9, true>(n->L[1], map, out, C_PAN2 / 8, 0, N, st);
-        case 2: return launch_conv<C_PAN2, C_PAN3, 9, true>(n->L[2], map, out, ocat, C_MS2 / 8, N, st);
-        case 3: return launch_conv<C_CAT, C_FUSE, 1, false>(n->L[3], map, out, C_FUSE / 8, 0, N, st);
+        case 0: return np2 ? launch_conv<C_MS1, C_MS2, 9, true, 3, 2>(n->L[0], map, out, ocat, 0, N, st, dbg)
+                           : launch_conv<C_MS1, C_MS2, 9, true, 3, 1>(n->L[0], map, out, ocat, 0, N, st, dbg);
+        case 1: return launch_conv<C_PAN1, C_PAN2, 9, true, 4, 1>(n->L[1], map, out, C_PAN2 / 8, 0, N, st, dbg);
+        case 2: return np2 ? launch_conv<C_PAN2, C_PAN3, 9, true, 3, 2>(n->L[2], map, out, ocat, C_MS2 / 8, N, st, dbg)
+                           : launch_conv<C_PAN2, C_PAN3, 9, true, 3, 1>(n->L[2], map, out, ocat, C_MS2 / 8, N, st, dbg);
+        case 3: return launch_conv<C_CAT, C_FUSE, 1, false, 2, 1>(n->L[3], map, out, C_FUSE / 8, 0, N, st, dbg);
     }
     return DMF_ERR_ARG;
 }
@@ -747,7 +760,7 @@ int dmf_net_debug_layer(dmf_net* n, int layer, int impl, const void* in_dev, voi
     }
     CUtensorMap map;
     DMF_TRY(make_map(&map, L.g, in_dev, N));
-    return run_layer(n, layer, map, (__nv_bfloat16*)out_dev, N, st);
+    return run_layer(n, layer, map, (__nv_bfloat16*)out_dev, N, st, impl >= 2 ? (impl == 5 ? 7 : impl - 1) : 0);
 }
 
 int dmf_net_debug_stem(dmf_net* n, int which, const float* patches_dev, void* out_dev, int64_t N, void* stream) {

@@ -143,7 +143,7 @@ int dmf_net_set_timing(dmf_net* n, int enabled);
 int dmf_net_get_timing(dmf_net* n, float out_ms[8]);
 
 /* test hooks: run ONE layer on caller buffers in the kernels' activation layout
- * [N][C/8][H][W][8] bf16.  layer: 0 ms2, 1 pan2, 2 pan3, 3 fuse.  impl: 0 = tcgen05 path,
+ * [N][C/8][H][W][8] bf16.  layer: 0 ms2, 1 pan2, 2 pan3, 3 fuse.  impl: 0 = tcgen05 path (2,3,4 = same with TMA loads / epilogue / both skipped: timing diagnostics),
  * 1 = CUDA-core direct convolution (debug oracle on device, never used by the product path). */
 int dmf_net_debug_layer(dmf_net* n, int layer, int impl, const void* in_dev, void* out_dev, int64_t N,
                         void* stream);
