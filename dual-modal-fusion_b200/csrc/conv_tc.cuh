@@ -130,6 +130,18 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -251,6 +263,10 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_c
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
         int st = 0;
         uint32_t ph = 0;
+        // (Tried and measured on B200: interleaving two tiles, or split-K over two accumulators per
+        // tile, lifts the bare MMA chain from ~94 to ~75 clk per M128xN128xK16 instruction — the gap
+        // is the accumulate read-after-write — but the first needs more A stages than fit beside the
+        // resident weights and the second doubles the epilogue's TMEM reads; both lost end to end.)
         for (int i = 0; i < n_local; ++i) {
             const int acc = i % G;
             mbar_wait(tempty_bar(acc), ((i / G) & 1) ^ 1);

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "stem_tc.cuh"
 
 namespace dmf {
 
@@ -123,11 +124,11 @@ struct dmf_net {
     bool ready = false;
     bool timing = false;
     // stems / head weights
-    float *w_ms1 = nullptr, *sc_ms1 = nullptr, *sh_ms1 = nullptr;      // [36][64]
-    float *w_pan1 = nullptr, *sc_pan1 = nullptr, *sh_pan1 = nullptr;   // [32][12]
+    __nv_bfloat16* w_pan1 = nullptr;                                    // hi/lo-split PAN stem weights [4][32][8]
+    float *sc_pan1 = nullptr, *sh_pan1 = nullptr;
     float *fc1t = nullptr, *fc1b = nullptr, *fc2t = nullptr, *fc2b = nullptr;
-    ConvLayer L[4];   // ms2, pan2, pan3, fuse
-    __nv_bfloat16 *A1 = nullptr, *B1 = nullptr, *B2 = nullptr, *CAT = nullptr, *F = nullptr;
+    ConvLayer L[5];   // ms2, pan2, pan3, fuse, ms1 (hi/lo-split stem, 16 -> 64)
+    __nv_bfloat16 *X0 = nullptr, *A1 = nullptr, *B1 = nullptr, *B2 = nullptr, *CAT = nullptr, *F = nullptr;
     cudaEvent_t ev[8] = {};
     float stage_ms[8] = {};
 };
@@ -144,137 +145,40 @@ struct PatchSrc {
     const float* patches;
 };
 
-// MS stem: conv3x3 4->64 (zero padding at the PATCH border) + BN + ReLU, fp32 on CUDA cores, one CTA
-// per patch, one thread per pixel; output bf16 C8-planar.
+// MS stem, step 1 (step 2 is a tcgen05 layer): the 4-band fp32 window of every patch is split into
+// bf16 hi + lo parts (x = hi + lo to ~2^-16) and written as a 16-channel C8-planar tensor
+//   chunk 0 = [hi0..hi3, lo0..lo3]    chunk 1 = [hi0..hi3, 0, 0, 0, 0]
+// The stem weights are packed to match ([w_hi, w_hi, w_lo, 0], net_finalize), so that one K=16
+// tcgen05.mma per tap evaluates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo: fp32-grade products on the bf16
+// tensor pipe.  One thread per pixel; 16-byte coalesced stores.
 template <bool FROM_SCENE>
-__global__ void __launch_bounds__(256) stem_ms_kernel(PatchSrc src, int p, int64_t N, const float* __restrict__ wt,
-                                                      const float* __restrict__ scale, const float* __restrict__ shift,
-                                                      __nv_bfloat16* __restrict__ out) {
-    extern __shared__ __align__(16) float sm[];
-    float4* tile = reinterpret_cast<float4*>(sm);                 // (p+2) x (p+2) pixels, zero border
-    float* w_s = sm + 4 * (p + 2) * (p + 2);                       // [36][64]
-    float* sc_s = w_s + 36 * C_MS1;
-    float* sh_s = sc_s + C_MS1;
-    const int T = p + 2;
-    for (int i = threadIdx.x; i < 36 * C_MS1; i += blockDim.x) w_s[i] = wt[i];
-    for (int i = threadIdx.x; i < C_MS1; i += blockDim.x) { sc_s[i] = scale[i]; sh_s[i] = shift[i]; }
-    const int64_t n = blockIdx.x;
-    int x = 0, y = 0;
-    if (FROM_SCENE) {
-        const int64_t k = src.idx ? src.idx[n] : src.first + n;
-        x = (int)(k / src.scene.W); y = (int)(k % src.scene.W);
-    }
-    for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-        const int r = i / T - 1, c = i % T - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r >= 0 && r < p && c >= 0 && c < p) {
-            if (FROM_SCENE) {
-                v = __ldg(reinterpret_cast<const float4*>(src.scene.ms) + (int64_t)(x + r) * src.scene.Wp + y + c);
-            } else {
-                const float* b = src.patches + n * 4 * p * p + r * p + c;
-                v = make_float4(b[0], b[p * p], b[2 * p * p], b[3 * p * p]);
-            }
+__global__ void __launch_bounds__(256) ms_prep_kernel(PatchSrc src, int p, int64_t N, __nv_bfloat16* __restrict__ out) {
+    const int pp = p * p;
+    const int64_t total = N * pp;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = t / pp;
+        const int px = (int)(t - n * pp);
+        const int r = px / p, c = px - r * p;
+        float4 v;
+        if (FROM_SCENE) {
+            const int64_t k = src.idx ? src.idx[n] : src.first + n;
+            const int x = (int)(k / src.scene.W), y = (int)(k % src.scene.W);
+            v = __ldg(reinterpret_cast<const float4*>(src.scene.ms) + (int64_t)(x + r) * src.scene.Wp + y + c);
+        } else {
+            const float* b = src.patches + n * 4 * pp + px;
+            v = make_float4(b[0], b[pp], b[2 * pp], b[3 * pp]);
         }
-        tile[i] = v;
-    }
-    __syncthreads();
-    for (int px = threadIdx.x; px < p * p; px += blockDim.x) {
-        const int h = px / p, w = px % p;
-        float in[36];
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        float hi[4], lo[4];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const float4 v = tile[(h + t / 3) * T + w + t % 3];
-            in[4 * t] = v.x; in[4 * t + 1] = v.y; in[4 * t + 2] = v.z; in[4 * t + 3] = v.w;
+        for (int i = 0; i < 4; ++i) {
+            hi[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+            lo[i] = f[i] - hi[i];
         }
-#pragma unroll 1
-        for (int ch = 0; ch < C_MS1 / 8; ++ch) {
-            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-            for (int k = 0; k < 36; ++k) {
-                const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * C_MS1 + ch * 8);
-                const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * C_MS1 + ch * 8 + 4);
-                acc[0] = fmaf(in[k], w0.x, acc[0]); acc[1] = fmaf(in[k], w0.y, acc[1]);
-                acc[2] = fmaf(in[k], w0.z, acc[2]); acc[3] = fmaf(in[k], w0.w, acc[3]);
-                acc[4] = fmaf(in[k], w1.x, acc[4]); acc[5] = fmaf(in[k], w1.y, acc[5]);
-                acc[6] = fmaf(in[k], w1.z, acc[6]); acc[7] = fmaf(in[k], w1.w, acc[7]);
-            }
-            uint32_t pk[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float a = fmaxf(fmaf(acc[2 * k], sc_s[ch * 8 + 2 * k], sh_s[ch * 8 + 2 * k]), 0.f);
-                const float b = fmaxf(fmaf(acc[2 * k + 1], sc_s[ch * 8 + 2 * k + 1], sh_s[ch * 8 + 2 * k + 1]), 0.f);
-                pk[k] = tc::pack_bf16x2(a, b);
-            }
-            *reinterpret_cast<uint4*>(out + (((n * (C_MS1 / 8) + ch) * p + h) * p + w) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-    }
-}
-
-// PAN stem: conv3x3 1->32 + BN + ReLU + maxpool2, fp32 on CUDA cores; one CTA per patch, one thread
-// per POOLED pixel (4x4 input window in registers); output bf16 C8-planar [N][4][2p][2p][8].
-template <bool FROM_SCENE>
-__global__ void __launch_bounds__(256) stem_pan_kernel(PatchSrc src, int p, int64_t N, const float* __restrict__ wt,
-                                                       const float* __restrict__ scale, const float* __restrict__ shift,
-                                                       __nv_bfloat16* __restrict__ out) {
-    extern __shared__ __align__(16) float sm[];
-    const int P = 4 * p, T = P + 2, S = 2 * p;
-    float* tile = sm;                            // T x T, zero border
-    float* w_s = sm + ((T * T + 3) & ~3);        // [32][12] (9 taps + 3 pad)
-    float* sc_s = w_s + C_PAN1 * 12;
-    float* sh_s = sc_s + C_PAN1;
-    for (int i = threadIdx.x; i < C_PAN1 * 12; i += blockDim.x) w_s[i] = wt[i];
-    for (int i = threadIdx.x; i < C_PAN1; i += blockDim.x) { sc_s[i] = scale[i]; sh_s[i] = shift[i]; }
-    const int64_t n = blockIdx.x;
-    int x = 0, y = 0;
-    if (FROM_SCENE) {
-        const int64_t k = src.idx ? src.idx[n] : src.first + n;
-        x = (int)(k / src.scene.W); y = (int)(k % src.scene.W);
-    }
-    for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-        const int r = i / T - 1, c = i % T - 1;
-        float v = 0.f;
-        if (r >= 0 && r < P && c >= 0 && c < P)
-            v = FROM_SCENE ? __ldg(src.scene.pan + (int64_t)(4 * x + r) * src.scene.pan_pitch + 4 * y + c)
-                           : src.patches[n * P * P + r * P + c];
-        tile[i] = v;
-    }
-    __syncthreads();
-    for (int px = threadIdx.x; px < S * S; px += blockDim.x) {
-        const int ph = px / S, pw = px % S;
-        float in[16];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) in[4 * r + c] = tile[(2 * ph + r) * T + 2 * pw + c];
-#pragma unroll 1
-        for (int ch = 0; ch < C_PAN1 / 8; ++ch) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-                float res[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int co = ch * 8 + 2 * k2 + e;
-                    const float4 wa = *reinterpret_cast<const float4*>(w_s + co * 12);
-                    const float4 wb = *reinterpret_cast<const float4*>(w_s + co * 12 + 4);
-                    const float w8 = w_s[co * 12 + 8];
-                    const float wv[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, w8};
-                    float best = -INFINITY;
-#pragma unroll
-                    for (int oy = 0; oy < 2; ++oy)
-#pragma unroll
-                        for (int ox = 0; ox < 2; ++ox) {
-                            float a = 0.f;
-#pragma unroll
-                            for (int t = 0; t < 9; ++t) a = fmaf(in[(oy + t / 3) * 4 + ox + t % 3], wv[t], a);
-                            best = fmaxf(best, fmaf(a, sc_s[co], sh_s[co]));
-                        }
-                    res[e] = fmaxf(best, 0.f);
-                }
-                pk[k2] = tc::pack_bf16x2(res[0], res[1]);
-            }
-            *reinterpret_cast<uint4*>(out + (((n * (C_PAN1 / 8) + ch) * S + ph) * S + pw) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
+        const uint32_t h01 = tc::pack_bf16x2(hi[0], hi[1]), h23 = tc::pack_bf16x2(hi[2], hi[3]);
+        uint4* o = reinterpret_cast<uint4*>(out + (n * 2 * pp + px) * 8);
+        o[0] = make_uint4(h01, h23, tc::pack_bf16x2(lo[0], lo[1]), tc::pack_bf16x2(lo[2], lo[3]));
+        o[pp] = make_uint4(h01, h23, 0u, 0u);
     }
 }
 
@@ -457,6 +361,29 @@ static int pack_conv(dmf_net* n, ConvLayer& L, const std::string& blk) {
     return DMF_OK;
 }
 
+// MS stem weights for the hi/lo-split input: per tap k = [w_hi(4), w_hi(4), w_lo(4), 0(4)]
+static int pack_ms_stem(dmf_net* n, ConvLayer& L) {
+    const int cout = C_MS1;
+    auto* w = param(n, "ms1.0.weight", (size_t)cout * 4 * 9);
+    if (!w) return DMF_ERR_STATE;
+    std::vector<__nv_bfloat16> pk((size_t)9 * 16 * cout, __float2bfloat16_rn(0.f));
+    for (int tap = 0; tap < 9; ++tap)
+        for (int co = 0; co < cout; ++co)
+            for (int ci = 0; ci < 4; ++ci) {
+                const float wv = (*w)[((size_t)co * 4 + ci) * 9 + tap];
+                const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+                auto at = [&](int k) -> __nv_bfloat16& { return pk[(((size_t)tap * 2 + k / 8) * cout + co) * 8 + k % 8]; };
+                at(ci) = hi; at(4 + ci) = hi; at(8 + ci) = lo;
+            }
+    std::vector<float> sc, sh;
+    DMF_TRY(fold_bn(n, "ms1", cout, sc, sh));
+    DMF_TRY(to_device(&L.w, pk));
+    DMF_TRY(to_device(&L.scale, sc));
+    DMF_TRY(to_device(&L.shift, sh));
+    return DMF_OK;
+}
+
 template <int CI, int CO, int TAPS, bool POOL, int G, int NP>
 static int launch_conv(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16* out, int out_chunks, int out_chunk0,
                        int64_t N, cudaStream_t st, int dbg = 0) {
@@ -482,7 +409,7 @@ static int launch_conv(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16
     return DMF_OK;
 }
 
-static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat16* out, int64_t N, cudaStream_t st, int dbg = 0) {
+static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat16* out, int64_t N, cudaStream_t st, int dbg) {
     const int ocat = C_CAT / 8;
     const bool np2 = n->L[layer].g.NP == 2;       // 8x8 maps (p = 8): two patches per 128-pixel tile
     switch (layer) {
@@ -492,14 +419,18 @@ static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat1
         case 2: return np2 ? launch_conv<C_PAN2, C_PAN3, 9, true, 3, 2>(n->L[2], map, out, ocat, C_MS2 / 8, N, st, dbg)
                            : launch_conv<C_PAN2, C_PAN3, 9, true, 3, 1>(n->L[2], map, out, ocat, C_MS2 / 8, N, st, dbg);
         case 3: return launch_conv<C_CAT, C_FUSE, 1, false, 2, 1>(n->L[3], map, out, C_FUSE / 8, 0, N, st, dbg);
+        case 4: return np2 ? launch_conv<16, C_MS1, 9, false, 4, 2>(n->L[4], map, out, C_MS1 / 8, 0, N, st, dbg)
+                           : launch_conv<16, C_MS1, 9, false, 4, 1>(n->L[4], map, out, C_MS1 / 8, 0, N, st, dbg);
     }
     return DMF_ERR_ARG;
 }
 
-static size_t stem_ms_smem(int p) { return sizeof(float) * (4 * (p + 2) * (p + 2) + 36 * C_MS1 + 2 * C_MS1); }
+static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat16* out, int64_t N, cudaStream_t st, int dbg);
+static int stem_pan_stages(int p) { return p >= 32 ? 2 : tc::kStemMaxStages; }
+static int stem_pan_raw_pitch(int p) { return 4 * p + 8; }
 static size_t stem_pan_smem(int p) {
-    const int T = 4 * p + 2;
-    return sizeof(float) * (((T * T + 3) & ~3) + C_PAN1 * 12 + 2 * C_PAN1);
+    const size_t raw = 2ull * (4 * p + 2) * stem_pan_raw_pitch(p) * 4;
+    return (size_t)stem_pan_stages(p) * tc::kStemStage + 4 * tc::kStemCout * 16 + 2 * tc::kStemCout * 4 + 18 * 8 + 16 + raw;
 }
 static size_t head_smem(int C) {
     return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + C_FUSE + C_HID + ((C + 3) & ~3)) +
@@ -508,20 +439,29 @@ static size_t head_smem(int C) {
 
 static int launch_stems(dmf_net* n, const PatchSrc& src, bool from_scene, int64_t N, __nv_bfloat16* A1, __nv_bfloat16* B1,
                         int which, cudaStream_t st) {
+    constexpr int GP = 2;                  // epilogue groups of the PAN stem kernel
     static bool attr_set = false;
     if (!attr_set) {
-        DMF_CUDA(cudaFuncSetAttribute(stem_pan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        DMF_CUDA(cudaFuncSetAttribute(stem_pan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        DMF_CUDA(cudaFuncSetAttribute(tc::stem_pan_tc_kernel<GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
     if (which & 1) {
-        if (from_scene) stem_ms_kernel<true><<<(unsigned)N, 256, stem_ms_smem(n->p), st>>>(src, n->p, N, n->w_ms1, n->sc_ms1, n->sh_ms1, A1);
-        else stem_ms_kernel<false><<<(unsigned)N, 256, stem_ms_smem(n->p), st>>>(src, n->p, N, n->w_ms1, n->sc_ms1, n->sh_ms1, A1);
+        const int grid = (int)std::min<int64_t>((N * n->p * n->p + 255) / 256, (int64_t)num_sms() * 16);
+        if (from_scene) ms_prep_kernel<true><<<grid, 256, 0, st>>>(src, n->p, N, n->X0);
+        else ms_prep_kernel<false><<<grid, 256, 0, st>>>(src, n->p, N, n->X0);
         DMF_LAUNCHED();
+        DMF_TRY(run_layer(n, 4, n->L[4].map, A1, N, st, 0));
     }
     if (which & 2) {
-        if (from_scene) stem_pan_kernel<true><<<(unsigned)N, 256, stem_pan_smem(n->p), st>>>(src, n->p, N, n->w_pan1, n->sc_pan1, n->sh_pan1, B1);
-        else stem_pan_kernel<false><<<(unsigned)N, 256, stem_pan_smem(n->p), st>>>(src, n->p, N, n->w_pan1, n->sc_pan1, n->sh_pan1, B1);
+        auto l2 = [](int v) { int e = 0; while ((1 << e) < v) ++e; return e; };
+        tc::StemPanParams Q;
+        Q.scene_pan = src.scene.pan; Q.pan_pitch = src.scene.pan_pitch; Q.scene_W = src.scene.W;
+        Q.idx = src.idx; Q.first = src.first; Q.patches = src.patches; Q.from_scene = from_scene ? 1 : 0;
+        Q.p = n->p; Q.S_l2 = l2(2 * n->p); Q.tpp_l2 = l2(4 * n->p * n->p / 128); Q.N = N;
+        Q.n_stage = stem_pan_stages(n->p); Q.raw_pitch = stem_pan_raw_pitch(n->p);
+        Q.w = n->w_pan1; Q.scale = n->sc_pan1; Q.shift = n->sh_pan1; Q.out = B1;
+        const int grid = (int)std::min<int64_t>(N, num_sms());
+        tc::stem_pan_tc_kernel<GP><<<grid, 320 + 128 * GP, stem_pan_smem(n->p), st>>>(Q);
         DMF_LAUNCHED();
     }
     return DMF_OK;
@@ -534,15 +474,15 @@ static int forward_chunk(dmf_net* n, const PatchSrc& src, bool from_scene, int64
     if (tm) cudaEventRecord(n->ev[0], st);
     DMF_TRY(launch_stems(n, src, from_scene, N, n->A1, n->B1, 1, st));
     if (tm) cudaEventRecord(n->ev[1], st);
-    DMF_TRY(run_layer(n, 0, n->L[0].map, n->CAT, N, st));
+    DMF_TRY(run_layer(n, 0, n->L[0].map, n->CAT, N, st, 0));
     if (tm) cudaEventRecord(n->ev[2], st);
     DMF_TRY(launch_stems(n, src, from_scene, N, n->A1, n->B1, 2, st));
     if (tm) cudaEventRecord(n->ev[3], st);
-    DMF_TRY(run_layer(n, 1, n->L[1].map, n->B2, N, st));
+    DMF_TRY(run_layer(n, 1, n->L[1].map, n->B2, N, st, 0));
     if (tm) cudaEventRecord(n->ev[4], st);
-    DMF_TRY(run_layer(n, 2, n->L[2].map, n->CAT, N, st));
+    DMF_TRY(run_layer(n, 2, n->L[2].map, n->CAT, N, st, 0));
     if (tm) cudaEventRecord(n->ev[5], st);
-    DMF_TRY(run_layer(n, 3, n->L[3].map, n->F, N, st));
+    DMF_TRY(run_layer(n, 3, n->L[3].map, n->F, N, st, 0));
     if (tm) cudaEventRecord(n->ev[6], st);
     const int npx = (n->p / 2) * (n->p / 2);
     const int grid = (int)std::min<int64_t>(N, (int64_t)num_sms() * 4);
@@ -579,6 +519,7 @@ int dmf_net_create(dmf_net** out, int p, int num_classes, int max_batch) {
     if (rc == DMF_OK) rc = make_geom(n->L[1].g, 2 * p, 9, C_PAN1, C_PAN2, 1);
     if (rc == DMF_OK) rc = make_geom(n->L[2].g, p, 9, C_PAN2, C_PAN3, 1);
     if (rc == DMF_OK) rc = make_geom(n->L[3].g, p / 2, 1, C_CAT, C_FUSE, 0);
+    if (rc == DMF_OK) rc = make_geom(n->L[4].g, p, 9, 16, C_MS1, 0);
     if (rc != DMF_OK) { delete n; return rc; }
     *out = n;
     return DMF_OK;
@@ -586,10 +527,11 @@ int dmf_net_create(dmf_net** out, int p, int num_classes, int max_batch) {
 
 int dmf_net_destroy(dmf_net* n) {
     if (!n) return DMF_OK;
-    float* fs[] = {n->w_ms1, n->sc_ms1, n->sh_ms1, n->w_pan1, n->sc_pan1, n->sh_pan1, n->fc1t, n->fc1b, n->fc2t, n->fc2b};
+    cudaFree(n->w_pan1);
+    float* fs[] = {n->sc_pan1, n->sh_pan1, n->fc1t, n->fc1b, n->fc2t, n->fc2b};
     for (float* f : fs) cudaFree(f);
     for (auto& L : n->L) { cudaFree(L.w); cudaFree(L.scale); cudaFree(L.shift); }
-    __nv_bfloat16* bs[] = {n->A1, n->B1, n->B2, n->CAT, n->F};
+    __nv_bfloat16* bs[] = {n->X0, n->A1, n->B1, n->B2, n->CAT, n->F};
     for (auto* b : bs) cudaFree(b);
     for (auto& e : n->ev) if (e) cudaEventDestroy(e);
     delete n;
@@ -616,24 +558,23 @@ int dmf_net_finalize(dmf_net* n, void* stream) {
     (void)stream;
     const int p = n->p, C = n->C;
     // --- stems
-    {
-        auto* w = param(n, "ms1.0.weight", (size_t)C_MS1 * 4 * 9);
-        if (!w) return DMF_ERR_STATE;
-        std::vector<float> wt(36 * C_MS1), sc, sh;   // [tap][cin][cout]
-        for (int co = 0; co < C_MS1; ++co)
-            for (int ci = 0; ci < 4; ++ci)
-                for (int t = 0; t < 9; ++t) wt[(t * 4 + ci) * C_MS1 + co] = (*w)[(co * 4 + ci) * 9 + t];
-        DMF_TRY(fold_bn(n, "ms1", C_MS1, sc, sh));
-        DMF_TRY(to_device(&n->w_ms1, wt)); DMF_TRY(to_device(&n->sc_ms1, sc)); DMF_TRY(to_device(&n->sh_ms1, sh));
-    }
+    DMF_TRY(pack_ms_stem(n, n->L[4]));
     {
         auto* w = param(n, "pan1.0.weight", (size_t)C_PAN1 * 9);
         if (!w) return DMF_ERR_STATE;
-        std::vector<float> wt(C_PAN1 * 12, 0.f), sc, sh;
+        // K = 32 per output channel: k = 2t, 2t+1 -> w_hi[t]; k = 18+t -> w_lo[t]; rest 0   (stem_tc.cuh)
+        std::vector<__nv_bfloat16> pk((size_t)4 * C_PAN1 * 8, __float2bfloat16_rn(0.f));
+        std::vector<float> sc, sh;
         for (int co = 0; co < C_PAN1; ++co)
-            for (int t = 0; t < 9; ++t) wt[co * 12 + t] = (*w)[co * 9 + t];
+            for (int t = 0; t < 9; ++t) {
+                const float wv = (*w)[co * 9 + t];
+                const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+                auto at = [&](int k) -> __nv_bfloat16& { return pk[((size_t)(k / 8) * C_PAN1 + co) * 8 + k % 8]; };
+                at(2 * t) = hi; at(2 * t + 1) = hi; at(18 + t) = lo;
+            }
         DMF_TRY(fold_bn(n, "pan1", C_PAN1, sc, sh));
-        DMF_TRY(to_device(&n->w_pan1, wt)); DMF_TRY(to_device(&n->sc_pan1, sc)); DMF_TRY(to_device(&n->sh_pan1, sh));
+        DMF_TRY(to_device(&n->w_pan1, pk)); DMF_TRY(to_device(&n->sc_pan1, sc)); DMF_TRY(to_device(&n->sh_pan1, sh));
     }
     // --- tensor-core layers
     DMF_TRY(pack_conv(n, n->L[0], "ms2"));
@@ -656,6 +597,7 @@ int dmf_net_finalize(dmf_net* n, void* stream) {
     // --- workspace + tensor maps (once)
     if (!n->A1) {
         const size_t NB = n->NB;
+        DMF_CUDA(cudaMalloc(&n->X0, NB * 16 * p * p * 2));
         DMF_CUDA(cudaMalloc(&n->A1, NB * C_MS1 * p * p * 2));
         DMF_CUDA(cudaMalloc(&n->B1, NB * C_PAN1 * 4 * p * p * 2));
         DMF_CUDA(cudaMalloc(&n->B2, NB * C_PAN2 * p * p * 2));
@@ -665,6 +607,7 @@ int dmf_net_finalize(dmf_net* n, void* stream) {
         DMF_TRY(make_map(&n->L[1].map, n->L[1].g, n->B1, n->NB));
         DMF_TRY(make_map(&n->L[2].map, n->L[2].g, n->B2, n->NB));
         DMF_TRY(make_map(&n->L[3].map, n->L[3].g, n->CAT, n->NB));
+        DMF_TRY(make_map(&n->L[4].map, n->L[4].g, n->X0, n->NB));
         for (auto& e : n->ev) DMF_CUDA(cudaEventCreate(&e));
         DMF_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     }
@@ -703,10 +646,10 @@ int dmf_net_forward_patches(dmf_net* n, const float* ms_dev, const float* pan_de
         cudaStream_t st = (cudaStream_t)stream;
         DMF_TRY(launch_stems(n, sm, false, nb, n->A1, n->B1, 1, st));
         DMF_TRY(launch_stems(n, sp, false, nb, n->A1, n->B1, 2, st));
-        DMF_TRY(run_layer(n, 0, n->L[0].map, n->CAT, nb, st));
-        DMF_TRY(run_layer(n, 1, n->L[1].map, n->B2, nb, st));
-        DMF_TRY(run_layer(n, 2, n->L[2].map, n->CAT, nb, st));
-        DMF_TRY(run_layer(n, 3, n->L[3].map, n->F, nb, st));
+        DMF_TRY(run_layer(n, 0, n->L[0].map, n->CAT, nb, st, 0));
+        DMF_TRY(run_layer(n, 1, n->L[1].map, n->B2, nb, st, 0));
+        DMF_TRY(run_layer(n, 2, n->L[2].map, n->CAT, nb, st, 0));
+        DMF_TRY(run_layer(n, 3, n->L[3].map, n->F, nb, st, 0));
         const int npx = (p / 2) * (p / 2);
         const int grid = (int)std::min<int64_t>(nb, (int64_t)num_sms() * 4);
         dmf_scene none{};
@@ -744,7 +687,7 @@ int dmf_infer_scene(dmf_net* n, const dmf_scene* s, int row0, int row1, uint8_t*
 
 int dmf_net_debug_layer(dmf_net* n, int layer, int impl, const void* in_dev, void* out_dev, int64_t N, void* stream) {
     DMF_NET_READY(n);
-    DMF_REQUIRE(layer >= 0 && layer < 4 && in_dev && out_dev && N > 0, "net_debug_layer: bad argument");
+    DMF_REQUIRE(layer >= 0 && layer < 5 && in_dev && out_dev && N > 0, "net_debug_layer: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const ConvLayer& L = n->L[layer];
     const int och = layer == 0 || layer == 2 ? C_CAT / 8 : L.g.cout / 8;
@@ -760,7 +703,7 @@ int dmf_net_debug_layer(dmf_net* n, int layer, int impl, const void* in_dev, voi
     }
     CUtensorMap map;
     DMF_TRY(make_map(&map, L.g, in_dev, N));
-    return run_layer(n, layer, map, (__nv_bfloat16*)out_dev, N, st, impl >= 2 ? (impl == 5 ? 7 : impl - 1) : 0);
+    return run_layer(n, layer, map, (__nv_bfloat16*)out_dev, N, st, impl >= 2 ? impl - 1 : 0);
 }
 
 int dmf_net_debug_stem(dmf_net* n, int which, const float* patches_dev, void* out_dev, int64_t N, void* stream) {

@@ -287,8 +287,9 @@ class NetHandle:
         names = ['stem_ms', 'conv_ms2', 'stem_pan', 'conv_pan2', 'conv_pan3', 'conv_fuse', 'head', 'total']
         return dict(zip(names, [float(v) for v in buf]))
 
-    def debug_layer(self, layer, impl, x, out_shape):
-        out = torch.zeros(out_shape, dtype=torch.bfloat16, device=x.device)
+    def debug_layer(self, layer, impl, x, out_shape, out=None):
+        if out is None:
+            out = torch.zeros(out_shape, dtype=torch.bfloat16, device=x.device)
         with torch.cuda.device(x.device):
             check(lib.dmf_net_debug_layer(self._h, layer, impl, _ptr(x.contiguous()), _ptr(out), x.shape[0], _stream()))
         return out
