@@ -184,88 +184,134 @@ __global__ void __launch_bounds__(256) ms_prep_kernel(PatchSrc src, int p, int64
 
 // ------------------------------------------------------------------------------------ head
 // F[N][16][px][8] bf16 -> global average pool -> Linear 128->64 + ReLU -> Linear 64->C -> logits,
-// argmax (first maximum), confusion matrix, prediction map.  128 threads, persistent over patches.
-__global__ void __launch_bounds__(128) head_kernel(const __nv_bfloat16* __restrict__ F, int64_t N, int npx, int C,
-                                                   const float* __restrict__ fc1t, const float* __restrict__ fc1b,
-                                                   const float* __restrict__ fc2t, const float* __restrict__ fc2b,
-                                                   const dmf_scene scene, const int64_t* __restrict__ idx, int64_t first,
-                                                   float* __restrict__ logits_out, uint8_t* __restrict__ pred_out,
-                                                   unsigned long long* __restrict__ cm, uint8_t* __restrict__ pred_map) {
+// argmax (first maximum), confusion matrix, prediction map.  One WARP per patch, no block barriers:
+// coalesced 512-byte reads of F, an exchange-halving warp reduction for the pooling (9 shuffles per
+// 8 channels instead of 40), the two small linears from shared-memory weights, shuffle argmax.
+constexpr int kHeadWarps = 8;
+
+__global__ void __launch_bounds__(32 * kHeadWarps) head_kernel(const __nv_bfloat16* __restrict__ F, int64_t N, int npx, int C,
+                                                              const float* __restrict__ fc1t, const float* __restrict__ fc1b,
+                                                              const float* __restrict__ fc2t, const float* __restrict__ fc2b,
+                                                              const dmf_scene scene, const int64_t* __restrict__ idx, int64_t first,
+                                                              float* __restrict__ logits_out, uint8_t* __restrict__ pred_out,
+                                                              unsigned long long* __restrict__ cm, uint8_t* __restrict__ pred_map) {
     extern __shared__ __align__(16) float hs[];
-    float* w1 = hs;                       // [128][64]
-    float* w2 = w1 + C_FUSE * C_HID;      // [64][C]
+    float* w1 = hs;                                   // [128][64]
+    float* w2 = w1 + C_FUSE * C_HID;                  // [64][C]
     float* b1 = w2 + C_HID * C;
     float* b2 = b1 + C_HID;
-    float* g = b2 + ((C + 3) & ~3);       // [128]
-    float* hid = g + C_FUSE;              // [64]
-    float* lg = hid + C_HID;              // [C]
-    unsigned int* hist = reinterpret_cast<unsigned int*>(lg + ((C + 3) & ~3));   // [C*C]
-    for (int i = threadIdx.x; i < C_FUSE * C_HID; i += 128) w1[i] = fc1t[i];
-    for (int i = threadIdx.x; i < C_HID * C; i += 128) w2[i] = fc2t[i];
+    float* gbuf = b2 + ((C + 3) & ~3);                // per warp: g[128] + hid[64]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(gbuf + kHeadWarps * (C_FUSE + C_HID));   // [C*C]
+    for (int i = threadIdx.x; i < C_FUSE * C_HID; i += blockDim.x) w1[i] = fc1t[i];
+    for (int i = threadIdx.x; i < C_HID * C; i += blockDim.x) w2[i] = fc2t[i];
     if (threadIdx.x < C_HID) b1[threadIdx.x] = fc1b[threadIdx.x];
     if (threadIdx.x < C) b2[threadIdx.x] = fc2b[threadIdx.x];
-    for (int i = threadIdx.x; i < C * C; i += 128) hist[i] = 0;
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    const int t = threadIdx.x, chunk = t >> 3, sub = t & 7;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* g = gbuf + warp * (C_FUSE + C_HID);
+    float* hid = g + C_FUSE;
     const float inv = 1.0f / (float)npx;
-    for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
-        // thread (chunk, sub): pixels sub, sub+8, ... of its 8-channel chunk, 16 bytes per load
-        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const uint4* base = reinterpret_cast<const uint4*>(F) + (n * 16 + chunk) * npx;
-        for (int px = sub; px < npx; px += 8) {
-            const uint4 v = __ldg(base + px);
-            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    const int64_t wstride = (int64_t)gridDim.x * kHeadWarps;
+    for (int64_t n = (int64_t)blockIdx.x * kHeadWarps + warp; n < N; n += wstride) {
+        const uint4* base = reinterpret_cast<const uint4*>(F) + n * 16 * npx;
+        for (int chunk = 0; chunk < 16; ++chunk) {
+            // the 32 lanes sweep the npx pixels of this 8-channel chunk, 16 bytes each (512 B per sweep)
+            float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int px = lane; px < npx; px += 32) {
+                const uint4 v = __ldg(base + chunk * npx + px);
+                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[k]));
-                s[2 * k] += f.x; s[2 * k + 1] += f.y;
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[k]));
+                    s[2 * k] += f.x; s[2 * k + 1] += f.y;
+                }
+            }
+            // exchange-halving reduction: 8 -> 4 -> 2 -> 1 values per lane, then two butterfly steps
+            float t4[4], t2[2], t1;
+            {
+                const bool up = lane & 16;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float send = up ? s[k] : s[k + 4], keep = up ? s[k + 4] : s[k];
+                    t4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            {
+                const bool up = lane & 8;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float send = up ? t4[k] : t4[k + 2], keep = up ? t4[k + 2] : t4[k];
+                    t2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+            }
+            {
+                const bool up = lane & 4;
+                const float send = up ? t2[0] : t2[1], keep = up ? t2[1] : t2[0];
+                t1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+            // lane bits (4,3,2) select the channel: bit4 -> +4, bit3 -> +2, bit2 -> +1
+            if ((lane & 3) == 0) g[chunk * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = t1 * inv;
+        }
+        __syncwarp();
+        float h0 = b1[lane], h1 = b1[lane + 32];
+#pragma unroll 4
+        for (int k4 = 0; k4 < C_FUSE; k4 += 4) {
+            const float4 gv = *reinterpret_cast<const float4*>(g + k4);
+            const float gk[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                h0 = fmaf(gk[e], w1[(k4 + e) * C_HID + lane], h0);
+                h1 = fmaf(gk[e], w1[(k4 + e) * C_HID + lane + 32], h1);
             }
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            s[k] += __shfl_xor_sync(0xffffffffu, s[k], 1);
-            s[k] += __shfl_xor_sync(0xffffffffu, s[k], 2);
-            s[k] += __shfl_xor_sync(0xffffffffu, s[k], 4);
-        }
-        if (sub == 0)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) g[chunk * 8 + k] = s[k] * inv;
-        __syncthreads();
-        if (t < C_HID) {
-            float a = b1[t];
+        hid[lane] = fmaxf(h0, 0.f);
+        hid[lane + 32] = fmaxf(h1, 0.f);
+        __syncwarp();
+        // logits: classes lane and lane + 32 (C <= 64)
+        float l0 = -INFINITY, l1 = -INFINITY;
+        if (lane < C) {
+            float a = b2[lane];
 #pragma unroll 8
-            for (int k = 0; k < C_FUSE; ++k) a = fmaf(g[k], w1[k * C_HID + t], a);
-            hid[t] = fmaxf(a, 0.f);
+            for (int k = 0; k < C_HID; ++k) a = fmaf(hid[k], w2[k * C + lane], a);
+            l0 = a;
+            if (logits_out) logits_out[n * C + lane] = a;
         }
-        __syncthreads();
-        if (t < C) {
-            float a = b2[t];
+        if (lane + 32 < C) {
+            float a = b2[lane + 32];
 #pragma unroll 8
-            for (int k = 0; k < C_HID; ++k) a = fmaf(hid[k], w2[k * C + t], a);
-            lg[t] = a;
-            if (logits_out) logits_out[n * C + t] = a;
+            for (int k = 0; k < C_HID; ++k) a = fmaf(hid[k], w2[k * C + lane + 32], a);
+            l1 = a;
+            if (logits_out) logits_out[n * C + lane + 32] = a;
         }
-        __syncthreads();
-        if (t == 0) {
-            int best = 0;
-            float bv = lg[0];
-            for (int c = 1; c < C; ++c)
-                if (lg[c] > bv) { bv = lg[c]; best = c; }
-            if (pred_out) pred_out[n] = (uint8_t)best;
+        // argmax with torch.max semantics: the first (lowest) index among equal maxima
+        float bv = l0;
+        int bi = lane;
+        if (l1 > bv) { bv = l1; bi = lane + 32; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            if (pred_out) pred_out[n] = (uint8_t)bi;
             if (cm || pred_map) {
                 const int64_t k = idx ? idx[n] : first + n;
-                if (pred_map) pred_map[k] = (uint8_t)best;
+                if (pred_map) pred_map[k] = (uint8_t)bi;
                 if (cm) {
                     const int lab = scene.label[k];
-                    if (lab < C) hist[best * C + lab] += 1;
+                    if (lab < C) atomicAdd(&hist[bi * C + lab], 1u);
                 }
             }
         }
-        // the next iteration's first __syncthreads orders these reads/writes against the reuse of g/hid/lg
+        __syncwarp();
     }
     __syncthreads();
     if (cm)
-        for (int i = threadIdx.x; i < C * C; i += 128)
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x)
             if (hist[i]) atomicAdd(&cm[i], (unsigned long long)hist[i]);
 }
 
@@ -426,14 +472,14 @@ static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat1
 }
 
 static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat16* out, int64_t N, cudaStream_t st, int dbg);
-static int stem_pan_stages(int p) { return p >= 32 ? 2 : tc::kStemMaxStages; }
+static int stem_pan_stages(int p) { (void)p; return tc::kStemMaxStages; }
 static int stem_pan_raw_pitch(int p) { return 4 * p + 8; }
 static size_t stem_pan_smem(int p) {
     const size_t raw = 2ull * (4 * p + 2) * stem_pan_raw_pitch(p) * 4;
-    return (size_t)stem_pan_stages(p) * tc::kStemStage + 4 * tc::kStemCout * 16 + 2 * tc::kStemCout * 4 + 18 * 8 + 16 + raw;
+    return (size_t)stem_pan_stages(p) * tc::kStemStage + tc::kStemWBytes + 2 * tc::kStemCout * 4 + 20 * 8 + 16 + raw;
 }
 static size_t head_smem(int C) {
-    return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + C_FUSE + C_HID + ((C + 3) & ~3)) +
+    return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + kHeadWarps * (C_FUSE + C_HID)) +
            sizeof(unsigned int) * C * C;
 }
 
@@ -442,7 +488,7 @@ static int launch_stems(dmf_net* n, const PatchSrc& src, bool from_scene, int64_
     constexpr int GP = 2;                  // epilogue groups of the PAN stem kernel
     static bool attr_set = false;
     if (!attr_set) {
-        DMF_CUDA(cudaFuncSetAttribute(tc::stem_pan_tc_kernel<GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        DMF_CUDA(cudaFuncSetAttribute(tc::stem_pan_tc_kernel<GP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
     if (which & 1) {
@@ -459,9 +505,9 @@ static int launch_stems(dmf_net* n, const PatchSrc& src, bool from_scene, int64_
         Q.idx = src.idx; Q.first = src.first; Q.patches = src.patches; Q.from_scene = from_scene ? 1 : 0;
         Q.p = n->p; Q.S_l2 = l2(2 * n->p); Q.tpp_l2 = l2(4 * n->p * n->p / 128); Q.N = N;
         Q.n_stage = stem_pan_stages(n->p); Q.raw_pitch = stem_pan_raw_pitch(n->p);
-        Q.w = n->w_pan1; Q.scale = n->sc_pan1; Q.shift = n->sh_pan1; Q.out = B1;
+        Q.w = n->w_pan1; Q.shift = n->sh_pan1; Q.out = B1;
         const int grid = (int)std::min<int64_t>(N, num_sms());
-        tc::stem_pan_tc_kernel<GP><<<grid, 320 + 128 * GP, stem_pan_smem(n->p), st>>>(Q);
+        tc::stem_pan_tc_kernel<GP, 4><<<grid, 320 + 128 * GP, stem_pan_smem(n->p), st>>>(Q);
         DMF_LAUNCHED();
     }
     return DMF_OK;
@@ -485,8 +531,8 @@ static int forward_chunk(dmf_net* n, const PatchSrc& src, bool from_scene, int64
     DMF_TRY(run_layer(n, 3, n->L[3].map, n->F, N, st, 0));
     if (tm) cudaEventRecord(n->ev[6], st);
     const int npx = (n->p / 2) * (n->p / 2);
-    const int grid = (int)std::min<int64_t>(N, (int64_t)num_sms() * 4);
-    head_kernel<<<grid, 128, head_smem(n->C), st>>>(n->F, N, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, src.scene,
+    const int grid = (int)std::min<int64_t>((N + kHeadWarps - 1) / kHeadWarps, (int64_t)num_sms() * 4);
+    head_kernel<<<grid, 32 * kHeadWarps, head_smem(n->C), st>>>(n->F, N, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, src.scene,
                                                     src.idx, src.first, logits, pred, (unsigned long long*)cm, pred_map);
     DMF_LAUNCHED();
     if (tm) {
@@ -562,18 +608,23 @@ int dmf_net_finalize(dmf_net* n, void* stream) {
     {
         auto* w = param(n, "pan1.0.weight", (size_t)C_PAN1 * 9);
         if (!w) return DMF_ERR_STATE;
-        // K = 32 per output channel: k = 2t, 2t+1 -> w_hi[t]; k = 18+t -> w_lo[t]; rest 0   (stem_tc.cuh)
-        std::vector<__nv_bfloat16> pk((size_t)4 * C_PAN1 * 8, __float2bfloat16_rn(0.f));
+        // B operand of the PAN stem (stem_tc.cuh): row n = q*32 + co, K = 48 over the 4x4 input region of a
+        // pooled pixel: region pixel i = 4*ry + rx carries tap (ry - qy, rx - qx) of window position q
+        // (zero outside the 3x3); k = 2i, 2i+1 -> w_hi, k = 32 + i -> w_lo.
+        std::vector<__nv_bfloat16> pk((size_t)tc::kStemKch * 128 * 8, __float2bfloat16_rn(0.f));
         std::vector<float> sc, sh;
-        for (int co = 0; co < C_PAN1; ++co)
-            for (int t = 0; t < 9; ++t) {
-                const float wv = (*w)[co * 9 + t];
-                const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
-                const __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
-                auto at = [&](int k) -> __nv_bfloat16& { return pk[((size_t)(k / 8) * C_PAN1 + co) * 8 + k % 8]; };
-                at(2 * t) = hi; at(2 * t + 1) = hi; at(18 + t) = lo;
-            }
         DMF_TRY(fold_bn(n, "pan1", C_PAN1, sc, sh));
+        for (int q = 0; q < 4; ++q)
+            for (int co = 0; co < C_PAN1; ++co)
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float wv = (*w)[co * 9 + dy * 3 + dx] * sc[co];    // BN scale folded in fp32, before the split
+                        const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+                        const __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+                        const int i = 4 * ((q >> 1) + dy) + (q & 1) + dx, row = q * C_PAN1 + co;
+                        auto at = [&](int k) -> __nv_bfloat16& { return pk[((size_t)(k / 8) * 128 + row) * 8 + k % 8]; };
+                        at(2 * i) = hi; at(2 * i + 1) = hi; at(32 + i) = lo;
+                    }
         DMF_TRY(to_device(&n->w_pan1, pk)); DMF_TRY(to_device(&n->sc_pan1, sc)); DMF_TRY(to_device(&n->sh_pan1, sh));
     }
     // --- tensor-core layers
@@ -651,9 +702,9 @@ int dmf_net_forward_patches(dmf_net* n, const float* ms_dev, const float* pan_de
         DMF_TRY(run_layer(n, 2, n->L[2].map, n->CAT, nb, st, 0));
         DMF_TRY(run_layer(n, 3, n->L[3].map, n->F, nb, st, 0));
         const int npx = (p / 2) * (p / 2);
-        const int grid = (int)std::min<int64_t>(nb, (int64_t)num_sms() * 4);
+        const int grid = (int)std::min<int64_t>((nb + kHeadWarps - 1) / kHeadWarps, (int64_t)num_sms() * 4);
         dmf_scene none{};
-        head_kernel<<<grid, 128, head_smem(n->C), st>>>(n->F, nb, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, none, nullptr,
+        head_kernel<<<grid, 32 * kHeadWarps, head_smem(n->C), st>>>(n->F, nb, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, none, nullptr,
                                                         0, logits_out_dev + o * n->C, nullptr, nullptr, nullptr);
         DMF_LAUNCHED();
     }

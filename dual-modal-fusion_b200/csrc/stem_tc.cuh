@@ -3,21 +3,26 @@
 //
 // A 1-channel 3x3 convolution has K = 9, far too thin for tcgen05 as a plain implicit GEMM, and the
 // first CUDA-core version of this stem was the most expensive stage of the network (23 % of the
-// time for 2 % of the FLOPs).  Here the operand is BUILT in shared memory:
+// time for 2 % of the FLOPs).  Here the operand is BUILT in shared memory, one row per POOLED pixel:
 //   * a loader warp streams the fp32 window rows of the NEXT patch into a zero-bordered,
 //     double-buffered staging tile with cp.async.bulk (one 16-byte-aligned row per copy);
-//   * builder warps split every tap into bf16 hi + lo (x = hi + lo to ~2^-16) and write, for every
-//     output pixel, one K = 32 row
-//         [ (hi_t, lo_t) t=0..8 | (hi_0,hi_1) (hi_2,hi_3) (hi_4,hi_5) (hi_6,hi_7) (hi_8,0) | 0 0 ]
-//     matching weights [ (w_hi_t, w_hi_t) | w_lo pairs | 0 ], i.e. x_hi*w_hi + x_lo*w_hi + x_hi*w_lo:
-//     fp32-grade products from two bf16 K=16 MMAs;
-//   * rows are grouped by POOLED pixel: the four pixels of a 2x2 pooling window go to four separate
-//     A matrices whose products land in four 32-column blocks of the same TMEM accumulator, so the
-//     epilogue thread that owns a pooled pixel finds its 4 candidates in its own TMEM lane: BN affine,
-//     max, ReLU, bf16, one 16-byte store per 8 channels — no shuffles.
+//   * builder warps convert the window IN PLACE to packed {hi, lo} bf16 pairs (x = hi + lo to ~2^-16)
+//     and then write, per pooled pixel, the 4x4 input region that its 2x2 pooling window touches as
+//     one K = 48 row:  [ (hi_i, lo_i) i=0..15 | (hi_0,hi_1) ... (hi_14,hi_15) ];
+//   * the B operand has N = 128 rows = 4 window positions x 32 channels: row (q, co) holds the 3x3
+//     kernel of channel co placed at offset (qy, qx) inside the 4x4 region, as
+//     [ (w_hi, w_hi) | w_lo ], i.e. x_hi*w_hi + x_lo*w_hi + x_hi*w_lo: fp32-grade products.  The folded
+//     BatchNorm scale is multiplied into the fp32 weights before the split;
+//   * three M128 x N128 x K16 MMAs per 128 pooled pixels put the four candidates of every pooled
+//     pixel into four 32-column blocks of its own TMEM lane: the epilogue is max -> + shift -> ReLU ->
+//     bf16 -> 16-byte stores, no shuffles.
+// (An earlier layout with one K = 32 row per output pixel and 8 N = 32 MMAs per tile was shared-memory
+// bandwidth bound: ~860 smem wavefronts per tile against ~420 here.)
 // Roles (64 + 256 + 128*G threads): warp 0 = MMA issuer / TMEM owner, warp 1 = window loader,
-// warps 2..9 = builders, then G epilogue groups of 4 warps.  Persistent over patches; 2-3 stage A ring
-// of 32 KB.
+// warps 2..9 = builders in NT teams (team k builds the tiles with tile % NT == k, so NT tiles are in
+// flight and the LDS -> PRMT -> STS -> proxy-fence -> arrive latency chain of one tile overlaps the
+// others; the ncu profile of the single-team version showed exactly that chain exposed), then G
+// epilogue groups of 4 warps.  Persistent over patches; NT..4 stage A ring of 32 KB.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -25,9 +30,10 @@ namespace dmf {
 namespace tc {
 
 constexpr int kStemCout = 32;
-constexpr int kStemMaxStages = 3;
-constexpr int kStemAq = 4 * 128 * 16;            // one A matrix: 4 k-chunks x 128 rows x 16 B
-constexpr int kStemStage = 4 * kStemAq;          // four window positions
+constexpr int kStemMaxStages = 4;
+constexpr int kStemKch = 6;                      // K = 48 = 6 chunks of 8 bf16
+constexpr int kStemStage = kStemKch * 128 * 16;  // A tile: 6 k-chunks x 128 rows x 16 B = 12 KB
+constexpr int kStemWBytes = kStemKch * 128 * 16; // B: 6 k-chunks x (4 positions x 32 channels) x 16 B
 
 struct StemPanParams {
     // source: scene windows (idx == null -> consecutive pixels from `first`) or materialised patches
@@ -43,53 +49,52 @@ struct StemPanParams {
     int n_stage;                   // A ring depth (2 or 3)
     int raw_pitch;                 // floats per staging row: 4 (left pad, keeps rows 16-byte aligned) + 4p + 4
     int64_t N;
-    const __nv_bfloat16* w;        // packed [4 k-chunks][32 co][8]
-    const float* scale;
-    const float* shift;
+    const __nv_bfloat16* w;        // packed [6 k-chunks][128 = (q, co)][8]
+    const float* shift;            // folded BatchNorm shift (the scale lives in the weights)
     __nv_bfloat16* out;            // [N][4][2p][2p][8]
 };
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr)
                  : "memory");
 }
 
-template <int G>
+template <int G, int NT>
 __global__ void __launch_bounds__(320 + 128 * G, 1) stem_pan_tc_kernel(const StemPanParams P) {
     constexpr int kBuilders = 256;
+    constexpr int kTeam = kBuilders / NT;            // threads per builder team
+    constexpr int kRows = 128 / kTeam;               // tile rows per builder thread
+    static_assert(NT == 2 || NT == 4, "builder teams");
     constexpr uint32_t TMEM_USED = G * 128;
     constexpr uint32_t TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int PW = 4 * P.p, S = 2 * P.p, RP = P.raw_pitch;
     const int raw_floats = (PW + 2) * RP;                                 // one staging buffer
     uint8_t* a_s = smem;                                                  // n_stage x kStemStage
-    uint8_t* w_s = a_s + P.n_stage * kStemStage;                          // 2 KB
-    float* scale_s = reinterpret_cast<float*>(w_s + 4 * kStemCout * 16);
-    float* shift_s = scale_s + kStemCout;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + kStemCout);    // full[3] empty[3] tfull[4] tempty[4] rawfull[2] rawempty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint8_t* w_s = a_s + P.n_stage * kStemStage;                          // 12 KB
+    float* shift_s = reinterpret_cast<float*>(w_s + kStemWBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + 2 * kStemCout);    // full[4] empty[4] tfull[4] tempty[4] rawfull[2] rawempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
     float* raw = reinterpret_cast<float*>(tmem_slot + 4);                 // 2 x (PW+2) x RP fp32, zero border
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (3 + s); };
-    auto tfull_bar = [&](int a) { return bar0 + 8u * (6 + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (10 + a); };
-    auto rawfull_bar = [&](int b) { return bar0 + 8u * (14 + b); };
-    auto rawempty_bar = [&](int b) { return bar0 + 8u * (16 + b); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (8 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (12 + a); };
+    auto rawfull_bar = [&](int b) { return bar0 + 8u * (16 + b); };
+    auto rawempty_bar = [&](int b) { return bar0 + 8u * (18 + b); };
 
-    for (int i = threadIdx.x; i < 4 * kStemCout * 4; i += blockDim.x)    // 2 KB of weights
+    for (int i = threadIdx.x; i < kStemWBytes / 4; i += blockDim.x)      // 12 KB of weights
         reinterpret_cast<uint32_t*>(w_s)[i] = reinterpret_cast<const uint32_t*>(P.w)[i];
     for (int i = threadIdx.x; i < 2 * raw_floats; i += blockDim.x) raw[i] = 0.f;   // borders stay zero for good
-    if (threadIdx.x < kStemCout) {
-        scale_s[threadIdx.x] = P.scale[threadIdx.x];
-        shift_s[threadIdx.x] = P.shift[threadIdx.x];
-    }
+    if (threadIdx.x < kStemCout) shift_s[threadIdx.x] = P.shift[threadIdx.x];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), kBuilders); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), kTeam / 32); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < G; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
         for (int b = 0; b < 2; ++b) { mbar_init(rawfull_bar(b), 1); mbar_init(rawempty_bar(b), kBuilders); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -110,9 +115,9 @@ __global__ void __launch_bounds__(320 + 128 * G, 1) stem_pan_tc_kernel(const Ste
 
     if (warp == 0) {
         // ------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(128, kStemCout);
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
         const bool leader = elect_one();
-        const uint64_t w_desc0 = umma_desc(smem_u32(w_s), kStemCout * 16, 128);
+        const uint64_t w_desc0 = umma_desc(smem_u32(w_s), 128 * 16, 128);
         int st = 0;
         uint32_t ph = 0;
         for (int64_t i = 0; i < n_local; ++i) {
@@ -124,11 +129,9 @@ __global__ void __launch_bounds__(320 + 128 * G, 1) stem_pan_tc_kernel(const Ste
             const uint32_t d0 = tmem_base + (uint32_t)(acc * 128);
             if (leader) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        umma_bf16(d0 + q * kStemCout, a_desc0 + (uint64_t)((q * kStemAq + 2 * j * 128 * 16) >> 4),
-                                  w_desc0 + (uint64_t)((2 * j * kStemCout * 16) >> 4), idesc, j ? 1u : 0u);
+                for (int j = 0; j < kStemKch / 2; ++j)
+                    umma_bf16(d0, a_desc0 + (uint64_t)((2 * j * 128 * 16) >> 4), w_desc0 + (uint64_t)((2 * j * 128 * 16) >> 4), idesc,
+                              j ? 1u : 0u);
                 umma_commit(empty_bar(st));
                 umma_commit(tfull_bar(acc));
             }
@@ -161,42 +164,55 @@ __global__ void __launch_bounds__(320 + 128 * G, 1) stem_pan_tc_kernel(const Ste
     } else if (warp <= 9) {
         // ------------------------------------------------ builders: hi/lo split + im2col rows
         const int bt = threadIdx.x - 64;                       // 0..255
-        const int m = bt & 127, qh = bt >> 7;                  // this thread builds q = qh and q = qh + 2
-        int st = 0;
-        uint32_t ph = 1;
+        const int team = bt / kTeam, r0 = bt % kTeam;
         for (int64_t pl = 0; pl < n_patches; ++pl) {
             const int b = (int)(pl & 1);
-            const float* win = raw + b * raw_floats;
+            uint32_t* win = reinterpret_cast<uint32_t*>(raw + b * raw_floats);
             mbar_wait(rawfull_bar(b), (uint32_t)((pl >> 1) & 1));
-            for (int t = 0; t < tpp; ++t) {
-                mbar_wait(empty_bar(st), ph);
-                const int pp = t * 128 + m;                     // pooled pixel of this row
-                const int prow = pp >> P.S_l2, pcol = pp & (S - 1);
+            // fp32 -> packed {hi, lo} bf16, in place, interior only (the zero border is already 0 = {0, 0})
+            for (int i = bt; i < PW * (PW / 4); i += kBuilders) {
+                const int r = i / (PW / 4), c4 = i - r * (PW / 4);
+                uint4* cell = reinterpret_cast<uint4*>(win + (r + 1) * RP + 4) + c4;
+                const uint4 u = *cell;
+                const float f[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float hi = __bfloat162float(__float2bfloat16_rn(f[e]));
+                    o[e] = pack_bf16x2(hi, f[e] - hi);
+                }
+                *cell = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int t = team; t < tpp; t += NT) {
+                const int64_t i = (pl << P.tpp_l2) + t;         // tile counter of this CTA -> ring slot and phase
+                const int st = (int)(i % P.n_stage);
+                mbar_wait(empty_bar(st), (uint32_t)((i / P.n_stage) & 1) ^ 1);
                 uint8_t* stage = a_s + (size_t)st * kStemStage;
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const int q = qh + 2 * it;                  // window position: qy = q >> 1, qx = q & 1
-                    // pixel (y, x) = (2 prow + qy, 2 pcol + qx); tap (dy, dx) sits at staging row y + dy, column x + dx + 3
-                    const float* wp = win + (2 * prow + (q >> 1)) * RP + 2 * pcol + (q & 1) + 3;
-                    uint32_t W9[9];
+                for (int rr = 0; rr < kRows; ++rr) {
+                    const int m = r0 + rr * kTeam;              // tile row = pooled pixel t*128 + m
+                    const int pp = t * 128 + m;
+                    const int prow = pp >> P.S_l2, pcol = pp & (S - 1);
+                    // 4x4 input region of the pooled pixel: rows 2 prow - 1 .. 2 prow + 2, cols 2 pcol - 1 .. 2 pcol + 2
+                    // = staging rows 2 prow .. 2 prow + 3, staging columns 2 pcol + 3 .. 2 pcol + 6
+                    const uint32_t* wp = win + (2 * prow) * RP + 2 * pcol + 3;
+                    uint32_t R[16];
 #pragma unroll
-                    for (int tp = 0; tp < 9; ++tp) {
-                        const float v = wp[(tp / 3) * RP + tp % 3];
-                        const float hi = __bfloat162float(__float2bfloat16_rn(v));
-                        W9[tp] = pack_bf16x2(hi, v - hi);
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(stage + q * kStemAq) + m;
-                    dst[0] = make_uint4(W9[0], W9[1], W9[2], W9[3]);
-                    dst[128] = make_uint4(W9[4], W9[5], W9[6], W9[7]);
-                    dst[256] = make_uint4(W9[8], __byte_perm(W9[0], W9[1], 0x5410), __byte_perm(W9[2], W9[3], 0x5410),
-                                          __byte_perm(W9[4], W9[5], 0x5410));
-                    dst[384] = make_uint4(__byte_perm(W9[6], W9[7], 0x5410), W9[8] & 0xffffu, 0u, 0u);
+                    for (int e = 0; e < 16; ++e) R[e] = wp[(e >> 2) * RP + (e & 3)];
+                    uint4* dst = reinterpret_cast<uint4*>(stage) + m;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[c * 128] = make_uint4(R[4 * c], R[4 * c + 1], R[4 * c + 2], R[4 * c + 3]);
+                    dst[4 * 128] = make_uint4(__byte_perm(R[0], R[1], 0x5410), __byte_perm(R[2], R[3], 0x5410),
+                                              __byte_perm(R[4], R[5], 0x5410), __byte_perm(R[6], R[7], 0x5410));
+                    dst[5 * 128] = make_uint4(__byte_perm(R[8], R[9], 0x5410), __byte_perm(R[10], R[11], 0x5410),
+                                              __byte_perm(R[12], R[13], 0x5410), __byte_perm(R[14], R[15], 0x5410));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(full_bar(st));
-                if (++st == P.n_stage) { st = 0; ph ^= 1; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(st));       // one arrival per builder warp of the team
             }
-            mbar_arrive(rawempty_bar(b));                       // this thread no longer reads staging buffer b
+            mbar_arrive(rawempty_bar(b));                       // this thread no longer touches staging buffer b
         }
     } else {
         // ------------------------------------------------ epilogue (G groups of 4 warps)
@@ -211,26 +227,31 @@ __global__ void __launch_bounds__(320 + 128 * G, 1) stem_pan_tc_kernel(const Ste
             mbar_wait(tfull_bar(eg), (uint32_t)((i / G) & 1));
             tc_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v0[8], v1[8], v2[8], v3[8];
-                tmem_ld8(t_row + ch * 8, v0);
-                tmem_ld8(t_row + 32 + ch * 8, v1);
-                tmem_ld8(t_row + 64 + ch * 8, v2);
-                tmem_ld8(t_row + 96 + ch * 8, v3);
+            for (int hf = 0; hf < 2; ++hf) {                  // 16 channels at a time
+                uint32_t v0[16], v1[16], v2[16], v3[16];
+                tmem_ld16(t_row + hf * 16, v0);
+                tmem_ld16(t_row + 32 + hf * 16, v1);
+                tmem_ld16(t_row + 64 + hf * 16, v2);
+                tmem_ld16(t_row + 96 + hf * 16, v3);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const float4 sc0 = *reinterpret_cast<const float4*>(scale_s + ch * 8), sc1 = *reinterpret_cast<const float4*>(scale_s + ch * 8 + 4);
-                const float4 sh0 = *reinterpret_cast<const float4*>(shift_s + ch * 8), sh1 = *reinterpret_cast<const float4*>(shift_s + ch * 8 + 4);
-                const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-                const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-                float r[8];
+                uint32_t pk[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float a = fmaxf(fmaf(__uint_as_float(v0[k]), scv[k], shv[k]), fmaf(__uint_as_float(v1[k]), scv[k], shv[k]));
-                    const float c = fmaxf(fmaf(__uint_as_float(v2[k]), scv[k], shv[k]), fmaf(__uint_as_float(v3[k]), scv[k], shv[k]));
-                    r[k] = fmaxf(fmaxf(a, c), 0.f);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 sh = *reinterpret_cast<const float4*>(shift_s + hf * 16 + 4 * k4);
+                    const float shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                    float r[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 4 * k4 + e;
+                        const float mx = fmaxf(fmaxf(__uint_as_float(v0[k]), __uint_as_float(v1[k])),
+                                               fmaxf(__uint_as_float(v2[k]), __uint_as_float(v3[k])));
+                        r[e] = fmaxf(mx + shv[e], 0.f);
+                    }
+                    pk[2 * k4] = pack_bf16x2(r[0], r[1]);
+                    pk[2 * k4 + 1] = pack_bf16x2(r[2], r[3]);
                 }
-                *reinterpret_cast<uint4*>(obase + (int64_t)ch * (S * S) * 8) =
-                    make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+                *reinterpret_cast<uint4*>(obase + (int64_t)(2 * hf) * (S * S) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(obase + (int64_t)(2 * hf + 1) * (S * S) * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
             tc_fence_before();
             __syncwarp();
