@@ -106,6 +106,15 @@ def cpu_reference_run(wl, budget_s, steps=1, warmup=0):
 
 
 def main():
+    # stdout carries exactly one JSON line: park the real fd and point fd 1 at stderr while libraries
+    # (NCCL's version banner, tqdm, ...) are active
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + '\n').encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
@@ -129,7 +138,7 @@ def main():
             return
         per_step = max(2.0, min(args.cpu_budget_s, 120.0 / max(1, args.steps + args.warmup)))
         v, cores, desc, ms_step = cpu_reference_run(wl, per_step, steps=args.steps, warmup=min(args.warmup, 1))
-        print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        emit(({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
                           'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
                           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
                           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
@@ -204,16 +213,22 @@ def main():
     pm_host = torch.empty((H, W), dtype=torch.uint8).pin_memory()
     cm_pin = torch.empty((C, C), dtype=torch.int64).pin_memory()
 
+    lab_pin = torch.from_numpy(label).pin_memory()
+    e2e_scene = dmf.Scene.from_raw(ms_pin, pan_pin, P, dev)         # buffers reused by every step (same-size scenes)
+    e2e_pm = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    e2e_cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+
     def e2e_step():
-        sc = dmf.Scene.from_raw(ms_pin, pan_pin, P, dev)
-        sc.set_labels(label)
-        pm, m = handle.infer_scene(sc, r0, r1)
+        """host rasters -> H2D -> normalise/pad -> fused inference -> D2H label band + matrix -> OA/AA/Kappa"""
+        e2e_scene.update_raw(ms_pin, pan_pin)
+        e2e_scene.set_labels(lab_pin)
+        e2e_cm.zero_()
+        handle.infer_scene(e2e_scene, r0, r1, pred_map=e2e_pm, cm=e2e_cm)
         if world > 1:
-            dist.all_reduce(m)
-        pm_host[r0:r1].copy_(pm[r0:r1], non_blocking=True)
-        cm_pin.copy_(m, non_blocking=True)
+            dist.all_reduce(e2e_cm)
+        pm_host[r0:r1].copy_(e2e_pm[r0:r1], non_blocking=True)
+        cm_pin.copy_(e2e_cm, non_blocking=True)
         torch.cuda.synchronize()
-        sc.close()
         with open(os.devnull, 'w') as null, _redirect(null):
             return aa_oa(cm_pin.numpy().astype(np.float64))
 
@@ -240,15 +255,22 @@ def main():
     n_chunks = -(-n_local // args.max_batch)
     conv = lambda cin, cout, k, h: 2 * cin * cout * k * k * h * h
     kernels = {   # kernel instance -> (stage keys, algorithmic FLOPs per pixel, launches per chunk)
-        'conv_tc_kernel<64,128,9,pool> (ms2 + pan3)': (['conv_ms2', 'conv_pan3'], 2 * conv(64, 128, 3, P), 2),
-        'conv_tc_kernel<32,64,9,pool> (pan2)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
-        'conv_tc_kernel<256,128,1> (fuse)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
+        'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': (['conv_ms2', 'conv_pan3'], 2 * conv(64, 128, 3, P), 2),
+        'conv_tc_kernel<32,64,9,pool,G=4> (pan2)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
+        'conv_tc_kernel<256,128,1,G=2> (fuse)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
     }
     name, (keys, fl_px, per_chunk) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
     k_ms = sum(stage[k] for k in keys)
     achieved = fl_px * n_local / (k_ms / 1e3) / 1e12
+    traffic = None            # dram bytes per launch of this kernel from the committed ncu --set full capture
+    try:
+        prof = json.load(open(os.path.join(REPO, 'profiles', 'r01_ncu_summary.json')))
+        if wl_key == prof.get('workload') and args.max_batch == prof.get('chunk_pixels'):
+            traffic = prof['kernels'].get(name.split(' ')[0], {}).get('dram_bytes_per_launch')
+    except Exception:
+        pass
     roofline = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+                'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': traffic,
                 'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
                 'avg_launch_ms': k_ms / (n_chunks * per_chunk), 'launches': n_chunks * per_chunk,
                 'flops_per_launch': fl_px * n_local / (n_chunks * per_chunk),
@@ -263,7 +285,7 @@ def main():
     if rank == 0:
         config.update({'global_pixels': npix_total, 'chunk_pixels': args.max_batch, 'row_band_rank0': [r0, r1],
                        'flops_per_pixel': handle.flops_per_patch, 'OA_AA_Kappa': [float(result[1]), float(result[0]), float(result[2])]})
-        print(json.dumps({'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        emit(({'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                           'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
                           'dtype': 'bf16', 'data': 'synthetic', 'config': config, 'clocks': clk.summary(),
                           'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},

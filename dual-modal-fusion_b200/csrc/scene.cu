@@ -168,8 +168,23 @@ __global__ void repitch_cast_kernel(const T* __restrict__ in, int rows, int64_t 
     }
 }
 
+// keep freed stream-ordered allocations cached in the device's default pool (the default threshold of 0
+// hands them back to the driver at every synchronisation, which costs 100+ ms for scene-sized buffers)
+static void keep_pool_memory() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done = true;
+}
+
 static int upload(const void* src, size_t bytes, int on_device, cudaStream_t st, void** tmp, const void** dev) {
     *tmp = nullptr;
+    keep_pool_memory();
     if (on_device) { *dev = src; return DMF_OK; }
     DMF_CUDA(cudaMallocAsync(tmp, bytes, st));
     DMF_CUDA(cudaMemcpyAsync(*tmp, src, bytes, cudaMemcpyHostToDevice, st));
@@ -270,24 +285,35 @@ int dmf_normalize_pad(const void* raw_dev, int raw_dtype, int H, int W, int band
                              (int64_t)(W + P - 1) * bands, (cudaStream_t)stream);
 }
 
-int dmf_scene_create_raw(dmf_scene** out, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int H, int W,
-                         int p, int on_device, void* stream) {
-    DMF_REQUIRE(out && ms && pan && H > 0 && W > 0 && p > 0, "scene_create_raw: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    dmf_scene* s = new dmf_scene();
-    int rc = scene_alloc(s, H, W, p);
-    if (rc != DMF_OK) { dmf_scene_destroy(s); return rc; }
-    void *t1, *t2;
+static int scene_fill_raw(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int on_device,
+                          cudaStream_t st) {
+    const int H = s->H, W = s->W, p = s->p;
+    void *t1 = nullptr, *t2 = nullptr;
     const void *dms, *dpan;
-    rc = upload(ms, dtype_size(ms_dtype) * 4 * (size_t)H * W, on_device, st, &t1, &dms);
+    int rc = upload(ms, dtype_size(ms_dtype) * 4 * (size_t)H * W, on_device, st, &t1, &dms);
     if (rc == DMF_OK) rc = upload(pan, dtype_size(pan_dtype) * 16 * (size_t)H * W, on_device, st, &t2, &dpan);
     if (rc == DMF_OK) rc = normalize_pad_any(dms, ms_dtype, H, W, 4, p, s->ms, DMF_F32, (int64_t)s->Wp * 4, st);
     if (rc == DMF_OK) rc = normalize_pad_any(dpan, pan_dtype, 4 * H, 4 * W, 1, 4 * p, s->pan, DMF_F32, s->pan_pitch, st);
-    if (rc == DMF_OK && t1) cudaFreeAsync(t1, st);
-    if (rc == DMF_OK && t2) cudaFreeAsync(t2, st);
+    if (t1) cudaFreeAsync(t1, st);
+    if (t2) cudaFreeAsync(t2, st);
+    return rc;
+}
+
+int dmf_scene_create_raw(dmf_scene** out, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int H, int W,
+                         int p, int on_device, void* stream) {
+    DMF_REQUIRE(out && ms && pan && H > 0 && W > 0 && p > 0, "scene_create_raw: bad argument");
+    dmf_scene* s = new dmf_scene();
+    int rc = scene_alloc(s, H, W, p);
+    if (rc == DMF_OK) rc = scene_fill_raw(s, ms, ms_dtype, pan, pan_dtype, on_device, (cudaStream_t)stream);
     if (rc != DMF_OK) { dmf_scene_destroy(s); return rc; }
     *out = s;
     return DMF_OK;
+}
+
+int dmf_scene_update_raw(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int on_device,
+                         void* stream) {
+    DMF_REQUIRE(s && ms && pan, "scene_update_raw: bad argument");
+    return scene_fill_raw(s, ms, ms_dtype, pan, pan_dtype, on_device, (cudaStream_t)stream);
 }
 
 static int copy_padded(const void* src, int dtype, int rows, int64_t row_elems, int64_t pitch, float* dst,

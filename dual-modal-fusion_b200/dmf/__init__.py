@@ -84,6 +84,23 @@ class Scene:
                     torch.cuda.current_stream().synchronize()
         return cls(h, H, W, p, device)
 
+    def update_raw(self, ms, pan):
+        """Re-fill this scene from new rasters of the same shape (pinned CPU or CUDA tensors, or ndarrays)."""
+        code = {torch.uint8: U8, torch.int16: U16, torch.uint16: U16, torch.float32: F32, torch.float64: F64}
+        with torch.cuda.device(self.device):
+            if isinstance(ms, np.ndarray):
+                a, b = np.ascontiguousarray(ms), np.ascontiguousarray(pan)
+                check(lib.dmf_scene_update_raw(self._h, a.ctypes.data_as(C.c_void_p), np_dtype_code(a),
+                                               b.ctypes.data_as(C.c_void_p), np_dtype_code(b), 0, _stream()))
+                torch.cuda.current_stream().synchronize()
+            else:
+                a, b = ms.contiguous(), pan.contiguous()
+                assert tuple(a.shape) == (self.H, self.W, 4) and tuple(b.shape) == (4 * self.H, 4 * self.W)
+                check(lib.dmf_scene_update_raw(self._h, _ptr(a), code[a.dtype], _ptr(b), code[b.dtype], 1 if a.is_cuda else 0, _stream()))
+                if not a.is_cuda and not (a.is_pinned() and b.is_pinned()):
+                    torch.cuda.current_stream().synchronize()
+        return self
+
     @classmethod
     def from_padded(cls, ms_pad, pan_pad, p, device='cuda:0'):
         """ms_pad / pan_pad exactly as data_padding() returns them (float64 or float32 ndarrays)."""
@@ -100,11 +117,19 @@ class Scene:
         return cls(h, H, W, p, device)
 
     def set_labels(self, label):
-        lab = np.ascontiguousarray(label, dtype=np.uint8)
-        assert lab.shape == (self.H, self.W)
+        """label: uint8 [H,W] ndarray, or a (pinned) CPU / CUDA uint8 tensor."""
         with torch.cuda.device(self.device):
-            check(lib.dmf_scene_set_labels(self._h, lab.ctypes.data_as(C.c_void_p), 0, _stream()))
-            torch.cuda.current_stream().synchronize()
+            if isinstance(label, torch.Tensor):
+                lab = label.contiguous()
+                assert lab.dtype == torch.uint8 and tuple(lab.shape) == (self.H, self.W)
+                check(lib.dmf_scene_set_labels(self._h, _ptr(lab), 1 if lab.is_cuda else 0, _stream()))
+                if not lab.is_cuda and not lab.is_pinned():
+                    torch.cuda.current_stream().synchronize()
+            else:
+                lab = np.ascontiguousarray(label, dtype=np.uint8)
+                assert lab.shape == (self.H, self.W)
+                check(lib.dmf_scene_set_labels(self._h, lab.ctypes.data_as(C.c_void_p), 0, _stream()))
+                torch.cuda.current_stream().synchronize()
         self.has_labels = True
 
     def set_mspan(self, mspan_pad):

@@ -20,6 +20,7 @@ SIGNATURES = {
     'dmf_launch_count': (i64, []),
     'dmf_normalize_pad': (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     'dmf_scene_create_raw': (i32, [C.POINTER(vp), vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    'dmf_scene_update_raw': (i32, [vp, vp, i32, vp, i32, i32, vp]),
     'dmf_scene_create_padded': (i32, [C.POINTER(vp), vp, vp, i32, i32, i32, i32, i32, vp]),
     'dmf_scene_set_mspan': (i32, [vp, vp, i32, i32, vp]),
     'dmf_scene_set_labels': (i32, [vp, vp, i32, vp]),

@@ -74,6 +74,10 @@ int dmf_normalize_pad(const void* raw_dev, int raw_dtype, int H, int W, int band
  * pointers are host memory (copied with cudaMemcpyAsync), 1 if already on the device. */
 int dmf_scene_create_raw(dmf_scene** out, const void* ms, int ms_dtype, const void* pan, int pan_dtype,
                          int H, int W, int p, int on_device, void* stream);
+/* Re-fill an existing scene with new rasters of the same H, W, p (no allocation: same-size scenes in a
+ * loop, e.g. tiles of a mosaic). */
+int dmf_scene_update_raw(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype,
+                         int on_device, void* stream);
 /* Build a device scene from ALREADY normalised+padded rasters as data_padding() returns them:
  * ms_pad[H+p-1][W+p-1][4], pan_pad[4H+4p-1][4W+4p-1]; dtype DMF_F32 or DMF_F64 (cast to f32 with
  * round-to-nearest, the cast dataset_dual applies per patch, train/dataset.py:183-184). */

@@ -165,3 +165,15 @@ def test_scatter_and_paint(dmf):
     ref = orc.scatter_labels(np.zeros((H, W)), idx // W, idx % W, pred)
     eq(lm.cpu().numpy(), ref.astype(np.uint8))
     eq(dmf.paint_labels(lm, colors).cpu().numpy(), orc.paint(ref, colors))
+
+
+def test_scene_update_in_place_matches_fresh_scene(dmf):
+    """dmf_scene_update_raw re-fills an existing scene (new min/max, new padding) without reallocating."""
+    p, H, W = 16, 40, 44
+    ms1, pan1, _ = orc.synthetic_scene(H, W, 5, seed=1)
+    ms2, pan2, _ = orc.synthetic_scene(H, W, 5, seed=2, blocky=True)
+    sc = dmf.Scene.from_raw(ms1, pan1, p, DEV)
+    sc.update_raw(torch.from_numpy(ms2.view(np.int16)).pin_memory(), torch.from_numpy(pan2.view(np.int16)).pin_memory())
+    torch.cuda.synchronize()
+    eq(sc.export(0).cpu().numpy(), orc.data_padding(ms2, p).astype(np.float32))
+    eq(sc.export(1).cpu().numpy(), orc.data_padding(pan2, p).astype(np.float32))
