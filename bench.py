@@ -259,6 +259,9 @@ def main():
         'conv_tc_kernel<32,64,9,pool,G=4> (pan2)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
         'conv_tc_kernel<256,128,1,G=2> (fuse)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
     }
+    ncu_key = {'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': 'tc::conv_tc_kernel<64,128,9,1,3,1>',
+               'conv_tc_kernel<32,64,9,pool,G=4> (pan2)': 'tc::conv_tc_kernel<32,64,9,1,4,1>',
+               'conv_tc_kernel<256,128,1,G=2> (fuse)': 'tc::conv_tc_kernel<256,128,1,0,2,1>'}
     name, (keys, fl_px, per_chunk) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
     k_ms = sum(stage[k] for k in keys)
     achieved = fl_px * n_local / (k_ms / 1e3) / 1e12
@@ -266,7 +269,7 @@ def main():
     try:
         prof = json.load(open(os.path.join(REPO, 'profiles', 'r01_ncu_summary.json')))
         if wl_key == prof.get('workload') and args.max_batch == prof.get('chunk_pixels'):
-            traffic = prof['kernels'].get(name.split(' ')[0], {}).get('dram_bytes_per_launch')
+            traffic = prof['kernels'].get(ncu_key[name], {}).get('dram_bytes_per_launch')
     except Exception:
         pass
     roofline = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
