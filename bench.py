@@ -121,7 +121,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default=None, choices=list(WORKLOADS))
-    ap.add_argument('--max-batch', type=int, default=4096)
+    ap.add_argument('--max-batch', type=int, default=16384)
     ap.add_argument('--cpu-budget-s', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

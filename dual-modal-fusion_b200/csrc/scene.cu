@@ -218,10 +218,22 @@ __global__ void __launch_bounds__(256) gather_kernel(dmf_scene s, const int64_t*
         const int nq = P * p;   // float4 per PAN window
         const float* base = s.pan + (int64_t)(4 * x) * s.pan_pitch + 4 * y;
         float4* dst = reinterpret_cast<float4*>(pan_out + n * (int64_t)P * P);
-        for (int i = threadIdx.x; i < nq; i += blockDim.x) {
-            int r = i / p, c4 = i - r * p;
-            float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * s.pan_pitch) + c4);
-            __stcs(dst + i, v);
+        // 4 independent 16-byte loads in flight per thread before the first store (latency-bound otherwise)
+        for (int i0 = threadIdx.x; i0 < nq; i0 += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < nq) {
+                    const int r = i / p, c4 = i - r * p;
+                    v[u] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * s.pan_pitch) + c4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < nq) __stcs(dst + i, v[u]);
+            }
         }
         if (mspan_out) {
             const float* b2 = s.mspan + (int64_t)(4 * x) * s.pan_pitch + 4 * y;

@@ -253,7 +253,7 @@ def paint_labels(label_map, colors):
 class NetHandle:
     """GMFNet weights packed for the sm_100a kernels + activation workspace for `max_batch` patches."""
 
-    def __init__(self, p, num_classes, max_batch=4096, device='cuda:0'):
+    def __init__(self, p, num_classes, max_batch=16384, device='cuda:0'):
         _require_cuda()
         self.p, self.C, self.max_batch, self.device = p, num_classes, max_batch, device
         self._h = C.c_void_p()

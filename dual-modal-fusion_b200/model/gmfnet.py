@@ -35,7 +35,7 @@ class Net(nn.Module):
         self.patch = int(args['patch_size'])
         if str(args.get('schedule', {}).get('activate', 'Relu')).lower() != 'relu':
             raise ValueError("gmfnet: schedule.activate must be Relu")
-        self.max_batch = int(args.get('b200', {}).get('max_batch', 4096)) if isinstance(args.get('b200'), dict) else 4096
+        self.max_batch = int(args.get('b200', {}).get('max_batch', 16384)) if isinstance(args.get('b200'), dict) else 16384
         for name, (cin, cout) in WIDTHS.items():
             setattr(self, name, _conv_bn(cin, cout, 3))
         self.fuse = _conv_bn(128 + 128, C_FUSE, 1)
