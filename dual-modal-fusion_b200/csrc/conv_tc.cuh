@@ -375,5 +375,185 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-pair variant for thin layers (C_OUT = 64): a tcgen05.mma costs ~30 clk + operand bytes / 128 B/clk
+// (measured), so N = 64 instructions run the pipe at ~40 %.  Here one accumulator row stands for TWO
+// vertically adjacent output pixels (h, w), (h+1, w) with h even: the N dimension is (s, co) = 2 x 64 and
+// the filter becomes a 4 x 3 tap window, W'[(s, co)][dy', dx] = W[co][dy' - s, dx] (zero outside).
+// 24 M128 x N128 x K16 MMAs per 256 output pixels instead of 36 M128 x N64 ones, and the vertical half of
+// the 2x2 max-pool is thread-local (columns c and 64 + c of the same TMEM lane).
+// Tile = 16 row pairs x 8 columns (32 image rows x 8 columns); halo 34 x 10 pixels; row-group stride of
+// the A descriptor = two halo rows.
+template <int C_IN, int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1) conv_rowpair_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams P) {
+    constexpr int kThreads = 64 + 128 * G;
+    constexpr int C_OUT = 64, N2 = 2 * C_OUT, TAPS = 12;
+    constexpr int KCH = C_IN / 8, KSTEPS = C_IN / 16;
+    constexpr int TH = 32;
+    constexpr uint32_t WBYTES = (uint32_t)TAPS * C_IN * N2 * 2;
+    constexpr uint32_t TMEM_USED = G * N2;
+    constexpr uint32_t TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    constexpr uint32_t A_PLANE = (uint32_t)(TH + 2) * kPitch * 16;
+    constexpr uint32_t SBO_A = 2u * kPitch * 16;
+    constexpr uint32_t A_STAGE = KCH * A_PLANE;
+    static_assert(G >= 1 && G <= 4 && C_IN % 16 == 0, "row-pair conv configuration");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;
+    uint8_t* a_s = smem + WBYTES;
+    float* scale_s = reinterpret_cast<float*>(a_s + (size_t)P.n_stage * A_STAGE);
+    float* shift_s = scale_s + C_OUT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+    const uint32_t w_bar = bar0 + 8u * 16;
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (17 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (21 + a); };
+
+    for (int i = threadIdx.x; i < C_OUT; i += kThreads) {
+        scale_s[i] = P.scale[i];
+        shift_s[i] = P.shift[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(w_bar, 1);
+        for (int a = 0; a < G; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // tile -> (patch, ty, tx): tiles_x = S/8 column strips, tiles_y = S/32 row blocks, both powers of two
+    const int tx_mask = (1 << P.tiles_x_l2) - 1;
+
+    if (warp == 0) {
+        const bool leader = elect_one();
+        if (leader) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
+            mbar_expect_tx(w_bar, WBYTES);
+            constexpr uint32_t CH = 16384;
+            for (uint32_t off = 0; off < WBYTES; off += CH)
+                bulk_load(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(P.w) + off, min(CH, WBYTES - off), w_bar);
+        }
+        __syncwarp();
+        int st = 0;
+        uint32_t ph = 1;
+        for (int i = 0; i < n_local; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            mbar_wait(empty_bar(st), ph);
+            if (leader) {
+                mbar_expect_tx(full_bar(st), A_STAGE);
+                const int n = tile >> P.tpg_l2, t = tile & ((1 << P.tpg_l2) - 1);
+                const int ty = t >> P.tiles_x_l2, tx = t & tx_mask;
+                tma_load_4d(smem_u32(a_s) + (uint32_t)st * A_STAGE, &in_map, full_bar(st), (tx * 8 - 1) * 8, n, ty * TH - 1, 0);
+            }
+            __syncwarp();
+            if (++st == P.n_stage) { st = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, N2);
+        const bool leader = elect_one();
+        mbar_wait(w_bar, 0);
+        const uint64_t w_desc0 = umma_desc(smem_u32(w_s), N2 * 16, 128);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < n_local; ++i) {
+            const int acc = i % G;
+            mbar_wait(tempty_bar(acc), ((i / G) & 1) ^ 1);
+            mbar_wait(full_bar(st), ph);
+            tc_fence_after();
+            const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * A_STAGE, A_PLANE, SBO_A);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N2);
+            if (leader) {
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    const uint32_t tap_off = (uint32_t)(((tap / 3) * kPitch + (tap % 3)) * 16);
+#pragma unroll
+                    for (int j = 0; j < KSTEPS; ++j) {
+                        const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(2 * j) * A_PLANE + tap_off) >> 4);
+                        const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((tap * KCH + 2 * j) * N2 * 16) >> 4);
+                        umma_bf16(d_tmem, ad, bd, idesc, (tap | j) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty_bar(st));
+                umma_commit(tfull_bar(acc));
+            }
+            __syncwarp();
+            if (++st == P.n_stage) { st = 0; ph ^= 1; }
+        }
+    } else {
+        const int eg = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int So_l2 = P.S_l2 - 1;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * N2);
+        const int half = lane & 1;                       // the two lanes of a horizontal pair share the stores
+        for (int i = eg; i < n_local; i += G) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int n = tile >> P.tpg_l2, t = tile & ((1 << P.tpg_l2) - 1);
+            const int ty = t >> P.tiles_x_l2, tx = t & tx_mask;
+            const int prow = ty * (TH / 2) + (m >> 3);   // pooled row = row-pair index
+            const int pcol = (tx * 8 + (m & 7)) >> 1;
+            const bool valid = n < P.N;
+            const int64_t chunk0 = (int64_t)n * P.out_chunks + P.out_chunk0;
+            __nv_bfloat16* const obase = P.out + (((chunk0 << So_l2) + prow) << So_l2) * 8 + pcol * 8;
+            const int64_t cstride = (int64_t)8 << (2 * So_l2);
+            mbar_wait(tfull_bar(eg), (i / G) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < C_OUT; c0 += 32) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32_nowait(t_row + c0, v0);                // row h     (s = 0)
+                tmem_ld32_nowait(t_row + C_OUT + c0, v1);        // row h + 1 (s = 1)
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t pk[16];
+                const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
+                const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 sc = sc4[k], sh = sh4[k];
+                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                    float r[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        r[e] = fmaxf(fmaxf(fmaf(__uint_as_float(v0[4 * k + e]), scv[e], shv[e]),
+                                           fmaf(__uint_as_float(v1[4 * k + e]), scv[e], shv[e])), 0.f);
+                    pk[2 * k] = pack_bf16x2(r[0], r[1]);
+                    pk[2 * k + 1] = pack_bf16x2(r[2], r[3]);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) pk[k] = max_bf16x2(pk[k], __shfl_xor_sync(0xffffffffu, pk[k], 1));
+                if (valid) {   // even lane: chunks 0,1 of this 32-channel group; odd lane: chunks 2,3
+                    const int cb = (c0 >> 3) + 2 * half;
+                    *reinterpret_cast<uint4*>(obase + cb * cstride) =
+                        half ? make_uint4(pk[8], pk[9], pk[10], pk[11]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(obase + (cb + 1) * cstride) =
+                        half ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(eg));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 }  // namespace tc
 }  // namespace dmf

@@ -45,12 +45,19 @@ struct LayerGeom {
     int S, taps, cin, cout, pool;
     int NP, TH, tiles_x, tiles_y, PX, tiles_per_group, a_plane, a_stage, sbo_a, n_stage, smem;
     int S_l2, NP_l2, tiles_x_l2, PX_l2, tpg_l2;
+    int rowpair;   // conv_rowpair_kernel: 32-row x 8-column tiles, N = 2 x cout
 };
 
-static int make_geom(LayerGeom& g, int S, int taps, int cin, int cout, int pool) {
-    g.S = S; g.taps = taps; g.cin = cin; g.cout = cout; g.pool = pool;
+static int make_geom(LayerGeom& g, int S, int taps, int cin, int cout, int pool, int rowpair = 0) {
+    g.S = S; g.taps = taps; g.cin = cin; g.cout = cout; g.pool = pool; g.rowpair = rowpair;
     const int kch = cin / 8;
-    if (taps == 9) {
+    if (rowpair) {
+        DMF_REQUIRE(taps == 9 && pool && cout == 64 && S % 32 == 0, "row-pair conv needs a pooled 3x3 layer, cout 64, map multiple of 32");
+        g.TH = 32; g.NP = 1; g.tiles_x = S / 8; g.tiles_y = S / 32; g.PX = 0;
+        g.tiles_per_group = g.tiles_x * g.tiles_y;
+        g.sbo_a = 2 * tc::kPitch * 16;
+        g.a_plane = (g.TH + 2) * tc::kPitch * 16;
+    } else if (taps == 9) {
         DMF_REQUIRE(S % 8 == 0, "conv3x3 map size %d is not a multiple of 8", S);
         g.TH = (S % 16 == 0) ? 16 : 8;
         g.NP = 16 / g.TH;
@@ -74,7 +81,7 @@ static int make_geom(LayerGeom& g, int S, int taps, int cin, int cout, int pool)
                 "layer geometry must be powers of two");
     g.S_l2 = l2(S); g.NP_l2 = l2(g.NP); g.tiles_x_l2 = taps == 9 ? l2(g.tiles_x) : 0; g.PX_l2 = taps == 1 ? l2(g.PX) : 0;
     g.tpg_l2 = l2(g.tiles_per_group);
-    const int fixed = taps * cin * cout * 2 + 2 * cout * 4 + 256;
+    const int fixed = (rowpair ? 12 * cin * 2 * cout * 2 : taps * cin * cout * 2) + 2 * cout * 4 + 256;
     g.n_stage = std::min(6, (kSmemLimit - fixed) / g.a_stage);
     DMF_REQUIRE(g.n_stage >= 1, "layer does not fit in shared memory");
     g.smem = fixed + g.n_stage * g.a_stage;
@@ -407,6 +414,29 @@ static int pack_conv(dmf_net* n, ConvLayer& L, const std::string& blk) {
     return DMF_OK;
 }
 
+// row-pair packing: tap' = dy'*3 + dx over a 4 x 3 window, row n = s*cout + co holds W[co][dy' - s][dx]
+static int pack_conv_rowpair(dmf_net* n, ConvLayer& L, const std::string& blk) {
+    const int cin = L.g.cin, cout = L.g.cout, kch = cin / 8, N2 = 2 * cout;
+    auto* w = param(n, blk + ".0.weight", (size_t)cout * cin * 9);
+    if (!w) return DMF_ERR_STATE;
+    std::vector<__nv_bfloat16> pk((size_t)12 * cin * N2, __float2bfloat16_rn(0.f));
+    for (int s2 = 0; s2 < 2; ++s2)
+        for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx)
+                for (int ci = 0; ci < cin; ++ci)
+                    for (int co = 0; co < cout; ++co) {
+                        const int tap = (dy + s2) * 3 + dx;
+                        pk[(((size_t)tap * kch + ci / 8) * N2 + s2 * cout + co) * 8 + ci % 8] =
+                            __float2bfloat16_rn((*w)[((size_t)co * cin + ci) * 9 + dy * 3 + dx]);
+                    }
+    std::vector<float> sc, sh;
+    DMF_TRY(fold_bn(n, blk, cout, sc, sh));
+    DMF_TRY(to_device(&L.w, pk));
+    DMF_TRY(to_device(&L.scale, sc));
+    DMF_TRY(to_device(&L.shift, sh));
+    return DMF_OK;
+}
+
 // MS stem weights for the hi/lo-split input: per tap k = [w_hi(4), w_hi(4), w_lo(4), 0(4)]
 static int pack_ms_stem(dmf_net* n, ConvLayer& L) {
     const int cout = C_MS1;
@@ -455,13 +485,35 @@ static int launch_conv(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16
     return DMF_OK;
 }
 
+template <int CI, int G>
+static int launch_rowpair(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16* out, int out_chunks, int out_chunk0,
+                          int64_t N, cudaStream_t st) {
+    tc::ConvParams P{};
+    const LayerGeom& g = L.g;
+    P.S = g.S; P.S_l2 = g.S_l2; P.NP = 1; P.NP_l2 = 0; P.TH = g.TH; P.tiles_x_l2 = g.tiles_x_l2; P.tpg_l2 = g.tpg_l2;
+    P.N = (int)N; P.n_tiles = (int)N * g.tiles_per_group;
+    P.a_plane = g.a_plane; P.a_stage = g.a_stage; P.n_stage = g.n_stage; P.sbo_a = g.sbo_a;
+    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0;
+    P.w = L.w; P.scale = L.scale; P.shift = L.shift; P.out = out;
+    auto kern = tc::conv_rowpair_kernel<CI, G>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr_set = true;
+    }
+    kern<<<std::min(P.n_tiles, num_sms()), 64 + 128 * G, g.smem, st>>>(map, P);
+    DMF_LAUNCHED();
+    return DMF_OK;
+}
+
 static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat16* out, int64_t N, cudaStream_t st, int dbg) {
     const int ocat = C_CAT / 8;
     const bool np2 = n->L[layer].g.NP == 2;       // 8x8 maps (p = 8): two patches per 128-pixel tile
     switch (layer) {
         case 0: return np2 ? launch_conv<C_MS1, C_MS2, 9, true, 3, 2>(n->L[0], map, out, ocat, 0, N, st, dbg)
                            : launch_conv<C_MS1, C_MS2, 9, true, 3, 1>(n->L[0], map, out, ocat, 0, N, st, dbg);
-        case 1: return launch_conv<C_PAN1, C_PAN2, 9, true, 4, 1>(n->L[1], map, out, C_PAN2 / 8, 0, N, st, dbg);
+        case 1: return n->L[1].g.rowpair ? launch_rowpair<C_PAN1, 3>(n->L[1], map, out, C_PAN2 / 8, 0, N, st)
+                                         : launch_conv<C_PAN1, C_PAN2, 9, true, 4, 1>(n->L[1], map, out, C_PAN2 / 8, 0, N, st, dbg);
         case 2: return np2 ? launch_conv<C_PAN2, C_PAN3, 9, true, 3, 2>(n->L[2], map, out, ocat, C_MS2 / 8, N, st, dbg)
                            : launch_conv<C_PAN2, C_PAN3, 9, true, 3, 1>(n->L[2], map, out, ocat, C_MS2 / 8, N, st, dbg);
         case 3: return launch_conv<C_CAT, C_FUSE, 1, false, 2, 1>(n->L[3], map, out, C_FUSE / 8, 0, N, st, dbg);
@@ -562,7 +614,7 @@ int dmf_net_create(dmf_net** out, int p, int num_classes, int max_batch) {
     dmf_net* n = new dmf_net();
     n->p = p; n->C = num_classes; n->NB = max_batch;
     int rc = make_geom(n->L[0].g, p, 9, C_MS1, C_MS2, 1);
-    if (rc == DMF_OK) rc = make_geom(n->L[1].g, 2 * p, 9, C_PAN1, C_PAN2, 1);
+    if (rc == DMF_OK) rc = make_geom(n->L[1].g, 2 * p, 9, C_PAN1, C_PAN2, 1, (2 * p) % 32 == 0);
     if (rc == DMF_OK) rc = make_geom(n->L[2].g, p, 9, C_PAN2, C_PAN3, 1);
     if (rc == DMF_OK) rc = make_geom(n->L[3].g, p / 2, 1, C_CAT, C_FUSE, 0);
     if (rc == DMF_OK) rc = make_geom(n->L[4].g, p, 9, 16, C_MS1, 0);
@@ -629,7 +681,7 @@ int dmf_net_finalize(dmf_net* n, void* stream) {
     }
     // --- tensor-core layers
     DMF_TRY(pack_conv(n, n->L[0], "ms2"));
-    DMF_TRY(pack_conv(n, n->L[1], "pan2"));
+    DMF_TRY(n->L[1].g.rowpair ? pack_conv_rowpair(n, n->L[1], "pan2") : pack_conv(n, n->L[1], "pan2"));
     DMF_TRY(pack_conv(n, n->L[2], "pan3"));
     DMF_TRY(pack_conv(n, n->L[3], "fuse"));
     // --- head
@@ -743,6 +795,7 @@ int dmf_net_debug_layer(dmf_net* n, int layer, int impl, const void* in_dev, voi
     const ConvLayer& L = n->L[layer];
     const int och = layer == 0 || layer == 2 ? C_CAT / 8 : L.g.cout / 8;
     const int oc0 = layer == 2 ? C_MS2 / 8 : 0;
+    if (impl == 1 && L.g.rowpair) { set_error("net_debug_layer: the CUDA-core debug conv does not read row-pair weights"); return DMF_ERR_UNSUPPORTED; }
     if (impl == 1) {
         const int So = L.g.pool ? L.g.S / 2 : L.g.S;
         const int64_t total = N * So * So * L.g.cout;
