@@ -225,3 +225,66 @@ def test_sharpened_net_margin_rule(dmf):
     assert len(np.unique(want.argmax(1))) >= 3
     assert margin_rule(want, got)
     print('sharpened-net argmax agreement: %.4f' % (got.argmax(1) == want.argmax(1)).mean())
+
+
+@pytest.mark.parametrize('H,W,ncls', [(1000, 1000, 12), (2001, 2101, 11)])
+def test_full_size_scene_properties(dmf, H, W, ncls):
+    """BASELINE.json configs[1] / [2] at full size (1 M and 4.2 M pixels): size-independent properties of
+    the fused band path — the matrix covers every pixel, equals the histogram of (label map, labels) bit
+    for bit, row bands add up to the whole scene, and a random sample of pixels agrees with the fp32 oracle."""
+    p, C = 16, ncls + 1
+    ms, pan, label = orc.synthetic_scene(H, W, ncls, seed=0, label_seed=1)
+    net = make_ref(p, C, seed=3407, randomize_bn=False)
+    h = dmf.NetHandle(p, C, device=DEV)
+    h.load_state_dict(net.state_dict())
+    sc = dmf.Scene.from_raw(ms, pan, p, DEV)
+    sc.set_labels(label)
+    pred_map, cm = h.infer_scene(sc)
+    assert int(cm.sum()) == H * W
+    lab = torch.from_numpy(label).to(DEV).long()
+    want = torch.bincount((pred_map.long() * C + lab).reshape(-1), minlength=C * C).reshape(C, C)
+    assert torch.equal(cm, want)
+    cm2, pm2 = torch.zeros_like(cm), torch.zeros_like(pred_map)
+    cut = [0, H // 3, H // 3 + 1, H]                  # uneven bands, one of them a single row
+    for a, b in zip(cut[:-1], cut[1:]):
+        h.infer_scene(sc, a, b, pred_map=pm2, cm=cm2)
+    assert torch.equal(cm2, cm) and torch.equal(pm2, pred_map)
+    idx = np.random.default_rng(1).integers(0, H * W, 400)
+    idx[:4] = [0, W - 1, (H - 1) * W, H * W - 1]      # scene corners: windows made of reflect padding
+    logits, pred = h.forward_scene(sc, flat_idx=idx, want_pred=True)
+    assert torch.equal(pred.cpu(), pred_map.reshape(-1)[torch.from_numpy(idx).to(DEV)].cpu())
+    MS = orc.data_padding(ms, p)
+    PAN = orc.data_padding(pan, p)
+    a, b = orc.gather_dual(MS, PAN, idx // W, idx % W, p)
+    with torch.no_grad():
+        ref = net(torch.from_numpy(a), torch.from_numpy(b)).numpy()
+    got = logits.cpu().numpy()
+    assert (np.abs(got - ref) <= LOGIT_ATOL + LOGIT_RTOL * np.abs(ref)).all()
+    assert (got.argmax(1) == ref.argmax(1)).mean() >= 0.999
+    aa, oa, k, _ = orc.aa_oa(cm.cpu().numpy().astype(np.float64))
+    assert 0.0 <= oa <= 1.0 and np.isfinite(k)
+
+
+def test_bad_arguments_raise_not_crash(dmf):
+    with pytest.raises(RuntimeError, match='patch_size'):
+        dmf.NetHandle(12, 8, device=DEV)
+    h = dmf.NetHandle(16, 8, max_batch=64, device=DEV)
+    with pytest.raises(RuntimeError, match='finalize'):
+        h.forward_patches(torch.zeros(1, 4, 16, 16, device=DEV), torch.zeros(1, 1, 64, 64, device=DEV))
+    net = make_ref(16, 8)
+    sd = net.state_dict()
+    sd.pop('fc2.bias')
+    with pytest.raises(RuntimeError, match='fc2.bias'):
+        h.load_state_dict(sd)
+    h.load_state_dict(net.state_dict())
+    ms, pan, label = orc.synthetic_scene(20, 20, 7, seed=1)
+    sc8 = dmf.Scene.from_raw(ms, pan, 8, DEV)
+    with pytest.raises(RuntimeError, match='patch size'):
+        h.forward_scene(sc8, first=0, count=4)
+    sc = dmf.Scene.from_raw(ms, pan, 16, DEV)
+    with pytest.raises(RuntimeError, match='labels'):
+        h.infer_scene(sc, cm=torch.zeros((8, 8), dtype=torch.int64, device=DEV))
+    with pytest.raises(RuntimeError, match='outside'):
+        h.forward_scene(sc, first=390, count=20)
+    with pytest.raises(RuntimeError, match='tri mode'):
+        sc.gather([0, 1], tri=True)
