@@ -280,6 +280,30 @@ def main():
                 'stage_ms': {k: round(v, 3) for k, v in stage.items()},
                 'whole_net_tflops': handle.flops_per_patch * n_local / (stage['total'] / 1e3) / 1e12}
 
+    # ---- secondary metrics named by BASELINE.json: K1 patch-gather GB/s and conv tensor-pipe utilisation
+    gidx = torch.randint(0, H * W, (8192,), device=dev)
+    for _ in range(3):
+        scene.gather(gidx, want_target=False)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g_ms = 1e9
+    for _ in range(5):
+        flush.fill_(1)
+        g0.record()
+        scene.gather(gidx, want_target=False)
+        g1.record()
+        torch.cuda.synchronize()
+        g_ms = min(g_ms, g0.elapsed_time(g1))
+    gather_gbs = 8192 * (4 * P * P + 16 * P * P) * 4 / g_ms / 1e6
+    conv_fl = 2 * conv(64, 128, 3, P) + conv(32, 64, 3, 2 * P) + conv(256, 128, 1, P // 2)
+    conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
+    secondary = {'patch_gather': {'GBs_written': gather_gbs, 'frac_of_hbm_copy_peak': gather_gbs / pk['hbm_gbs'], 'batch': 8192,
+                                  'bytes_per_patch': (4 * P * P + 16 * P * P) * 4,
+                                  'note': 'write-only kernel; measured pure-write ceiling on this pool is 3934 GB/s (memset), copy peak counts read+write'},
+                 'conv_tensor_util': {'achieved_TFLOPs': conv_fl * n_local / (conv_ms / 1e3) / 1e12,
+                                      'frac_of_sustained_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
+                                      'frac_of_burst_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
+                                      'ncu_tensor_pipe_active_pct': 'profiles/r01_ncu_summary.json'}}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, desc, _ = cpu_reference_run(wl, args.cpu_budget_s)
@@ -292,7 +316,7 @@ def main():
                           'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
                           'dtype': 'bf16', 'data': 'synthetic', 'config': config, 'clocks': clk.summary(),
                           'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
-                          'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline}))
+                          'gpu_launches': int(launches), 'roofline': roofline, 'secondary': secondary, 'cpu_baseline': cpu_baseline}))
     if world > 1:
         dist.destroy_process_group()
 

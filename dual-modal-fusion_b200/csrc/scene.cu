@@ -103,19 +103,20 @@ template <> struct Norm<double> {
 };
 
 // out[r][c][b] = norm(raw[reflect(r)][reflect(c)][b]); out rows have `out_pitch` elements.
+// One output row per blockIdx.y (no 64-bit div/mod per element); threads sweep the row's Wp*bands elements.
 template <typename T, typename O>
-__global__ void normalize_pad_kernel(const T* __restrict__ raw, int H, int W, int bands, int Hp, int Wp,
-                                     int64_t out_pitch, const double* __restrict__ lohi, O* __restrict__ out) {
+__global__ void __launch_bounds__(256) normalize_pad_kernel(const T* __restrict__ raw, int H, int W, int bands, int Hp, int Wp,
+                                                            int64_t out_pitch, const double* __restrict__ lohi, O* __restrict__ out) {
     const double lo = lohi[0], hi = lohi[1];
-    const int64_t row_elems = (int64_t)Wp * bands;
-    const int64_t total = (int64_t)Hp * row_elems;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int r = (int)(i / row_elems);
-        int rem = (int)(i - (int64_t)r * row_elems);
-        int c = rem / bands, b = rem - c * bands;
-        T v = raw[((int64_t)reflect101(r, H) * W + reflect101(c, W)) * bands + b];
-        double q = Norm<T>::q(v, lo, hi);
-        out[(int64_t)r * out_pitch + rem] = (O)q;   // double -> float is round-to-nearest-even
+    const int row_elems = Wp * bands;
+    for (int r = blockIdx.y; r < Hp; r += gridDim.y) {
+        const T* src = raw + (int64_t)reflect101(r, H) * W * bands;
+        O* dst = out + (int64_t)r * out_pitch;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < row_elems; e += gridDim.x * blockDim.x) {
+            const int c = e / bands, b = e - c * bands;
+            const T v = src[(int64_t)reflect101(c, W) * bands + b];
+            dst[e] = (O)Norm<T>::q(v, lo, hi);      // double -> float is round-to-nearest-even
+        }
     }
 }
 
@@ -132,8 +133,7 @@ static int normalize_pad_t(const T* raw, int H, int W, int bands, int P, void* o
     minmax_final_kernel<<<1, 32, 0, st>>>(scratch, nblk, lohi);
     DMF_LAUNCHED();
     const int Hp = H + P - 1, Wp = W + P - 1;
-    const int64_t total = (int64_t)Hp * Wp * bands;
-    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+    const dim3 grid((unsigned)std::min<int64_t>(((int64_t)Wp * bands + 255) / 256, 64), (unsigned)std::min(Hp, 65535));
     if (out_dtype == DMF_F32)
         normalize_pad_kernel<T, float><<<grid, 256, 0, st>>>(raw, H, W, bands, Hp, Wp, out_pitch, lohi, (float*)out);
     else
