@@ -51,6 +51,7 @@ struct ConvParams {
     const float* scale;         // folded BatchNorm scale  [C_out]
     const float* shift;         // folded BatchNorm shift  [C_out]
     __nv_bfloat16* out;
+    float* gap;                 // GAPOUT layers: per-patch channel sums [N][C_out] fp32 (zeroed by the caller)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -165,7 +166,10 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int C_IN, int C_OUT, int TAPS, bool POOL, int G, int NP>
+// GAPOUT (1x1 layers whose 128-pixel tile holds whole patches): instead of storing the activation, the
+// epilogue reduces it over the pixels of each patch (global average pool fused in) with an
+// exchange-halving warp reduction and emits per-patch channel sums; the activation never goes to HBM.
+template <int C_IN, int C_OUT, int TAPS, bool POOL, int G, int NP, bool GAPOUT = false>
 __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams P) {
     constexpr int kThreads = 64 + 128 * G;
     constexpr int KCH = C_IN / 8;
@@ -341,7 +345,46 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_c
                     pk[2 * k] = pack_bf16x2(a0, a1);
                     pk[2 * k + 1] = pack_bf16x2(a2, a3);
                 }
-                if (POOL) {
+                if (GAPOUT) {
+                    // fp32 post-ReLU values of this pixel for channels c0..c0+31 -> sums over the patch's pixels.
+                    // PX >= 32: the warp's 32 lanes belong to one patch; after 5 exchange-halving steps lane l owns
+                    // channel c0 + l.  PX == 16: two patches per warp, 4 steps, lane l owns channels c0 + 2(l&15), +1.
+                    float f[32];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 sc = sc4[k], sh = sh4[k];
+                        f[4 * k] = fmaxf(fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x), 0.f);
+                        f[4 * k + 1] = fmaxf(fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y), 0.f);
+                        f[4 * k + 2] = fmaxf(fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z), 0.f);
+                        f[4 * k + 3] = fmaxf(fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w), 0.f);
+                    }
+                    const bool wide = P.PX >= 32;
+                    if (wide) {
+                        const bool up = lane & 16;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const float send = up ? f[k] : f[k + 16], keep = up ? f[k + 16] : f[k];
+                            f[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+                    }
+                    // live values per lane before a step with lane distance d: 2d (wide) or 4d (two patches per warp)
+#pragma unroll
+                    for (int d = 8; d >= 1; d >>= 1) {
+                        const bool up = lane & d;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            if (k < 2 * d && (k < d || !wide)) {
+                                const float fh = wide ? f[k + d] : f[k + 2 * d];
+                                const float send = up ? f[k] : fh, keep = up ? fh : f[k];
+                                f[k] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+                            }
+                        }
+                    }
+                    if (valid) {
+                        if (wide) atomicAdd(P.gap + (int64_t)n * C_OUT + c0 + lane, f[0]);     // PX/32 warps add: 2 addends at p=16 -> order-independent
+                        else *reinterpret_cast<float2*>(P.gap + (int64_t)n * C_OUT + c0 + 2 * (lane & 15)) = make_float2(f[0], f[1]);
+                    }
+                } else if (POOL) {
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         pk[k] = max_bf16x2(pk[k], __shfl_xor_sync(0xffffffffu, pk[k], 1));

@@ -136,6 +136,7 @@ struct dmf_net {
     float *fc1t = nullptr, *fc1b = nullptr, *fc2t = nullptr, *fc2b = nullptr;
     ConvLayer L[5];   // ms2, pan2, pan3, fuse, ms1 (hi/lo-split stem, 16 -> 64)
     __nv_bfloat16 *X0 = nullptr, *A1 = nullptr, *B1 = nullptr, *B2 = nullptr, *CAT = nullptr, *F = nullptr;
+    float* gap = nullptr;     // [NB][128] per-patch channel sums when the pooling is fused into the fusion conv (p <= 16)
     cudaEvent_t ev[8] = {};
     float stage_ms[8] = {};
 };
@@ -196,7 +197,10 @@ __global__ void __launch_bounds__(256) ms_prep_kernel(PatchSrc src, int p, int64
 // 8 channels instead of 40), the two small linears from shared-memory weights, shuffle argmax.
 constexpr int kHeadWarps = 8;
 
-__global__ void __launch_bounds__(32 * kHeadWarps) head_kernel(const __nv_bfloat16* __restrict__ F, int64_t N, int npx, int C,
+// GAPIN: the pooled sums come from the fusion conv's epilogue (gap [N][128] fp32) instead of F.
+template <bool GAPIN>
+__global__ void __launch_bounds__(32 * kHeadWarps) head_kernel(const __nv_bfloat16* __restrict__ F, const float* __restrict__ gap,
+                                                              int64_t N, int npx, int C,
                                                               const float* __restrict__ fc1t, const float* __restrict__ fc1b,
                                                               const float* __restrict__ fc2t, const float* __restrict__ fc2b,
                                                               const dmf_scene scene, const int64_t* __restrict__ idx, int64_t first,
@@ -221,8 +225,12 @@ __global__ void __launch_bounds__(32 * kHeadWarps) head_kernel(const __nv_bfloat
     const float inv = 1.0f / (float)npx;
     const int64_t wstride = (int64_t)gridDim.x * kHeadWarps;
     for (int64_t n = (int64_t)blockIdx.x * kHeadWarps + warp; n < N; n += wstride) {
+        if (GAPIN) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(gap + n * C_FUSE) + lane);
+            *reinterpret_cast<float4*>(g + 4 * lane) = make_float4(s4.x * inv, s4.y * inv, s4.z * inv, s4.w * inv);
+        }
         const uint4* base = reinterpret_cast<const uint4*>(F) + n * 16 * npx;
-        for (int chunk = 0; chunk < 16; ++chunk) {
+        for (int chunk = 0; chunk < (GAPIN ? 0 : 16); ++chunk) {
             // the 32 lanes sweep the npx pixels of this 8-channel chunk, 16 bytes each (512 B per sweep)
             float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int px = lane; px < npx; px += 32) {
@@ -460,9 +468,9 @@ static int pack_ms_stem(dmf_net* n, ConvLayer& L) {
     return DMF_OK;
 }
 
-template <int CI, int CO, int TAPS, bool POOL, int G, int NP>
+template <int CI, int CO, int TAPS, bool POOL, int G, int NP, bool GAPOUT = false>
 static int launch_conv(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16* out, int out_chunks, int out_chunk0,
-                       int64_t N, cudaStream_t st, int dbg = 0) {
+                       int64_t N, cudaStream_t st, int dbg = 0, float* gap = nullptr) {
     tc::ConvParams P;
     const LayerGeom& g = L.g;
     P.S = g.S; P.S_l2 = g.S_l2; P.NP = g.NP; P.NP_l2 = g.NP_l2; P.TH = g.TH; P.tiles_x_l2 = g.tiles_x_l2;
@@ -471,9 +479,10 @@ static int launch_conv(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16
     P.n_tiles = (int)((N + g.NP - 1) / g.NP) * g.tiles_per_group;
     P.a_plane = g.a_plane; P.a_stage = g.a_stage; P.n_stage = g.n_stage; P.sbo_a = g.sbo_a;
     P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0; P.dbg = dbg;
-    P.w = L.w; P.scale = L.scale; P.shift = L.shift; P.out = out;
+    P.w = L.w; P.scale = L.scale; P.shift = L.shift; P.out = out; P.gap = gap;
+    if (GAPOUT) DMF_CUDA(cudaMemsetAsync(gap, 0, sizeof(float) * (size_t)N * CO, st));
     if (TAPS == 9 && (g.NP != NP || g.TH != 16 / NP)) { set_error("conv geometry/template mismatch"); return DMF_ERR_STATE; }
-    auto kern = tc::conv_tc_kernel<CI, CO, TAPS, POOL, G, NP>;
+    auto kern = tc::conv_tc_kernel<CI, CO, TAPS, POOL, G, NP, GAPOUT>;
     static bool attr_set = false;
     if (!attr_set) {
         DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -516,7 +525,8 @@ static int run_layer(dmf_net* n, int layer, const CUtensorMap& map, __nv_bfloat1
                                          : launch_conv<C_PAN1, C_PAN2, 9, true, 4, 1>(n->L[1], map, out, C_PAN2 / 8, 0, N, st, dbg);
         case 2: return np2 ? launch_conv<C_PAN2, C_PAN3, 9, true, 3, 2>(n->L[2], map, out, ocat, C_MS2 / 8, N, st, dbg)
                            : launch_conv<C_PAN2, C_PAN3, 9, true, 3, 1>(n->L[2], map, out, ocat, C_MS2 / 8, N, st, dbg);
-        case 3: return launch_conv<C_CAT, C_FUSE, 1, false, 2, 1>(n->L[3], map, out, C_FUSE / 8, 0, N, st, dbg);
+        case 3: return (n->gap && out == n->F) ? launch_conv<C_CAT, C_FUSE, 1, false, 2, 1, true>(n->L[3], map, out, C_FUSE / 8, 0, N, st, dbg, n->gap)
+                                               : launch_conv<C_CAT, C_FUSE, 1, false, 2, 1>(n->L[3], map, out, C_FUSE / 8, 0, N, st, dbg);
         case 4: return np2 ? launch_conv<16, C_MS1, 9, false, 4, 2>(n->L[4], map, out, C_MS1 / 8, 0, N, st, dbg)
                            : launch_conv<16, C_MS1, 9, false, 4, 1>(n->L[4], map, out, C_MS1 / 8, 0, N, st, dbg);
     }
@@ -584,8 +594,14 @@ static int forward_chunk(dmf_net* n, const PatchSrc& src, bool from_scene, int64
     if (tm) cudaEventRecord(n->ev[6], st);
     const int npx = (n->p / 2) * (n->p / 2);
     const int grid = (int)std::min<int64_t>((N + kHeadWarps - 1) / kHeadWarps, (int64_t)num_sms() * 4);
-    head_kernel<<<grid, 32 * kHeadWarps, head_smem(n->C), st>>>(n->F, N, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, src.scene,
-                                                    src.idx, src.first, logits, pred, (unsigned long long*)cm, pred_map);
+    if (n->gap)
+        head_kernel<true><<<grid, 32 * kHeadWarps, head_smem(n->C), st>>>(n->F, n->gap, N, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b,
+                                                                          src.scene, src.idx, src.first, logits, pred,
+                                                                          (unsigned long long*)cm, pred_map);
+    else
+        head_kernel<false><<<grid, 32 * kHeadWarps, head_smem(n->C), st>>>(n->F, nullptr, N, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b,
+                                                                           src.scene, src.idx, src.first, logits, pred,
+                                                                           (unsigned long long*)cm, pred_map);
     DMF_LAUNCHED();
     if (tm) {
         cudaEventRecord(n->ev[7], st);
@@ -631,6 +647,7 @@ int dmf_net_destroy(dmf_net* n) {
     for (auto& L : n->L) { cudaFree(L.w); cudaFree(L.scale); cudaFree(L.shift); }
     __nv_bfloat16* bs[] = {n->X0, n->A1, n->B1, n->B2, n->CAT, n->F};
     for (auto* b : bs) cudaFree(b);
+    cudaFree(n->gap);
     for (auto& e : n->ev) if (e) cudaEventDestroy(e);
     delete n;
     return DMF_OK;
@@ -706,13 +723,15 @@ int dmf_net_finalize(dmf_net* n, void* stream) {
         DMF_CUDA(cudaMalloc(&n->B2, NB * C_PAN2 * p * p * 2));
         DMF_CUDA(cudaMalloc(&n->CAT, NB * C_CAT * (p / 2) * (p / 2) * 2));
         DMF_CUDA(cudaMalloc(&n->F, NB * C_FUSE * (p / 2) * (p / 2) * 2));
+        if ((p / 2) * (p / 2) <= 64) DMF_CUDA(cudaMalloc(&n->gap, NB * C_FUSE * sizeof(float)));   // whole patches per 128-pixel tile
         DMF_TRY(make_map(&n->L[0].map, n->L[0].g, n->A1, n->NB));
         DMF_TRY(make_map(&n->L[1].map, n->L[1].g, n->B1, n->NB));
         DMF_TRY(make_map(&n->L[2].map, n->L[2].g, n->B2, n->NB));
         DMF_TRY(make_map(&n->L[3].map, n->L[3].g, n->CAT, n->NB));
         DMF_TRY(make_map(&n->L[4].map, n->L[4].g, n->X0, n->NB));
         for (auto& e : n->ev) DMF_CUDA(cudaEventCreate(&e));
-        DMF_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        DMF_CUDA(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        DMF_CUDA(cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     }
     DMF_CUDA(cudaDeviceSynchronize());
     n->ready = true;
@@ -756,8 +775,12 @@ int dmf_net_forward_patches(dmf_net* n, const float* ms_dev, const float* pan_de
         const int npx = (p / 2) * (p / 2);
         const int grid = (int)std::min<int64_t>((nb + kHeadWarps - 1) / kHeadWarps, (int64_t)num_sms() * 4);
         dmf_scene none{};
-        head_kernel<<<grid, 32 * kHeadWarps, head_smem(n->C), st>>>(n->F, nb, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, none, nullptr,
-                                                        0, logits_out_dev + o * n->C, nullptr, nullptr, nullptr);
+        if (n->gap)
+            head_kernel<true><<<grid, 32 * kHeadWarps, head_smem(n->C), st>>>(n->F, n->gap, nb, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b,
+                                                                              none, nullptr, 0, logits_out_dev + o * n->C, nullptr, nullptr, nullptr);
+        else
+            head_kernel<false><<<grid, 32 * kHeadWarps, head_smem(n->C), st>>>(n->F, nullptr, nb, npx, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b,
+                                                                               none, nullptr, 0, logits_out_dev + o * n->C, nullptr, nullptr, nullptr);
         DMF_LAUNCHED();
     }
     return DMF_OK;
