@@ -256,12 +256,12 @@ def main():
     conv = lambda cin, cout, k, h: 2 * cin * cout * k * k * h * h
     kernels = {   # kernel instance -> (stage keys, algorithmic FLOPs per pixel, launches per chunk)
         'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': (['conv_ms2', 'conv_pan3'], 2 * conv(64, 128, 3, P), 2),
-        'conv_tc_kernel<32,64,9,pool,G=4> (pan2)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
-        'conv_tc_kernel<256,128,1,G=2> (fuse)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
+        'conv_rowpair_kernel<32,G=3> (pan2, 32->64)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
+        'conv_tc_kernel<256,128,1,G=2,gap> (fuse + pooling)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
     }
-    ncu_key = {'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': 'tc::conv_tc_kernel<64,128,9,1,3,1>',
-               'conv_tc_kernel<32,64,9,pool,G=4> (pan2)': 'tc::conv_tc_kernel<32,64,9,1,4,1>',
-               'conv_tc_kernel<256,128,1,G=2> (fuse)': 'tc::conv_tc_kernel<256,128,1,0,2,1>'}
+    ncu_key = {'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': 'tc::conv_tc_kernel<64,128,9,1,3,1,0>',
+               'conv_rowpair_kernel<32,G=3> (pan2, 32->64)': 'tc::conv_rowpair_kernel<32,3>',
+               'conv_tc_kernel<256,128,1,G=2,gap> (fuse + pooling)': 'tc::conv_tc_kernel<256,128,1,0,2,1,1>'}
     name, (keys, fl_px, per_chunk) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
     k_ms = sum(stage[k] for k in keys)
     achieved = fl_px * n_local / (k_ms / 1e3) / 1e12
