@@ -52,6 +52,8 @@ struct ConvParams {
     const float* shift;         // folded BatchNorm shift  [C_out]
     __nv_bfloat16* out;
     float* gap;                 // GAPOUT layers: per-patch channel sums [N][C_out] fp32 (zeroed by the caller)
+    double* stats;              // MODE 2: sum(z) at [c], sum(z^2) at [stat_stride + c] (zeroed by the caller)
+    int stat_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -166,10 +168,32 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// Sum over the 32 lanes of a warp of 32 per-lane values: exchange-halving (31 shuffles instead of 160);
+// afterwards f[0] of lane l is the warp total of element l.
+__device__ __forceinline__ void warp_channel_sums(float (&f)[32], int lane) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const bool up = lane & d;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k < d) {
+                const float send = up ? f[k] : f[k + d], keep = up ? f[k + d] : f[k];
+                f[k] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+            }
+        }
+    }
+}
+
 // GAPOUT (1x1 layers whose 128-pixel tile holds whole patches): instead of storing the activation, the
 // epilogue reduces it over the pixels of each patch (global average pool fused in) with an
 // exchange-halving warp reduction and emits per-patch channel sums; the activation never goes to HBM.
-template <int C_IN, int C_OUT, int TAPS, bool POOL, int G, int NP, bool GAPOUT = false>
+//
+// MODE (training path, train.cu): 0 = inference epilogue (folded BN + ReLU, optional pool / GAP);
+// 1 = RAW: the bf16 rounding of the fp32 accumulator is stored unpooled (dgrad, and the pre-BatchNorm
+// tensor Z of a training forward); 2 = RAW + batch statistics: additionally sum(z) and sum(z^2) per
+// output channel over everything this launch computes are added (double atomics) to P.stats[2][C_OUT]
+// — train-mode BatchNorm needs them before anything can be normalised.
+template <int C_IN, int C_OUT, int TAPS, bool POOL, int G, int NP, bool GAPOUT = false, int MODE = 0>
 __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams P) {
     constexpr int kThreads = 64 + 128 * G;
     constexpr int KCH = C_IN / 8;
@@ -190,7 +214,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_c
     uint8_t* a_s = smem + WBYTES;
     float* scale_s = reinterpret_cast<float*>(a_s + (size_t)P.n_stage * P.a_stage);
     float* shift_s = scale_s + C_OUT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
+    float* stat_s = shift_s + C_OUT;                  // [2][C_OUT] per-CTA partial statistics (MODE 2)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 2 * C_OUT);
     // bars: [0,8) full, [8,16) empty, 16 weights, 17..20 tmem_full, 21..24 tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
@@ -203,8 +228,12 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_c
     auto tempty_bar = [&](int a) { return bar0 + 8u * (21 + a); };
 
     for (int i = threadIdx.x; i < C_OUT; i += kThreads) {
-        scale_s[i] = P.scale[i];
-        shift_s[i] = P.shift[i];
+        if (MODE == 0) {
+            scale_s[i] = P.scale[i];
+            shift_s[i] = P.shift[i];
+        }
+        stat_s[i] = 0.f;
+        stat_s[C_OUT + i] = 0.f;
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -333,6 +362,27 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_c
                 uint32_t v[32];
                 tmem_ld32(t_row + c0, v);
                 uint32_t pk[16];
+                if (MODE != 0) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) pk[k] = pack_bf16x2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                    if (valid) {
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; ++s4)
+                            *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + s4) * cstride) =
+                                make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                    }
+                    if (MODE == 2) {
+                        // rows of patches beyond N come from out-of-bounds TMA boxes: all zeros, they add nothing
+                        float f[32], q2[32];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) { f[k] = __uint_as_float(v[k]); q2[k] = f[k] * f[k]; }
+                        warp_channel_sums(f, lane);
+                        warp_channel_sums(q2, lane);
+                        atomicAdd(stat_s + c0 + lane, f[0]);
+                        atomicAdd(stat_s + C_OUT + c0 + lane, q2[0]);
+                    }
+                    continue;
+                }
                 const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
                 const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
 #pragma unroll
@@ -416,6 +466,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_c
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+    if (MODE == 2)
+        for (int i = threadIdx.x; i < 2 * C_OUT; i += kThreads)
+            atomicAdd(P.stats + (i < C_OUT ? i : P.stat_stride + i - C_OUT), (double)stat_s[i]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -335,3 +335,205 @@ class NetHandle:
             self.close()
         except Exception:
             pass
+
+
+def softmax_ce(logits, target, want_grad=True):
+    """CrossEntropyLoss(reduction='mean') on the device: (loss f32 [], dlogits f32 [N,C] | None).
+    target: float32 labels (as the loaders deliver them) or int64."""
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2
+    logits, target = logits.contiguous(), target.contiguous()
+    assert target.dtype in (torch.float32, torch.int64) and target.numel() == logits.shape[0]
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits) if want_grad else None
+    with torch.cuda.device(logits.device):
+        check(lib.dmf_softmax_ce(_ptr(logits), _ptr(target), 1 if target.dtype == torch.int64 else 0, logits.shape[0],
+                                 logits.shape[1], _ptr(loss), _ptr(dl), _stream()))
+    return loss, dl
+
+
+class TrainHandle:
+    """Native training step for a GMFNet nn.Module (solver/mainsolver.py:49-55).
+
+    The module's parameters are re-seated as views of ONE flat fp32 tensor (``flat``) with a matching flat
+    gradient tensor (``flat_grad``; every ``p.grad`` is a view of it), so the data-parallel gradient all-reduce is
+    one collective and Adam is one kernel.  The library reads / writes those tensors in place."""
+
+    def __init__(self, module, p, num_classes, max_batch=512, device='cuda:0'):
+        _require_cuda()
+        self.p, self.C, self.max_batch, self.device = p, num_classes, max_batch, str(device)
+        self._h = C.c_void_p()
+        check(lib.dmf_train_create(C.byref(self._h), p, num_classes, max_batch))
+        self.module = module
+        self._bind()
+
+    def _bind(self):
+        named = list(self.module.named_parameters())
+        total = sum(q.numel() for _, q in named)
+        dev = named[0][1].device
+        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        self._views = []
+        with torch.cuda.device(dev):
+            for name, q in named:
+                k = q.numel()
+                self.flat[off:off + k].copy_(q.data.reshape(-1))
+                q.data = self.flat[off:off + k].view(q.shape)
+                q.grad = self.flat_grad[off:off + k].view(q.shape)
+                self._views.append((q, off, k))
+                check(lib.dmf_train_bind(self._h, name.encode(), _ptr(q.data), _ptr(q.grad), k))
+                off += k
+            for name, b in self.module.named_buffers():
+                check(lib.dmf_train_bind(self._h, name.encode(), _ptr(b), C.c_void_p(0), b.numel()))
+            check(lib.dmf_train_finalize(self._h))
+        self._key = self.key(self.module)
+
+    @staticmethod
+    def key(module):
+        return tuple(t.data_ptr() for t in list(module.parameters()) + list(module.buffers()))
+
+    def stale(self):
+        return self._key != self.key(self.module)
+
+    def reseat_grads(self):
+        """Make every p.grad a view of flat_grad again (optimizer.zero_grad(set_to_none=True) drops them)."""
+        for q, off, k in self._views:
+            if q.grad is None or q.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                q.grad = self.flat_grad[off:off + k].view(q.shape)
+
+    def forward(self, ms, pan):
+        assert ms.is_cuda and pan.is_cuda
+        ms, pan = ms.float().contiguous(), pan.float().contiguous()
+        N = ms.shape[0]
+        assert tuple(ms.shape[1:]) == (4, self.p, self.p) and tuple(pan.shape) == (N, 1, 4 * self.p, 4 * self.p)
+        out = torch.empty((N, self.C), dtype=torch.float32, device=ms.device)
+        self._keep = (ms, pan)               # the PAN stem's weight gradient re-reads the input in backward
+        with torch.cuda.device(ms.device):
+            check(lib.dmf_train_forward(self._h, _ptr(ms), _ptr(pan), N, _ptr(out), _stream()))
+        return out
+
+    def backward(self, dlogits):
+        dlogits = dlogits.float().contiguous()
+        with torch.cuda.device(dlogits.device):
+            check(lib.dmf_train_backward(self._h, _ptr(dlogits), _stream()))
+
+    def step_patches(self, ms, pan, target, loss_out=None):
+        """zero grads -> forward -> CrossEntropyLoss(mean) -> backward; returns the loss (0-d CUDA tensor)."""
+        ms, pan, target = ms.float().contiguous(), pan.float().contiguous(), target.contiguous()
+        assert target.dtype in (torch.float32, torch.int64)
+        loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=ms.device)
+        self._keep = (ms, pan)
+        self.flat_grad.zero_()
+        with torch.cuda.device(ms.device):
+            check(lib.dmf_train_step_patches(self._h, _ptr(ms), _ptr(pan), _ptr(target), 1 if target.dtype == torch.int64 else 0,
+                                             ms.shape[0], _ptr(loss), _stream()))
+        return loss
+
+    def step_scene(self, scene, flat_idx, use_mspan=False, loss_out=None):
+        """Same, with the batch cropped from the device scene by flat pixel index (no patches leave the library)."""
+        idx = torch.as_tensor(flat_idx, dtype=torch.int64).to(self.device).contiguous()
+        loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=self.device)
+        self.flat_grad.zero_()
+        with torch.cuda.device(self.device):
+            check(lib.dmf_train_step_scene(self._h, scene._h, _ptr(idx), idx.numel(), 1 if use_mspan else 0, _ptr(loss), _stream()))
+        return loss
+
+    def buffer(self, name, dtype, shape, alias=False):
+        """Test hook: a copy (or, with alias=True, a writable view) of an internal activation / gradient buffer."""
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        check(lib.dmf_train_buffer(self._h, name.encode(), C.byref(ptr), C.byref(nbytes)))
+        n = int(np.prod(shape))
+        item = torch.empty((), dtype=dtype).element_size()
+        assert n * item <= nbytes.value, 'buffer %s holds %d bytes' % (name, nbytes.value)
+        view = _from_ptr(ptr.value, n * item, self.device).view(dtype)[:n].view(shape)
+        return view if alias else view.clone()
+
+    def debug_op(self, op, layer, N):
+        """Test hook: 'pack' | 'fwd' | 'wgrad' | 'dgrad' of one layer on the internal buffers."""
+        code = {'pack': 0, 'fwd': 1, 'wgrad': 2, 'dgrad': 3}[op]
+        lay = {'ms1': 0, 'ms2': 1, 'pan1': 2, 'pan2': 3, 'pan3': 4, 'fuse': 5}[layer]
+        with torch.cuda.device(self.device):
+            check(lib.dmf_train_debug_op(self._h, code, lay, N, _stream()))
+
+    def set_debug(self, swap_lbo_sbo):
+        check(lib.dmf_train_set_debug(self._h, int(swap_lbo_sbo)))
+
+    def close(self):
+        if self._h:
+            lib.dmf_train_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _from_ptr(ptr, nbytes, device):
+    """uint8 CUDA tensor aliasing `nbytes` of device memory at `ptr` (no ownership)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 3, 'strides': None}
+    return torch.as_tensor(h, device=device)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, betas, eps; no weight decay / amsgrad) with the update done by dmf_adam_step.
+    When the parameters are contiguous slices of one flat tensor (TrainHandle re-seats them that way) the whole
+    model is ONE kernel launch; otherwise one launch per tensor.  State layout follows torch's names
+    (step / exp_avg / exp_avg_sq) so checkpoints stay readable (utils/utils.py:82-88)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._flat = None
+
+    def _flat_view(self, group):
+        """(param_flat, grad_flat) if the group's tensors tile one contiguous block in order, else None."""
+        ps = [q for q in group['params'] if q.requires_grad]
+        if not ps or any(q.grad is None for q in ps):
+            return None
+        p0, g0 = ps[0].data_ptr(), ps[0].grad.data_ptr()
+        off = 0
+        for q in ps:
+            if q.data_ptr() != p0 + 4 * off or q.grad.data_ptr() != g0 + 4 * off or q.dtype != torch.float32:
+                return None
+            off += q.numel()
+        key = (p0, g0, off)
+        if self._flat is None or self._flat[0] != key:
+            self._flat = (key, _from_ptr(p0, 4 * off, ps[0].device).view(torch.float32), _from_ptr(g0, 4 * off, ps[0].device).view(torch.float32))
+        return self._flat[1], self._flat[2]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            lr, (b1, b2), eps = float(group['lr']), group['betas'], group['eps']
+            flat = self._flat_view(group)
+            # flat mode: one state entry (whole-model exp_avg / exp_avg_sq) stored under the group's first parameter
+            items = [(group['params'][0], flat[0], flat[1])] if flat is not None else \
+                    [(q, q.data, q.grad) for q in group['params'] if q.grad is not None]
+            for key, pt, gt in items:
+                st = self.state[key]
+                if 'step' not in st or st['exp_avg'].numel() != pt.numel():
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(pt)
+                    st['exp_avg_sq'] = torch.zeros_like(pt)
+                st['step'] += 1
+                assert pt.is_cuda and pt.is_contiguous() and gt.is_contiguous(), 'FusedAdam needs contiguous CUDA tensors (no CPU path)'
+                with torch.cuda.device(pt.device):
+                    check(lib.dmf_adam_step(_ptr(pt), _ptr(gt), _ptr(st['exp_avg']), _ptr(st['exp_avg_sq']), pt.numel(),
+                                            lr, b1, b2, eps, st['step'], _stream()))
+        return loss
+
+    def zero_grad(self, set_to_none=False):
+        """Gradients stay allocated (they are views of the flat buffer the library writes into)."""
+        for group in self.param_groups:
+            flat = self._flat_view(group)
+            if flat is not None:
+                flat[1].zero_()
+            else:
+                for q in group['params']:
+                    if q.grad is not None:
+                        q.grad.zero_()

@@ -42,6 +42,19 @@ SIGNATURES = {
     'dmf_net_get_timing': (i32, [vp, C.POINTER(C.c_float)]),
     'dmf_net_debug_layer': (i32, [vp, i32, i32, vp, vp, i64, vp]),
     'dmf_net_debug_stem': (i32, [vp, i32, vp, vp, i64, vp]),
+    'dmf_train_create': (i32, [C.POINTER(vp), i32, i32, i32]),
+    'dmf_train_destroy': (i32, [vp]),
+    'dmf_train_bind': (i32, [vp, cstr, vp, vp, i64]),
+    'dmf_train_finalize': (i32, [vp]),
+    'dmf_train_forward': (i32, [vp, vp, vp, i64, vp, vp]),
+    'dmf_train_backward': (i32, [vp, vp, vp]),
+    'dmf_softmax_ce': (i32, [vp, vp, i32, i64, i32, vp, vp, vp]),
+    'dmf_adam_step': (i32, [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]),
+    'dmf_train_step_patches': (i32, [vp, vp, vp, vp, i32, i64, vp, vp]),
+    'dmf_train_step_scene': (i32, [vp, vp, vp, i64, i32, vp, vp]),
+    'dmf_train_buffer': (i32, [vp, cstr, C.POINTER(vp), C.POINTER(i64)]),
+    'dmf_train_set_debug': (i32, [vp, i32]),
+    'dmf_train_debug_op': (i32, [vp, i32, i32, i64, vp]),
     'dmf_argmax_confusion': (i32, [vp, vp, i32, i64, i32, vp, vp, vp]),
     'dmf_scatter_labels': (i32, [vp, vp, vp, i64, vp, i32, vp]),
     'dmf_paint_labels': (i32, [vp, i64, vp, i32, vp, vp]),

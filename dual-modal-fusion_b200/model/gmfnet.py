@@ -9,13 +9,18 @@ CUDA-core stems, tcgen05/TMEM implicit-GEMM convolutions fed by TMA, fused head.
 weights are rebuilt whenever a parameter changes.  ``infer_scene`` is the fused whole-scene path
 (gather + network + argmax + confusion matrix without materialising patches).
 
-Training mode builds the same graph from torch ops so that autograd / Adam work (Solver.train);
-native backward kernels are the next scope row.  There is no CPU path: eval-mode
-forward on CPU tensors raises.
+Training (train mode, or grad enabled) also runs on libdmf_b200 (csrc/train.cu): ``forward`` returns
+logits attached to a torch.autograd.Function whose backward is the native backward pass (BatchNorm
+batch statistics, max-pool routing, tcgen05 dgrad / wgrad), so the reference's loop
+``loss = criterion(model(a, b), t.long()); loss.backward(); optimizer.step()``
+(solver/mainsolver.py:49-55) works unchanged with any torch loss / optimizer.  ``train_step`` is the
+fused fast path (forward + CrossEntropyLoss + backward in one library call, gradients written into one
+flat buffer -> a single NCCL all-reduce under torch.distributed, Adam in one kernel).
+There is no CPU path and no torch-op fallback: forward on CPU tensors raises.
 """
 import torch
+import torch.distributed as dist
 import torch.nn as nn
-import torch.nn.functional as F
 
 import dmf
 
@@ -28,6 +33,26 @@ def _conv_bn(cin, cout, k):
     return nn.Sequential(nn.Conv2d(cin, cout, k, padding=k // 2, bias=True), nn.BatchNorm2d(cout))
 
 
+class _NativeTrainFn(torch.autograd.Function):
+    """logits = net(ms, pan) in train mode; the parameters are inputs so that autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, net, ms, pan, *params):
+        h = net.trainer()
+        ctx.h, ctx.n_params = h, len(params)
+        return h.forward(ms, pan)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        h = ctx.h
+        h.flat_grad.zero_()
+        h.backward(dlogits)
+        g = h.flat_grad.clone()                       # the buffer is reused by the next backward
+        h.flat_grad.zero_()
+        grads = tuple(g[off:off + k].view(q.shape) for q, off, k in h._views)
+        return (None, None, None) + grads
+
+
 class Net(nn.Module):
     def __init__(self, args):
         super().__init__()
@@ -35,7 +60,9 @@ class Net(nn.Module):
         self.patch = int(args['patch_size'])
         if str(args.get('schedule', {}).get('activate', 'Relu')).lower() != 'relu':
             raise ValueError("gmfnet: schedule.activate must be Relu")
-        self.max_batch = int(args.get('b200', {}).get('max_batch', 16384)) if isinstance(args.get('b200'), dict) else 16384
+        b200 = args.get('b200') if isinstance(args.get('b200'), dict) else {}
+        self.max_batch = int(b200.get('max_batch', 16384))
+        self.max_train_batch = int(b200.get('max_train_batch', max(512, int(args.get('batchsize', 0) or 0))))
         for name, (cin, cout) in WIDTHS.items():
             setattr(self, name, _conv_bn(cin, cout, 3))
         self.fuse = _conv_bn(128 + 128, C_FUSE, 1)
@@ -43,17 +70,22 @@ class Net(nn.Module):
         self.fc2 = nn.Linear(C_HID, self.num_classes)
         self._native = None
         self._native_key = None
+        self._trainer = None
 
     # ---------------------------------------------------------------- native (sm_100a) inference
     def _weights_key(self):
         ts = list(self.parameters()) + list(self.buffers())
         return tuple((t.data_ptr(), t._version) for t in ts)
 
-    def native(self):
-        """NetHandle with weights matching the current parameters."""
+    def _device(self):
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
-            raise RuntimeError("gmfnet inference needs the model on a CUDA device (no CPU fallback); got %s" % dev)
+            raise RuntimeError("gmfnet needs the model on a CUDA device (no CPU fallback); got %s" % dev)
+        return dev
+
+    def native(self):
+        """NetHandle with weights matching the current parameters."""
+        dev = self._device()
         key = (str(dev),) + self._weights_key()
         if self._native is None or self._native.device != str(dev):
             self._native = dmf.NetHandle(self.patch, self.num_classes, self.max_batch, str(dev))
@@ -66,22 +98,52 @@ class Net(nn.Module):
     def infer_scene(self, scene, row0=0, row1=None, pred_map=None, cm=None):
         return self.native().infer_scene(scene, row0, row1, pred_map, cm)
 
-    # ---------------------------------------------------------------- autograd graph for training
-    def _graph(self, ms, pan):
-        r, mp = F.relu, F.max_pool2d
-        m = r(self.ms1(ms))
-        m = mp(r(self.ms2(m)), 2)
-        q = mp(r(self.pan1(pan)), 2)
-        q = mp(r(self.pan2(q)), 2)
-        q = mp(r(self.pan3(q)), 2)
-        f = r(self.fuse(torch.cat([m, q], dim=1)))
-        return self.fc2(r(self.fc1(f.mean(dim=(2, 3)))))
+    # ---------------------------------------------------------------- native training
+    def trainer(self):
+        """TrainHandle bound to this module's (flattened) parameters."""
+        dev = self._device()
+        if self._trainer is None or self._trainer.stale():
+            if self._trainer is not None:
+                self._trainer.close()
+            self._trainer = dmf.TrainHandle(self, self.patch, self.num_classes, self.max_train_batch, str(dev))
+        # the library updates parameters / BatchNorm buffers through raw pointers (no torch version bump):
+        # whatever the inference handle packed is stale after any training call
+        self._native_key = None
+        return self._trainer
+
+    def train_step(self, ms, pan, target, optimizer):
+        """One fused step of Solver.train(): zero_grad -> forward -> CrossEntropyLoss(mean) -> backward ->
+        (all-reduce of the flat gradient under torch.distributed) -> optimizer.step().  Returns the loss tensor."""
+        h = self.trainer()
+        h.reseat_grads()
+        loss = h.step_patches(ms, pan, target)
+        self._sync_grads(h)
+        optimizer.step()
+        return loss
+
+    def train_step_scene(self, scene, flat_idx, optimizer, use_mspan=False):
+        """The same with the batch cropped from the device scene (K1 + IHS-product input fused in front)."""
+        h = self.trainer()
+        h.reseat_grads()
+        loss = h.step_scene(scene, flat_idx, use_mspan)
+        self._sync_grads(h)
+        optimizer.step()
+        return loss
+
+    @staticmethod
+    def _sync_grads(h):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(h.flat_grad)                          # one bucket: the whole model
+            h.flat_grad.div_(dist.get_world_size())
 
     def forward(self, ms, pan):
-        if self.training or torch.is_grad_enabled():
-            if not ms.is_cuda:
-                raise RuntimeError("gmfnet: tensors must be on a CUDA device (no CPU path)")
-            return self._graph(ms, pan)
+        if not ms.is_cuda:
+            raise RuntimeError("gmfnet: tensors must be on a CUDA device (no CPU path)")
+        if self.training:
+            return _NativeTrainFn.apply(self, ms, pan, *[q for q in self.parameters()])
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+            raise RuntimeError("gmfnet: eval-mode forward with autograd enabled is not implemented natively; "
+                               "wrap inference in torch.no_grad() or call .train()")
         return self.native().forward_patches(ms.float(), pan.float())
 
     def _apply(self, fn, *a, **k):

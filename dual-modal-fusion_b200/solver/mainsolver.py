@@ -73,12 +73,20 @@ class Solver(BaseSolver):
         while self.epoch < self.EPOCH:
             self.cur_model.train()
             bar = self._bar(self.train_loader)
+            # CrossEntropyLoss + a native model: one library call does zero_grad / forward / loss / backward and the
+            # optimizer one kernel (model.train_step); any other loss runs the reference's loop text, with the
+            # network's backward still native (autograd.Function in model/gmfnet.py)
+            fused = isinstance(self.loss, torch.nn.CrossEntropyLoss) and hasattr(self.cur_model, 'train_step') \
+                and not cfg.get('b200', {}).get('autograd_loop', False)
             for data1, data2, target, _, _ in bar:
                 data1, data2, target = data1.to(self.DEVICE), data2.to(self.DEVICE), target.to(self.DEVICE)
-                self.optimizer.zero_grad()
-                loss = self.loss(self.cur_model(data1, data2), target.long())
-                loss.backward()
-                self.optimizer.step()
+                if fused:
+                    loss = self.cur_model.train_step(data1, data2, target, self.optimizer)
+                else:
+                    self.optimizer.zero_grad()
+                    loss = self.loss(self.cur_model(data1, data2), target.long())
+                    loss.backward()
+                    self.optimizer.step()
                 if cfg['nohup']:
                     print("{} times {}th epoch is trained".format(self.time, self.epoch))
                 else:

@@ -1,5 +1,6 @@
 """Optimizer / loss / scheduler / checkpoint factories, same names and file formats as the
-reference's utils/utils.py:8-122 (plain torch objects; no kernel work here)."""
+reference's utils/utils.py:8-122.  ADAM is dmf.FusedAdam (torch.optim.Adam's update in one sm_100a kernel over the
+flattened model, same defaults and state names); the other factories are the plain torch objects."""
 import os
 import random
 
@@ -13,7 +14,8 @@ def make_optimizer(cfg, params):
     sch = cfg['schedule']
     kind = sch['optimizer']
     if kind == "ADAM":
-        return torch.optim.Adam(params, lr=sch['lr'])
+        import dmf
+        return dmf.FusedAdam(params, lr=sch['lr'])
     if kind == "SGD":
         return torch.optim.SGD(params, lr=sch['lr'], momentum=sch['momentum'])
     if kind == "RMSprop":

@@ -155,6 +155,46 @@ int dmf_net_debug_stem(dmf_net* n, int which /*0 ms, 1 pan*/, const float* patch
                        int64_t N, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training step — replaces the inner loop of Solver.train() (solver/mainsolver.py:49-55): forward in train mode
+ * (BatchNorm batch statistics + running-stat update), CrossEntropyLoss(mean) (utils/utils.py:28-29), backward, and
+ * torch.optim.Adam (utils/utils.py:12).  bf16 tensor-core arithmetic with fp32 accumulation; the parameters, their
+ * gradients and the BatchNorm buffers stay the caller's fp32 device tensors (the nn.Module's own storage), bound
+ * once by state_dict name.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dmf_train dmf_train;
+int dmf_train_create(dmf_train** out, int p, int num_classes, int max_batch);
+int dmf_train_destroy(dmf_train* t);
+/* name = state_dict key.  param_dev: fp32 device tensor (int64 for "*.num_batches_tracked"); grad_dev: fp32 gradient
+ * buffer of the same shape (NULL for BatchNorm buffers).  Gradients are ACCUMULATED by dmf_train_backward. */
+int dmf_train_bind(dmf_train* t, const char* name, void* param_dev, float* grad_dev, int64_t numel);
+int dmf_train_finalize(dmf_train* t);
+/* train-mode forward of a batch of N <= max_batch patches: ms [N][4][p][p], pan [N][1][4p][4p] fp32 -> logits [N][C];
+ * activations are kept inside the handle for the backward call. */
+int dmf_train_forward(dmf_train* t, const float* ms_dev, const float* pan_dev, int64_t N, float* logits_out_dev, void* stream);
+/* dlogits [N][C] fp32 = dLoss/dlogits of the last forward -> parameter gradients (accumulated) */
+int dmf_train_backward(dmf_train* t, const float* dlogits_dev, void* stream);
+/* CrossEntropyLoss(reduction='mean'): loss (1 float, overwritten; may be NULL) and dLoss/dlogits (may be NULL).
+ * target: float32 labels as the loaders deliver them, or int64 (target_is_i64) */
+int dmf_softmax_ce(const float* logits_dev, const void* target_dev, int target_is_i64, int64_t N, int C, float* loss_out_dev,
+                   float* dlogits_out_dev, void* stream);
+/* torch.optim.Adam without weight decay / amsgrad over one flat tensor; step = 1 for the first update */
+int dmf_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t numel, float lr,
+                  float beta1, float beta2, float eps, int64_t step, void* stream);
+/* forward + loss + backward in one call, from materialised patches ... */
+int dmf_train_step_patches(dmf_train* t, const float* ms_dev, const float* pan_dev, const void* target_dev, int target_is_i64, int64_t N,
+                           float* loss_out_dev, void* stream);
+/* ... or cropped from the scene by flat pixel index (K1 gather in front; targets = scene labels).  use_mspan: feed the
+ * IHS product's window (dataset_tri's third tensor, train/dataset.py:259-279) as the PAN input. */
+int dmf_train_step_scene(dmf_train* t, const dmf_scene* s, const int64_t* flat_idx_dev, int64_t N, int use_mspan, float* loss_out_dev,
+                         void* stream);
+/* test hooks */
+int dmf_train_buffer(dmf_train* t, const char* name, void** ptr_out, int64_t* bytes_out);
+int dmf_train_set_debug(dmf_train* t, int swap_lbo_sbo);
+/* run one stage on the internal buffers: op 0 pack weights, 1 forward conv, 2 wgrad, 3 dgrad; layer 0..5 = ms1, ms2, pan1, pan2,
+ * pan3, fuse */
+int dmf_train_debug_op(dmf_train* t, int op, int layer, int64_t N, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K4 argmax + confusion — replaces the loop at solver/mainsolver.py:139-141 (train/test.py:58-60):
  * pred = first index of the row maximum; cm[pred][target] += 1 (int64, caller zeroes it).
  * target_dtype: DMF_F32 (the loaders' float labels) or DMF_U8.  pred_out (int64[N]) may be NULL.

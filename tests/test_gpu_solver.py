@@ -8,6 +8,7 @@ import torch
 from oracle import dmf_oracle as orc
 
 pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
 
 
 def c1_cfg(tmp, ms, pan, label, train=0, color=1):
@@ -80,10 +81,14 @@ def test_train_epoch_then_eval_uses_updated_weights(tmp_path):
     s.run()
     assert s.train_time > 0 and (tmp_path / 'out' / '0_weights.pth').exists() and (tmp_path / 'out' / '0_curweights.pth').exists()
     assert s.test_matrix.sum() == len(s.test_loader.indices)
-    # native inference must track the trained parameters: compare with the autograd graph in eval mode
+    # native inference must track the trained parameters: compare with the fp32 oracle network holding the same state_dict
+    from oracle.gmfnet_ref import Net as RefNet
     net = s.cur_model.eval()
+    chk = RefNet(cfg).to(DEV)
+    chk.load_state_dict(net.state_dict())
+    chk.eval()
     d1, d2, _, _, _ = next(iter(s.test_loader))
     with torch.no_grad():
         native = net(d1, d2)
-        graph = net._graph(d1, d2)
+        graph = chk(d1.to(DEV), d2.to(DEV))
     assert torch.allclose(native, graph, rtol=2e-2, atol=5e-3), float((native - graph).abs().max())
