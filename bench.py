@@ -105,6 +105,55 @@ def cpu_reference_run(wl, budget_s, steps=1, warmup=0):
     return per_step_px / total, torch.get_num_threads(), desc, 1e3 * total / max(1, steps)
 
 
+def train_step_metric(dev, world, batch=512, steps=30, warmup=5):
+    """BASELINE.json configs[3]: IHS-input training step, `batch` patches per GPU (data-parallel, weak scaling): K2 IHS
+    product -> K1 tri-gather from the resident scene -> native forward (train-mode BatchNorm) -> CrossEntropyLoss ->
+    native backward -> one flat-gradient all-reduce -> FusedAdam.  CUDA events, max over ranks."""
+    import random
+    import torch.distributed as dist
+    import dmf
+    from oracle import dmf_oracle as orc
+    from image_convert.IHS import draw_offsets
+    from model.gmfnet import Net
+    C, Hs, Ws = 12, 400, 400
+    ms, pan, label = orc.synthetic_scene(Hs, Ws, C - 1, seed=0, label_seed=1)
+    msn = (ms - ms.min()) / (ms.max() - ms.min())
+    pann = (pan - pan.min()) / (pan.max() - pan.min())
+    random.seed(7)
+    offs = draw_offsets(Hs, Ws, 4, 4)
+    mspan = dmf.ihs_tran(torch.from_numpy(msn).to(dev), torch.from_numpy(pann).to(dev), torch.from_numpy(offs).to(dev), device=dev)
+    sc = dmf.Scene.from_raw(ms, pan, P, dev)
+    sc.set_labels(label)
+    sc.set_mspan(np.pad(mspan.cpu().numpy(), ((0, 4 * P - 1), (0, 4 * P - 1)), mode='reflect'))
+    torch.manual_seed(0)
+    net = Net({'Categories_Number': C, 'patch_size': P, 'schedule': {'activate': 'Relu'}, 'b200': {'max_train_batch': batch}}).to(dev).train()
+    opt = dmf.FusedAdam(net.parameters(), lr=1e-3)
+    labelled = torch.from_numpy(np.flatnonzero(label.reshape(-1) != 0)).to(dev)
+    g = torch.Generator(device=dev).manual_seed(1 + (dist.get_rank() if world > 1 else 0))
+    batches = [labelled[torch.randint(0, labelled.numel(), (batch,), device=dev, generator=g)] for _ in range(8)]
+    for i in range(warmup):
+        net.train_step_scene(sc, batches[i % 8], opt, use_mspan=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = dmf.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = net.train_step_scene(sc, batches[i % 8], opt, use_mspan=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t)
+    flops = 3 * net.native().flops_per_patch * batch * world
+    return {'workload': 'C4 IHS-input training step, batch %d per GPU, p=16, 12 classes, data-parallel x%d' % (batch, world),
+            'ms_per_step': ms_step, 'patches_per_s': batch * world / ms_step * 1e3, 'algorithmic_TFLOPs': flops / ms_step / 1e9,
+            'kernels_per_step': (dmf.launch_count() - l0) / steps, 'loss_after': float(loss), 'steps': steps,
+            'collective': 'one NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step' % (net.trainer().flat_grad.numel() * 4 / 1e6) if world > 1 else None}
+
+
 def main():
     # stdout carries exactly one JSON line: park the real fd and point fd 1 at stderr while libraries
     # (NCCL's version banner, tqdm, ...) are active
@@ -124,6 +173,7 @@ def main():
     ap.add_argument('--max-batch', type=int, default=16384)
     ap.add_argument('--cpu-budget-s', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the secondary C4 training-step measurement')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -303,6 +353,9 @@ def main():
                                       'frac_of_sustained_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
                                       'frac_of_burst_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
                                       'ncu_tensor_pipe_active_pct': 'profiles/r01_ncu_summary.json'}}
+
+    if not args.no_train:
+        secondary['train_step'] = train_step_metric(dev, world)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

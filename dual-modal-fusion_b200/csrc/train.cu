@@ -121,58 +121,96 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJobs J) {
     }
 }
 
-// ------------------------------------------------------------------------------------ PAN stem, forward (CUDA cores, fp32)
-// x [N][S][S] fp32 -> Z [N][4][S][S][8] bf16 (conv3x3 1->32, zero padding, no bias) + sum z, sum z^2.
+// ------------------------------------------------------------------------------------ wgrad scratch -> PyTorch layout
+// wgrad_tc_kernel accumulates into fp32 scratch laid out [tap][ci][co] (co contiguous = the TMEM lane index, so every
+// atomic instruction of a warp hits one 128-byte line).  This adds it into the gradient tensor [co][ci][kh][kw];
+// mode 1 (MS stem, hi/lo-split input): dw[co][c] += scratch[c][co] + scratch[4 + c][co].
+struct FinishJob { const float* scratch; float* grad; int co, ci, taps, cin_real, mode; };
+struct FinishJobs { FinishJob j[6]; int count; };
+
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const FinishJobs J) {
+    const FinishJob& q = J.j[blockIdx.y];
+    const int total = q.co * q.cin_real * q.taps;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < total; o += gridDim.x * blockDim.x) {
+        // o enumerates (tap, ci, co) with co fastest so that the scratch reads are coalesced
+        const int co = o % q.co;
+        const int r = o / q.co;
+        const int ci = r % q.cin_real, tap = r / q.cin_real;
+        float v = q.scratch[((size_t)tap * q.ci + ci) * q.co + co];
+        if (q.mode == 1) v += q.scratch[((size_t)tap * q.ci + ci + 4) * q.co + co];
+        q.grad[((size_t)co * q.cin_real + ci) * q.taps + tap] += v;
+    }
+}
+
+// ------------------------------------------------------------------------------------ PAN stem (CUDA cores, fp32)
+// Both stem kernels give one THREAD a column of one 8-channel chunk and march it down `kStemRows` image rows with a
+// sliding 3x3 window: per pixel 3 coalesced loads of the new window row, 72 FMAs on register-resident weights /
+// accumulators, one 16-byte store (forward) or one 16-byte load (wgrad).  A warp = 32 adjacent columns, so every
+// access is a contiguous 128..512-byte run.  Tasks = (patch, row segment, chunk, 32-column group), grid-strided.
+constexpr int kStemRows = 16;
+
+// forward: x [N][S][S] fp32 -> Z [N][4][S][S][8] bf16 (conv3x3 1->32, zero padding, no bias) + sum z, sum z^2
 __global__ void __launch_bounds__(256) pan1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int S, int64_t N,
                                                        __nv_bfloat16* __restrict__ Z, double* __restrict__ stats) {
-    __shared__ __align__(16) float w_s[9][T_PAN1];
     __shared__ float st_s[2][T_PAN1];
-    for (int i = threadIdx.x; i < 9 * T_PAN1; i += blockDim.x) w_s[i % 9][i / 9] = w[i];      // w is [32][1][3][3]
     if (threadIdx.x < 2 * T_PAN1) (&st_s[0][0])[threadIdx.x] = 0.f;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t SS = (int64_t)S * S, total = N * SS;
-    const int64_t total_pad = (total + 31) & ~(int64_t)31;           // whole warps stay in the loop (shuffles below)
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_pad; t += (int64_t)gridDim.x * blockDim.x) {
-        const bool live = t < total;
-        const int64_t n = live ? t / SS : 0;
-        const int px = live ? (int)(t - n * SS) : 0;
-        const int h = px / S, c = px - h * S;
-        float xv[9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int cgroups = S / 32, segs = S / kStemRows;
+    const int64_t SS = (int64_t)S * S, tasks = N * segs * 4 * cgroups;
+    for (int64_t task = (int64_t)blockIdx.x * wpb + warp; task < tasks; task += (int64_t)gridDim.x * wpb) {
+        const int cg = (int)(task % cgroups);
+        int64_t r = task / cgroups;
+        const int ch = (int)(r & 3); r >>= 2;
+        const int seg = (int)(r % segs);
+        const int64_t n = r / segs;
+        const int c = cg * 32 + lane, h0 = seg * kStemRows;
+        float wr[8][9];                          // w is [32][1][3][3]
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int hh = h + k / 3 - 1, cc = c + k % 3 - 1;
-            xv[k] = (live && hh >= 0 && hh < S && cc >= 0 && cc < S) ? __ldg(x + n * SS + (int64_t)hh * S + cc) : 0.f;
-        }
-        float acc[32];
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int co = 0; co < 32; ++co) acc[co] = 0.f;
+            for (int k = 0; k < 9; ++k) wr[j][k] = __ldg(w + (ch * 8 + j) * 9 + k);
+        const float* xp = x + n * SS;
+        auto ld = [&](int hh, int cc) { return (hh >= 0 && hh < S && cc >= 0 && cc < S) ? __ldg(xp + (int64_t)hh * S + cc) : 0.f; };
+        float win[3][3];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
+        for (int d = 0; d < 2; ++d)
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-                const float4 wv = *reinterpret_cast<const float4*>(&w_s[k][4 * c4]);
-                acc[4 * c4] = fmaf(xv[k], wv.x, acc[4 * c4]);
-                acc[4 * c4 + 1] = fmaf(xv[k], wv.y, acc[4 * c4 + 1]);
-                acc[4 * c4 + 2] = fmaf(xv[k], wv.z, acc[4 * c4 + 2]);
-                acc[4 * c4 + 3] = fmaf(xv[k], wv.w, acc[4 * c4 + 3]);
+            for (int e = 0; e < 3; ++e) win[d + 1][e] = ld(h0 - 1 + d, c - 1 + e);
+        float s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        uint4* zo = reinterpret_cast<uint4*>(Z) + ((n * 4 + ch) * SS + (int64_t)h0 * S + c);
+#pragma unroll 4
+        for (int i = 0; i < kStemRows; ++i) {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) { win[0][e] = win[1][e]; win[1][e] = win[2][e]; win[2][e] = ld(h0 + i + 1, c - 1 + e); }
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a = fmaf(win[k / 3][k % 3], wr[j][k], a);
+                acc[j] = a;
+                s1[j] += a;
+                s2[j] = fmaf(a, a, s2[j]);
             }
+            zo[(int64_t)i * S] = pack8(acc);
         }
-        if (live) {
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const float f8[8] = {acc[8 * ch], acc[8 * ch + 1], acc[8 * ch + 2], acc[8 * ch + 3],
-                                     acc[8 * ch + 4], acc[8 * ch + 5], acc[8 * ch + 6], acc[8 * ch + 7]};
-                *reinterpret_cast<uint4*>(Z + ((n * 4 + ch) * SS + px) * 8) = pack8(f8);
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
             }
-        }
-        float q2[32];
+        float m1 = s1[0], m2 = s2[0];
 #pragma unroll
-        for (int co = 0; co < 32; ++co) q2[co] = acc[co] * acc[co];
-        tc::warp_channel_sums(acc, lane);
-        tc::warp_channel_sums(q2, lane);
-        atomicAdd(&st_s[0][lane], acc[0]);
-        atomicAdd(&st_s[1][lane], q2[0]);
+        for (int j = 1; j < 8; ++j) { m1 = lane == j ? s1[j] : m1; m2 = lane == j ? s2[j] : m2; }
+        if (lane < 8) {
+            atomicAdd(&st_s[0][ch * 8 + lane], m1);
+            atomicAdd(&st_s[1][ch * 8 + lane], m2);
+        }
     }
     __syncthreads();
     if (threadIdx.x < T_PAN1) {
@@ -181,51 +219,60 @@ __global__ void __launch_bounds__(256) pan1_fwd_kernel(const float* __restrict__
     }
 }
 
-// PAN stem weight gradient: dW[co][tap] += sum_px dZ[co][px] * x[px + tap].  One warp per image row, lane = channel,
-// sliding 3x3 window of broadcast loads; per-block partials in shared memory, 288 atomics per block at the end.
+// weight gradient: dW[co][tap] += sum_px dZ[co][px] * x[px + tap]
 __global__ void __launch_bounds__(256) pan1_wgrad_kernel(const __nv_bfloat16* __restrict__ dZ, const float* __restrict__ x, int S,
                                                          int64_t N, float* __restrict__ dw) {
-    __shared__ float acc_s[9][T_PAN1];
+    __shared__ float acc_s[T_PAN1][9];
     for (int i = threadIdx.x; i < 9 * T_PAN1; i += blockDim.x) (&acc_s[0][0])[i] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int64_t SS = (int64_t)S * S, rows = N * S;
-    float acc[9];
+    const int cgroups = S / 32, segs = S / kStemRows;
+    const int64_t SS = (int64_t)S * S, tasks = N * segs * cgroups * 4;
+    // chunk = task & 3 is fixed per warp when the stride is a multiple of 4: accumulate across tasks in registers
+    const int64_t stride = (int64_t)gridDim.x * wpb;         // multiple of 8
+    const int ch = warp & 3;
+    float acc[8][9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-    for (int64_t r = (int64_t)blockIdx.x * wpb + warp; r < rows; r += (int64_t)gridDim.x * wpb) {
-        const int64_t n = r / S;
-        const int h = (int)(r - n * S);
-        const float* xr[3];
-        bool ok[3];
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int hh = h + d - 1;
-            ok[d] = hh >= 0 && hh < S;
-            xr[d] = x + n * SS + (int64_t)(ok[d] ? hh : h) * S;
-        }
-        const __nv_bfloat16* dz = dZ + ((n * 4 + (lane >> 3)) * SS + (int64_t)h * S) * 8 + (lane & 7);
-        float win[3][3];      // win[d][0..2] = x[h+d-1][c-1 .. c+1]
+        for (int k = 0; k < 9; ++k) acc[j][k] = 0.f;
+    for (int64_t task = (int64_t)blockIdx.x * wpb + warp; task < tasks; task += stride) {
+        int64_t r = task >> 2;                                // (task & 3) == ch
+        const int cg = (int)(r % cgroups); r /= cgroups;
+        const int seg = (int)(r % segs);
+        const int64_t n = r / segs;
+        const int c = cg * 32 + lane, h0 = seg * kStemRows;
+        const float* xp = x + n * SS;
+        auto ld = [&](int hh, int cc) { return (hh >= 0 && hh < S && cc >= 0 && cc < S) ? __ldg(xp + (int64_t)hh * S + cc) : 0.f; };
+        float win[3][3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { win[d][0] = 0.f; win[d][1] = 0.f; win[d][2] = ok[d] ? __ldg(xr[d]) : 0.f; }
-        for (int c = 0; c < S; ++c) {
+        for (int d = 0; d < 2; ++d)
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                win[d][0] = win[d][1]; win[d][1] = win[d][2];
-                win[d][2] = (ok[d] && c + 1 < S) ? __ldg(xr[d] + c + 1) : 0.f;
-            }
-            const float g = __bfloat162float(dz[(int64_t)c * 8]);
+            for (int e = 0; e < 3; ++e) win[d + 1][e] = ld(h0 - 1 + d, c - 1 + e);
+        const uint4* zi = reinterpret_cast<const uint4*>(dZ) + ((n * 4 + ch) * SS + (int64_t)h0 * S + c);
+#pragma unroll 4
+        for (int i = 0; i < kStemRows; ++i) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) acc[k] = fmaf(g, win[k / 3][k % 3], acc[k]);
+            for (int e = 0; e < 3; ++e) { win[0][e] = win[1][e]; win[1][e] = win[2][e]; win[2][e] = ld(h0 + i + 1, c - 1 + e); }
+            float g8[8];
+            unpack8(__ldg(zi + (int64_t)i * S), g8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc[j][k] = fmaf(g8[j], win[k / 3][k % 3], acc[j][k]);
         }
     }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) atomicAdd(&acc_s[k][lane], acc[k]);
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            float v = acc[j][k];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(&acc_s[ch * 8 + j][k], v);
+        }
     __syncthreads();
-    for (int i = threadIdx.x; i < 9 * T_PAN1; i += blockDim.x) {
-        const int k = i / T_PAN1, co = i % T_PAN1;
-        atomicAdd(dw + co * 9 + k, acc_s[k][co]);
-    }
+    for (int i = threadIdx.x; i < 9 * T_PAN1; i += blockDim.x) atomicAdd(dw + i, (&acc_s[0][0])[i]);
 }
 
 // ------------------------------------------------------------------------------------ BatchNorm apply (+ReLU, +2x2 max-pool)
@@ -321,7 +368,10 @@ __global__ void __launch_bounds__(256) bn_gap_kernel(const __nv_bfloat16* __rest
         for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int o = 16; o; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-        if (lane < 8) g[(it / kch) * C + ch * 8 + lane] = s[lane] * inv;   // s[] is uniform across lanes after the butterfly
+        float mine = s[0];                        // s[] is uniform across lanes after the butterfly: lane j keeps s[j]
+#pragma unroll
+        for (int j = 1; j < 8; ++j) mine = lane == j ? s[j] : mine;
+        if (lane < 8) g[(it / kch) * C + ch * 8 + lane] = mine * inv;
     }
 }
 
@@ -535,8 +585,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     }
 }
 
-// weight / bias gradients of the linears: block b < 64 -> row b of dW1 (= sum_n dhid[n][b] g[n][:]) and db1[b];
-// block 64 + c -> row c of dW2 (= sum_n dlogits[n][c] hid[n][:]) and db2[c].  128 threads.
+// weight / bias gradients of the linears: block x < 64 -> row x of dW1 (= sum_n dhid[n][x] g[n][:]) and db1[x];
+// block 64 + c -> row c of dW2 (= sum_n dlogits[n][c] hid[n][:]) and db2[c].  The batch is split over blockIdx.y
+// (partials combined with atomics); 128 threads, 4 independent accumulators per thread.
 __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ hid, const float* __restrict__ dhid,
                                                          const float* __restrict__ dlogits, int64_t N, int C, float* __restrict__ dw1,
                                                          float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2) {
@@ -545,15 +596,25 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
     const int width = first ? T_FUSE : T_HID, ld = first ? T_HID : C;
     const float* coef = first ? dhid : dlogits;      // [N][ld], column `row`
     const float* act = first ? g : hid;              // [N][width]
-    float acc = 0.f, bsum = 0.f;
-    const int j = threadIdx.x;
-    for (int64_t n = 0; n < N; ++n) {
+    const int64_t per = (N + gridDim.y - 1) / gridDim.y, n0 = blockIdx.y * per, n1 = n0 + per < N ? n0 + per : N;
+    const int j = threadIdx.x < width ? threadIdx.x : width - 1;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
+    int64_t n = n0;
+    for (; n + 4 <= n1; n += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float c = __ldg(coef + (n + u) * ld + row);
+            acc[u] = fmaf(c, __ldg(act + (n + u) * width + j), acc[u]);
+            bsum += c;
+        }
+    }
+    for (; n < n1; ++n) {
         const float c = __ldg(coef + n * ld + row);
-        if (j < width) acc = fmaf(c, __ldg(act + n * width + j), acc);
+        acc[0] = fmaf(c, __ldg(act + n * width + j), acc[0]);
         bsum += c;
     }
-    if (j < width) (first ? dw1 : dw2)[row * width + j] += acc;
-    if (j == 0) (first ? db1 : db2)[row] += bsum;
+    if ((int)threadIdx.x < width) atomicAdd((first ? dw1 : dw2) + row * width + threadIdx.x, (acc[0] + acc[1]) + (acc[2] + acc[3]));
+    if (threadIdx.x == 0) atomicAdd((first ? db1 : db2) + row, bsum);
 }
 
 // CrossEntropyLoss(reduction='mean') forward + gradient (utils/utils.py:28-29; solver/mainsolver.py:53).
@@ -620,6 +681,7 @@ struct TLayer {
     CUtensorMap map_dz_halo{}; // halo / 1x1 tile of dZ (dgrad A operand)
     CUtensorMap map_dz{};      // dense tile of dZ (wgrad A operand)
     int wg_stage = 0, wg_smem = 0;
+    float* wg_scratch = nullptr;   // [taps][cin][cout] fp32 partial sums of wgrad_tc_kernel
 };
 
 struct dmf_train {
@@ -635,6 +697,8 @@ struct dmf_train {
     float *pan1w = nullptr, *dpan1w = nullptr;
     float* dconvw[L_COUNT] = {};
     double* stats = nullptr;   // [L_COUNT][4][kStatStride]
+    float* wg_all = nullptr;   // all wgrad scratch tensors, one allocation (one memset per step)
+    size_t wg_all_floats = 0;
     float *in_ms = nullptr, *in_pan = nullptr, *in_tgt = nullptr;   // staged patches when the batch comes from a scene
     const float* pan_patches = nullptr;                              // PAN input of the last forward (for the stem's wgrad)
     __nv_bfloat16 *X0 = nullptr, *A1 = nullptr, *B1 = nullptr, *B2 = nullptr, *CAT = nullptr;
@@ -686,15 +750,15 @@ static int launch_raw(const LayerGeom& g, const CUtensorMap& map, const __nv_bfl
     return DMF_OK;
 }
 
-template <int CO, int CI, int TAPS, int ROLES, int NP, int WMODE>
-static int launch_wgrad(const dmf_train* t, const TLayer& L, float* dw, int cin_real, int64_t N, cudaStream_t st) {
+template <int CO, int CI, int TAPS, int ROLES, int NP>
+static int launch_wgrad(const dmf_train* t, const TLayer& L, int64_t N, cudaStream_t st) {
     const LayerGeom& g = L.g;
     tc::WgradParams P{};
     P.n_tiles = (int)((N + g.NP - 1) / g.NP) * g.tiles_per_group;
     P.tpg_l2 = g.tpg_l2; P.tiles_x_l2 = g.tiles_x_l2; P.NP_l2 = g.NP_l2; P.PX_l2 = g.PX_l2;
-    P.n_stage = L.wg_stage; P.cin_real = cin_real; P.swap_lbo_sbo = t->swap_lbo_sbo; P.dw = dw;
+    P.n_stage = L.wg_stage; P.swap_lbo_sbo = t->swap_lbo_sbo; P.dw = L.wg_scratch;
     if (TAPS == 9 && g.NP != NP) { set_error("train wgrad geometry/template mismatch"); return DMF_ERR_STATE; }
-    auto kern = tc::wgrad_tc_kernel<CO, CI, TAPS, ROLES, NP, WMODE>;
+    auto kern = tc::wgrad_tc_kernel<CO, CI, TAPS, ROLES, NP>;
     static bool attr_set = false;
     if (!attr_set) {
         DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -745,16 +809,35 @@ static int dgrad_conv(dmf_train* t, int layer, __nv_bfloat16* out, int64_t N, cu
 
 static int wgrad_conv(dmf_train* t, int layer, int64_t N, cudaStream_t st) {
     TLayer& L = t->L[layer];
-    float* dw = t->dconvw[layer];
     const bool np2 = L.g.NP == 2;
     switch (layer) {
-        case L_MS1: return np2 ? launch_wgrad<T_MS1, 16, 9, 1, 2, 1>(t, L, dw, 4, N, st) : launch_wgrad<T_MS1, 16, 9, 1, 1, 1>(t, L, dw, 4, N, st);
+        case L_MS1: return np2 ? launch_wgrad<T_MS1, 16, 9, 1, 2>(t, L, N, st) : launch_wgrad<T_MS1, 16, 9, 1, 1>(t, L, N, st);
         case L_MS2: case L_PAN3:
-            return np2 ? launch_wgrad<128, 64, 9, 3, 2, 0>(t, L, dw, 64, N, st) : launch_wgrad<128, 64, 9, 3, 1, 0>(t, L, dw, 64, N, st);
-        case L_PAN2: return launch_wgrad<T_PAN2, T_PAN1, 9, 1, 1, 0>(t, L, dw, T_PAN1, N, st);
-        case L_FUSE: return launch_wgrad<T_FUSE, T_CAT, 1, 1, 1, 0>(t, L, dw, T_CAT, N, st);
+            return np2 ? launch_wgrad<128, 64, 9, 3, 2>(t, L, N, st) : launch_wgrad<128, 64, 9, 3, 1>(t, L, N, st);
+        case L_PAN2: return launch_wgrad<T_PAN2, T_PAN1, 9, 1, 1>(t, L, N, st);
+        case L_FUSE: return launch_wgrad<T_FUSE, T_CAT, 1, 1, 1>(t, L, N, st);
     }
     return DMF_ERR_ARG;
+}
+
+// scratch of the listed layers -> gradient tensors (one launch)
+static int wgrad_finish(dmf_train* t, const int* layers, int count, cudaStream_t st) {
+    FinishJobs J{};
+    for (int i = 0; i < count; ++i) {
+        const int l = layers[i];
+        const LayerGeom& g = t->L[l].g;
+        J.j[i] = FinishJob{t->L[l].wg_scratch, t->dconvw[l], g.cout, g.cin, g.taps, l == L_MS1 ? 4 : g.cin, l == L_MS1 ? 1 : 0};
+    }
+    J.count = count;
+    wgrad_finish_kernel<<<dim3(72, count), 256, 0, st>>>(J);
+    DMF_LAUNCHED();
+    return DMF_OK;
+}
+
+// PAN stem kernels: one warp per (patch, 16-row segment, chunk, 32-column group)
+static int stem_grid(int64_t N, int S) {
+    const int64_t tasks = N * (S / kStemRows) * 4 * (S / 32);
+    return (int)std::max<int64_t>(1, std::min<int64_t>((tasks + 7) / 8, (int64_t)num_sms() * 4));
 }
 
 static int ew_grid(int64_t items) { return (int)std::min<int64_t>((items + 255) / 256, (int64_t)num_sms() * 8); }
@@ -822,7 +905,7 @@ static int train_forward(dmf_train* t, const float* ms, const float* pan, int64_
     // PAN branch
     {
         const int S = 4 * p;
-        pan1_fwd_kernel<<<ew_grid(N * S * S), 256, 0, st>>>(pan, t->pan1w, S, N, t->Z[L_PAN1], t->bn[L_PAN1].stats);
+        pan1_fwd_kernel<<<stem_grid(N, S), 256, 0, st>>>(pan, t->pan1w, S, N, t->Z[L_PAN1], t->bn[L_PAN1].stats);
         DMF_LAUNCHED();
     }
     DMF_TRY(bn_forward(t, L_PAN1, true, t->B1, T_PAN1 / 8, 0, N, st));
@@ -847,10 +930,11 @@ static int train_backward(dmf_train* t, const float* dlogits, cudaStream_t st) {
     const int64_t N = t->N;
     const int p = t->p;
     DMF_REQUIRE(N > 0, "train_backward: no forward to differentiate");
+    DMF_CUDA(cudaMemsetAsync(t->wg_all, 0, sizeof(float) * t->wg_all_floats, st));
     head_bwd_kernel<<<(int)std::min<int64_t>((N + 7) / 8, num_sms()), 256, head_bwd_smem(t->C), st>>>(dlogits, t->hid, N, t->C, t->fc1w, t->fc2w,
                                                                                                        t->dhid, t->dg);
     DMF_LAUNCHED();
-    head_wgrad_kernel<<<T_HID + t->C, 128, 0, st>>>(t->g, t->hid, t->dhid, dlogits, N, t->C, t->dfc1w, t->dfc1b, t->dfc2w, t->dfc2b);
+    head_wgrad_kernel<<<dim3(T_HID + t->C, (unsigned)std::max<int64_t>(1, std::min<int64_t>(16, N / 32))), 128, 0, st>>>(t->g, t->hid, t->dhid, dlogits, N, t->C, t->dfc1w, t->dfc1b, t->dfc2w, t->dfc2b);
     DMF_LAUNCHED();
     // fusion block
     DMF_TRY(bn_backward<2>(t, L_FUSE, t->dg, 0, 0, N, st));
@@ -872,10 +956,11 @@ static int train_backward(dmf_train* t, const float* dlogits, cudaStream_t st) {
     DMF_TRY(bn_backward<0>(t, L_PAN1, t->dA, T_PAN1 / 8, 0, N, st));
     {
         const int S = 4 * p;
-        pan1_wgrad_kernel<<<(int)std::min<int64_t>((N * S + 7) / 8, (int64_t)num_sms() * 4), 256, 0, st>>>(t->dZ, t->pan_patches, S, N, t->dpan1w);
+        pan1_wgrad_kernel<<<stem_grid(N, S), 256, 0, st>>>(t->dZ, t->pan_patches, S, N, t->dpan1w);
         DMF_LAUNCHED();
     }
-    return DMF_OK;
+    const int all[5] = {L_MS1, L_MS2, L_PAN2, L_PAN3, L_FUSE};
+    return wgrad_finish(t, all, 5, st);
 }
 
 }  // namespace dmf
@@ -1001,6 +1086,15 @@ int dmf_train_finalize(dmf_train* t) {
             DMF_TRY(dalloc(t, (std::string("w_") + kBlk[l]).c_str(), &t->L[l].w, n));
             DMF_TRY(dalloc(t, (std::string("wd_") + kBlk[l]).c_str(), &t->L[l].wd, n));
         }
+        {
+            const int lw[5] = {L_MS1, L_MS2, L_PAN2, L_PAN3, L_FUSE};
+            size_t tot = 0;
+            for (int l : lw) tot += (size_t)t->L[l].g.taps * t->L[l].g.cin * t->L[l].g.cout;
+            DMF_TRY(dalloc(t, "wg_scratch", &t->wg_all, tot));
+            t->wg_all_floats = tot;
+            size_t off = 0;
+            for (int l : lw) { t->L[l].wg_scratch = t->wg_all + off; off += (size_t)t->L[l].g.taps * t->L[l].g.cin * t->L[l].g.cout; }
+        }
         // tensor maps: layer inputs (forward + wgrad B operand), dZ views (dgrad A operand, wgrad A operand)
         DMF_TRY(make_map(&t->L[L_MS1].map_in, t->L[L_MS1].g, t->X0, t->NB));
         DMF_TRY(make_map(&t->L[L_MS2].map_in, t->L[L_MS2].g, t->A1, t->NB));
@@ -1107,13 +1201,17 @@ int dmf_train_debug_op(dmf_train* t, int op, int layer, int64_t N, void* stream)
     if (op == 1) {
         DMF_CUDA(cudaMemsetAsync(t->bn[layer].stats, 0, sizeof(double) * 4 * kStatStride, st));
         if (layer != L_PAN1) return fwd_conv(t, layer, N, st);
-        pan1_fwd_kernel<<<ew_grid(N * S * S), 256, 0, st>>>(t->in_pan, t->pan1w, S, N, t->Z[L_PAN1], t->bn[L_PAN1].stats);
+        pan1_fwd_kernel<<<stem_grid(N, S), 256, 0, st>>>(t->in_pan, t->pan1w, S, N, t->Z[L_PAN1], t->bn[L_PAN1].stats);
         DMF_LAUNCHED();
         return DMF_OK;
     }
     if (op == 2) {
-        if (layer != L_PAN1) return wgrad_conv(t, layer, N, st);
-        pan1_wgrad_kernel<<<(int)std::min<int64_t>((N * S + 7) / 8, (int64_t)num_sms() * 4), 256, 0, st>>>(t->dZ, t->in_pan, S, N, t->dpan1w);
+        if (layer != L_PAN1) {
+            DMF_CUDA(cudaMemsetAsync(t->wg_all, 0, sizeof(float) * t->wg_all_floats, st));
+            DMF_TRY(wgrad_conv(t, layer, N, st));
+            return wgrad_finish(t, &layer, 1, st);
+        }
+        pan1_wgrad_kernel<<<stem_grid(N, S), 256, 0, st>>>(t->dZ, t->in_pan, S, N, t->dpan1w);
         DMF_LAUNCHED();
         return DMF_OK;
     }

@@ -13,8 +13,8 @@
 //
 // One tcgen05.mma = D_tap[128 co, CI] += dZ_tile[16 px, 128 co]^T * A_tap[16 px, CI] (M = 128, N = CI, K = 16 pixels =
 // two rows of 8).  The accumulators of all taps stay in TMEM for the whole kernel (persistent over this
-// CTA's pixel tiles, TAPS/ROLES x CI columns); one epilogue at the end adds them to the fp32 gradient in
-// PyTorch's [co][ci][kh][kw] layout with atomics.  When 9 x CI columns do not fit in TMEM the taps are split
+// CTA's pixel tiles, TAPS/ROLES x CI columns); one epilogue at the end adds them with atomics to an fp32 scratch
+// tensor [tap][ci][co] (see below).  When 9 x CI columns do not fit in TMEM the taps are split
 // by kernel row over ROLES = 3 CTAs that walk the same tiles.  Layers with 64 output channels still issue
 // M = 128: rows 64..127 read whatever follows the dZ tile in shared memory and are never looked at.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = final epilogue.
@@ -28,9 +28,8 @@ struct WgradParams {
     int n_tiles;        // pixel tiles (same tiling as the forward layer)
     int tpg_l2, tiles_x_l2, NP_l2, PX_l2;
     int n_stage;
-    int cin_real;       // channels of the fp32 weight tensor (4 for the hi/lo-split MS stem, else CI)
     int swap_lbo_sbo;   // diagnostics: exchange the two descriptor strides
-    float* dw;          // fp32 [CO][cin_real][TAPS], accumulated
+    float* dw;          // fp32 scratch [TAPS][CI][CO], accumulated (co contiguous: one 128-byte line per warp atomic)
 };
 
 // instruction descriptor: bf16 x bf16 -> f32, A and B both MN-major (bits 15, 16)
@@ -38,9 +37,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
     return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
-// WMODE 0: dw[co][ci][tap] += D[co][ci].   WMODE 1 (MS stem, CI = 16 = [hi0-3, lo0-3 | hi0-3, 0]): the
-// input was split x = hi + lo, so dw[co][c][tap] += D[co][c] + D[co][4 + c] for c < 4.
-template <int CO, int CI, int TAPS, int ROLES, int NP, int WMODE>
+// (Measured on B200: with the atomics going straight to PyTorch's [co][ci][kh][kw] layout every lane of a warp hit
+// a different cache line and the epilogue cost 2-10x the MMAs; hence the co-contiguous scratch + one small
+// re-layout kernel, wgrad_finish_kernel in train.cu, which also folds the hi/lo halves of the MS stem.)
+template <int CO, int CI, int TAPS, int ROLES, int NP>
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap dz_map,
                                                           const __grid_constant__ CUtensorMap a_map, const WgradParams P) {
     constexpr int MCH = CO / 8, KCH = CI / 8;
@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 #pragma unroll 1
             for (int tp = 0; tp < TPR; ++tp) {
                 const int tap = role * TPR + tp;
-                if (WMODE == 1) {
+                float* const dst = P.dw + (size_t)tap * CI * CO + co;
+                if (CI == 16) {
                     uint32_t v[16];
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -165,16 +166,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
                                  : "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        atomicAdd(P.dw + ((size_t)co * P.cin_real + c) * TAPS + tap, __uint_as_float(v[c]) + __uint_as_float(v[4 + c]));
+                    for (int c = 0; c < 16; ++c) atomicAdd(dst + (size_t)c * CO, __uint_as_float(v[c]));
                 } else {
 #pragma unroll 1
                     for (int c0 = 0; c0 < CI; c0 += 32) {
                         uint32_t v[32];
                         tmem_ld32(t_row + (uint32_t)(tp * CI + c0), v);
 #pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            atomicAdd(P.dw + ((size_t)co * P.cin_real + c0 + c) * TAPS + tap, __uint_as_float(v[c]));
+                        for (int c = 0; c < 32; ++c) atomicAdd(dst + (size_t)(c0 + c) * CO, __uint_as_float(v[c]));
                     }
                 }
             }
