@@ -1,0 +1,611 @@
+// Scene-dense whole-scene inference: GMFNet evaluated as scene-level maps instead of per-patch tensors.
+//
+// Replaces the two whole-scene loader passes of Solver.color() and the full-loader Solver.test()
+// (solver/mainsolver.py:104-141, 167-185), where the patches of neighbouring pixels overlap in all but one row /
+// column.  Patch (x, y) covers MS positions X = x + i, Y = y + j (i, j in [0, p)) and PAN pooled-once positions
+// U = 2x + u, V = 2y + v (u, v in [0, 2p)).  A layer's value at a patch-relative position depends on the absolute
+// position and on the position's border class only (see dense_tc.cuh), so per row band [r0, r1) of anchors:
+//
+//   scene --ms_stem_map--> A  [9 ][ 8][R][C][8]     9  = {first, interior, last}^2 of the 3x3/pad-1 stem conv
+//   A  --conv_dense 25 cls--> Z [25][16][R][C][8]   25 = {0, 1, interior, p-2, p-1}^2
+//   Z  --pool_s1-----------> CAT[9 ][0..15]         2x2 max over (X..X+1, Y..Y+1); pooled cell k = 0 reads classes (0,1), ...
+//   scene --pan_stem_map--> B1 [9 ][ 4][2R][2C][8]  stem conv + pool, on the pooled-once grid
+//   B1 --conv_dense 5+20 cls--> Z [25][8][2R][2C][8]  (edge row classes exist on one row parity: row stride 2)
+//   Z  --pool_s2-----------> B2 [9 ][ 8][R][C][8]   aligned 2x2 max (the pooled-once grid moves 2 cells per pixel)
+//   B2 --conv_dense 25 cls--> Z --pool_s1--> CAT[9][16..31]
+//   CAT --conv_dense 1x1, 9 cls--> F [9][16][R][C][8]
+//   F  --head_dense--> per pixel: mean over the (p/2)^2 strided samples F[cls(k),cls(l)][x+2k][y+2l], 2 linears,
+//                      argmax, confusion matrix, label map
+// with R = (r1 - r0) + p - 1 rows and C = W + p - 1 columns.  Positions a band never needs hold don't-care values
+// (they only ever feed other don't-care positions).  Results equal the per-patch path up to fp32 summation order.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "dense_tc.cuh"
+#include "net_types.cuh"
+
+namespace dmf {
+
+struct DenseWs {
+    int W = 0, band = 0, p = 0, R1 = 0, C1 = 0;
+    __nv_bfloat16 *A = nullptr, *Z = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr, *F = nullptr;
+    float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
+    __nv_bfloat16* w_pan2 = nullptr;                 // tap-major packing of pan2 (the per-patch path may use the row-pair one)
+    CUtensorMap mapA, mapB1, mapB1s2, mapB2, mapCAT;
+    cudaEvent_t ev[12] = {};
+    float stage_ms[12] = {};
+    size_t bytes = 0;
+};
+
+// ---------------------------------------------------------------------------------------------- stem maps
+// masked tap sums of one output position: t[k], k = (dy+1)*3 + (dx+1)  ->  s[rc*3 + cc]
+// rc: 0 = first row of a patch (no dy = -1 taps), 1 = interior, 2 = last row (no dy = +1); cc likewise for dx.
+__device__ __forceinline__ void masked_sums(const float (&t)[9], float (&s)[9]) {
+    float u[3][3];                    // u[dy][cc]
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        u[d][0] = t[3 * d + 1] + t[3 * d + 2];
+        u[d][1] = (t[3 * d] + t[3 * d + 1]) + t[3 * d + 2];
+        u[d][2] = t[3 * d] + t[3 * d + 1];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        s[0 + c] = u[1][c] + u[2][c];
+        s[3 + c] = (u[0][c] + u[1][c]) + u[2][c];
+        s[6 + c] = u[0][c] + u[1][c];
+    }
+}
+
+// MS stem (conv3x3 4->64 + BN + ReLU) at every position of the band: ms = padded scene [Hp][Wp] float4, band-local
+// row Xl <-> scene row r0 + Xl.  w: fp32 [64][4][3][3].  grid.y = channel chunk.  out: A[9][8][R1][C1][8].
+__global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restrict__ ms, int Hp, int Wp, int r0, int rows, int R1, int C1,
+                                                          const float* __restrict__ w, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ A) {
+    __shared__ float w_s[8][36], sc_s[8], sh_s[8];
+    const int ch = blockIdx.y;
+    for (int i = threadIdx.x; i < 8 * 36; i += blockDim.x) w_s[i / 36][i % 36] = w[ch * 8 * 36 + i];
+    if (threadIdx.x < 8) { sc_s[threadIdx.x] = scale[ch * 8 + threadIdx.x]; sh_s[threadIdx.x] = shift[ch * 8 + threadIdx.x]; }
+    __syncthreads();
+    const int64_t total = (int64_t)rows * C1;
+    const int64_t plane = (int64_t)R1 * C1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int Xl = (int)(i / C1), Y = (int)(i % C1);
+        const int X = r0 + Xl;
+        float4 nb[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int xx = X + k / 3 - 1, yy = Y + k % 3 - 1;
+            nb[k] = (xx >= 0 && xx < Hp && yy >= 0 && yy < Wp) ? __ldg(ms + (int64_t)xx * Wp + yy) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t out[9][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t[9], s[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k)      // weight index [j][band][k]
+                t[k] = fmaf(nb[k].w, w_s[j][27 + k], fmaf(nb[k].z, w_s[j][18 + k], fmaf(nb[k].y, w_s[j][9 + k], nb[k].x * w_s[j][k])));
+            masked_sums(t, s);
+#pragma unroll
+            for (int v = 0; v < 9; ++v) {
+                const float y = fmaxf(fmaf(s[v], sc_s[j], sh_s[j]), 0.f);
+                const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y));
+                if (j & 1) out[v][j >> 1] |= b << 16;
+                else out[v][j >> 1] = b;
+            }
+        }
+        uint4* o = reinterpret_cast<uint4*>(A) + ((int64_t)ch * R1 + Xl) * C1 + Y;
+#pragma unroll
+        for (int v = 0; v < 9; ++v) o[(int64_t)v * 8 * plane] = make_uint4(out[v][0], out[v][1], out[v][2], out[v][3]);
+    }
+}
+
+// PAN stem (conv3x3 1->32 + BN + ReLU + maxpool2) on the pooled grid: band-local pooled row Ul <-> pooled row u0 + Ul
+// = PAN rows 2(u0+Ul), 2(u0+Ul)+1.  The pooling grid is aligned to every patch origin (4x is even).  A pooled cell on
+// the first pooled row of a patch = max(first-row variant of its upper conv row, interior variant of its lower one).
+// w: fp32 [32][1][3][3].  grid.y = channel chunk.  out: B1[9][4][R2][C2][8].
+__global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restrict__ pan, int H4p, int W4p, int pitch, int u0, int rows,
+                                                           int R2, int C2, const float* __restrict__ w, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ B1) {
+    __shared__ float w_s[8][9], sc_s[8], sh_s[8];
+    const int ch = blockIdx.y;
+    for (int i = threadIdx.x; i < 72; i += blockDim.x) w_s[i / 9][i % 9] = w[ch * 72 + i];
+    if (threadIdx.x < 8) { sc_s[threadIdx.x] = scale[ch * 8 + threadIdx.x]; sh_s[threadIdx.x] = shift[ch * 8 + threadIdx.x]; }
+    __syncthreads();
+    const int64_t total = (int64_t)rows * C2;
+    const int64_t plane = (int64_t)R2 * C2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int Ul = (int)(i / C2), PY = (int)(i % C2);
+        const int PX = u0 + Ul;
+        float xw[4][4];                  // PAN rows 2PX-1 .. 2PX+2, cols 2PY-1 .. 2PY+2
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int xx = 2 * PX - 1 + a, yy = 2 * PY - 1 + b;
+                xw[a][b] = (xx >= 0 && xx < H4p && yy >= 0 && yy < W4p) ? __ldg(pan + (int64_t)xx * pitch + yy) : 0.f;
+            }
+        uint32_t out[9][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s[2][2][9];            // masked sums of the 4 conv positions of this pooled cell
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float t[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) t[k] = xw[a + k / 3][b + k % 3] * w_s[j][k];
+                    masked_sums(t, s[a][b]);
+                }
+#pragma unroll
+            for (int ey = 0; ey < 3; ++ey)
+#pragma unroll
+                for (int ex = 0; ex < 3; ++ex) {
+                    const int ra = ey == 0 ? 0 : 1, rb = ey == 2 ? 2 : 1, ca = ex == 0 ? 0 : 1, cb = ex == 2 ? 2 : 1;
+                    float m = fmaf(s[0][0][ra * 3 + ca], sc_s[j], sh_s[j]);
+                    m = fmaxf(m, fmaf(s[0][1][ra * 3 + cb], sc_s[j], sh_s[j]));
+                    m = fmaxf(m, fmaf(s[1][0][rb * 3 + ca], sc_s[j], sh_s[j]));
+                    m = fmaxf(m, fmaf(s[1][1][rb * 3 + cb], sc_s[j], sh_s[j]));
+                    const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(m, 0.f)));
+                    const int v = ey * 3 + ex;
+                    if (j & 1) out[v][j >> 1] |= bits << 16;
+                    else out[v][j >> 1] = bits;
+                }
+        }
+        uint4* o = reinterpret_cast<uint4*>(B1) + ((int64_t)ch * R2 + Ul) * C2 + PY;
+#pragma unroll
+        for (int v = 0; v < 9; ++v) o[(int64_t)v * 4 * plane] = make_uint4(out[v][0], out[v][1], out[v][2], out[v][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- pooling between maps
+__device__ __forceinline__ uint4 max4(uint4 a, uint4 b) {
+    return make_uint4(tc::max_bf16x2(a.x, b.x), tc::max_bf16x2(a.y, b.y), tc::max_bf16x2(a.z, b.z), tc::max_bf16x2(a.w, b.w));
+}
+// conv class of the two rows (columns) a pooled cell of border class a covers: first cell -> (0, 1), interior -> (2, 2), last -> (3, 4)
+__device__ __forceinline__ int pool_cls(int a, int s) { return a == 0 ? s : a == 1 ? 2 : 3 + s; }
+
+// STRIDE 1 (ms2, pan3): out[(a,b)][ch][X][Y] = max_{s,t} Z[(pool_cls(a,s), pool_cls(b,t))][ch][X+s][Y+t], Z and out on the same grid.
+// STRIDE 2 (pan2):      out[(a,b)][ch][X][Y] = max_{s,t} Z[...][ch][2X+s][2Y+t], Z on the (2 rows) x (2 cols) grid.
+template <int STRIDE>
+__global__ void __launch_bounds__(256) pool_maps_kernel(const uint4* __restrict__ Z, int zch, int rows, int R1, int C1, uint4* __restrict__ out,
+                                                        int out_chunks, int out_chunk0) {
+    const int64_t per_plane = (int64_t)zch * rows * C1;
+    const int64_t total = 9 * per_plane;
+    const int ZR = STRIDE * R1, ZC = STRIDE * C1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int Y = (int)(i % C1);
+        int64_t r = i / C1;
+        const int X = (int)(r % rows); r /= rows;
+        const int ch = (int)(r % zch);
+        const int ab = (int)(r / zch);
+        const int a = ab / 3, b = ab % 3;
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);                      // post-ReLU values are >= 0
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int zr = STRIDE * X + s, zc = STRIDE * Y + t;
+                if (zr < ZR && zc < ZC) {
+                    const int cls = pool_cls(a, s) * 5 + pool_cls(b, t);
+                    m = max4(m, __ldg(Z + (((int64_t)cls * zch + ch) * ZR + zr) * ZC + zc));
+                }
+            }
+        out[(((int64_t)ab * out_chunks + out_chunk0 + ch) * R1 + X) * C1 + Y] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- head
+// One block = 32 consecutive pixels of one anchor row.  Phase 1: warp w = channel chunk w, lane = pixel: the global
+// average pool is a strided gather from the 9 F planes (512-byte coalesced warp loads, (p/2)^2 of them).  Phase 2:
+// warp per pixel, the two linears from shared-memory weights, first-maximum argmax, confusion matrix (per-block
+// shared histogram -> 64-bit global atomics), label map.
+constexpr int kDenseHeadThreads = 512;
+static size_t dense_head_smem(int C) {
+    return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + C_FUSE * 32 + (kDenseHeadThreads / 32) * C_HID) +
+           sizeof(unsigned int) * C * C;
+}
+
+__global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const uint4* __restrict__ F, int R1, int C1, int p, int nb, int W, int C,
+                                                                       const float* __restrict__ fc1t, const float* __restrict__ fc1b,
+                                                                       const float* __restrict__ fc2t, const float* __restrict__ fc2b,
+                                                                       int64_t pix0 /* flat index of the band's first pixel */,
+                                                                       const uint8_t* __restrict__ label, float* __restrict__ logits_out,
+                                                                       unsigned long long* __restrict__ cm, uint8_t* __restrict__ pred_map) {
+    extern __shared__ __align__(16) float hs[];
+    float* w1 = hs;                                   // [128][64]
+    float* w2 = w1 + C_FUSE * C_HID;                  // [64][C]
+    float* b1 = w2 + C_HID * C;
+    float* b2 = b1 + C_HID;
+    float* gbuf = b2 + ((C + 3) & ~3);                // [128 channels][32 pixels]
+    float* hidb = gbuf + C_FUSE * 32;                 // per warp [64]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(hidb + (kDenseHeadThreads / 32) * C_HID);
+    for (int i = threadIdx.x; i < C_FUSE * C_HID; i += blockDim.x) w1[i] = fc1t[i];
+    for (int i = threadIdx.x; i < C_HID * C; i += blockDim.x) w2[i] = fc2t[i];
+    if (threadIdx.x < C_HID) b1[threadIdx.x] = fc1b[threadIdx.x];
+    if (threadIdx.x < C) b2[threadIdx.x] = fc2b[threadIdx.x];
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P2 = p >> 1;
+    const float inv = 1.0f / (float)(P2 * P2);
+    const int segs = (W + 31) >> 5;
+    const int n_seg = nb * segs;
+    float* hid = hidb + warp * C_HID;
+    for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+        const int xl = seg / segs, y0 = (seg - xl * segs) << 5;
+        {
+            const int y = y0 + lane;
+            float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (y < W) {
+                for (int k = 0; k < P2; ++k) {
+                    const int a = k == 0 ? 0 : (k == P2 - 1 ? 2 : 1);
+                    for (int l = 0; l < P2; ++l) {
+                        const int b = l == 0 ? 0 : (l == P2 - 1 ? 2 : 1);
+                        const uint4 v = __ldg(F + ((((int64_t)(a * 3 + b) * 16 + warp) * R1 + xl + 2 * k) * C1 + y + 2 * l));
+                        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+                            s[2 * e] += f.x;
+                            s[2 * e + 1] += f.y;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gbuf[(warp * 8 + j) * 32 + lane] = s[j] * inv;
+        }
+        __syncthreads();
+        for (int q = 0; q < 2; ++q) {
+            const int px = warp * 2 + q;
+            const int y = y0 + px;
+            if (y >= W) break;                                    // warp-uniform
+            float h0 = b1[lane], h1 = b1[lane + 32];
+#pragma unroll 8
+            for (int k = 0; k < C_FUSE; ++k) {
+                const float g = gbuf[k * 32 + px];
+                h0 = fmaf(g, w1[k * C_HID + lane], h0);
+                h1 = fmaf(g, w1[k * C_HID + lane + 32], h1);
+            }
+            hid[lane] = fmaxf(h0, 0.f);
+            hid[lane + 32] = fmaxf(h1, 0.f);
+            __syncwarp();
+            const int64_t n = (int64_t)xl * W + y;                // pixel index inside the band
+            float l0 = -INFINITY, l1 = -INFINITY;
+            if (lane < C) {
+                float a = b2[lane];
+#pragma unroll 8
+                for (int k = 0; k < C_HID; ++k) a = fmaf(hid[k], w2[k * C + lane], a);
+                l0 = a;
+                if (logits_out) logits_out[n * C + lane] = a;
+            }
+            if (lane + 32 < C) {
+                float a = b2[lane + 32];
+#pragma unroll 8
+                for (int k = 0; k < C_HID; ++k) a = fmaf(hid[k], w2[k * C + lane + 32], a);
+                l1 = a;
+                if (logits_out) logits_out[n * C + lane + 32] = a;
+            }
+            // argmax with torch.max semantics: the first (lowest) index among equal maxima
+            float bv = l0;
+            int bi = lane;
+            if (l1 > bv) { bv = l1; bi = lane + 32; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                const int64_t kflat = pix0 + n;
+                if (pred_map) pred_map[kflat] = (uint8_t)bi;
+                if (cm) {
+                    const int lab = label[kflat];
+                    if (lab < C) atomicAdd(&hist[bi * C + lab], 1u);
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    if (cm)
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+            if (hist[i]) atomicAdd(&cm[i], (unsigned long long)hist[i]);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int make_dense_map(CUtensorMap* m, const void* base, int planes, int kch, int rows, int cols, int box_cols, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DMF_ERR_CUDA; }
+    cuuint64_t dims[4] = {8ull * cols, (cuuint64_t)planes, (cuuint64_t)rows, (cuuint64_t)kch};
+    cuuint64_t strides[3] = {(cuuint64_t)kch * rows * cols * 16, (cuuint64_t)cols * 16, (cuuint64_t)rows * cols * 16};
+    cuuint32_t box[4] = {(cuuint32_t)(8 * box_cols), 1, (cuuint32_t)box_rows, (cuuint32_t)kch}, es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (dense map %dx%d, %d planes) failed: CUresult %d", rows, cols, planes, (int)r); return DMF_ERR_CUDA; }
+    return DMF_OK;
+}
+
+// variant of the input row read by tap dy (0..2) of an output row of class c (0, 1, interior, S-2, S-1); -1 = outside the patch
+static const int kTapVariant[5][3] = {{-1, 0, 1}, {0, 1, 1}, {1, 1, 1}, {1, 1, 2}, {1, 2, -1}};
+
+static void build_cls(tc::DenseCls& c, int cr, int cc, int out_plane, int row0) {
+    memset(&c, 0, sizeof(c));
+    c.out_plane = (int16_t)out_plane;
+    c.row0 = (int16_t)row0;
+    for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx) {
+            const int vr = kTapVariant[cr][dy], vc = kTapVariant[cc][dx];
+            if (vr < 0 || vc < 0) continue;
+            const int plane = vr * 3 + vc;
+            int s = 0;
+            while (s < c.n_steps && c.in_plane[s] != plane) ++s;
+            if (s == c.n_steps) { c.in_plane[s] = (int16_t)plane; c.mask[s] = 0; ++c.n_steps; }
+            c.mask[s] |= (uint16_t)(1u << (dy * 3 + dx));
+        }
+}
+
+template <int CI, int CO, int TAPS, int RS, int G>
+static int launch_dense(const CUtensorMap& map, tc::DenseParams& P, cudaStream_t st) {
+    constexpr int HR = RS * 15 + 3;
+    constexpr size_t a_stage = (size_t)(CI / 8) * (TAPS == 9 ? HR * tc::kPitch * 16 : 128 * 16);
+    constexpr size_t fixed = (size_t)TAPS * CI * CO * 2 + 2 * CO * 4 + 26 * 8 + 16;
+    static_assert(fixed + a_stage <= (size_t)kSmemLimit, "dense layer does not fit in shared memory");
+    P.n_stage = (int)std::min<size_t>(8, (kSmemLimit - fixed) / a_stage);
+    P.n_tiles = P.tiles_x * P.tiles_y * P.n_cls;
+    auto kern = tc::conv_dense_kernel<CI, CO, TAPS, RS, G>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr_set = true;
+    }
+    if (P.n_tiles <= 0) return DMF_OK;
+    kern<<<std::min(P.n_tiles, num_sms()), 64 + 128 * G, fixed + (size_t)P.n_stage * a_stage, st>>>(map, P);
+    DMF_LAUNCHED();
+    return DMF_OK;
+}
+
+int dense_pack(dmf_net* n) {
+    if (!n->dense) n->dense = new DenseWs();
+    DenseWs* d = n->dense;
+    auto* w1 = param(n, "ms1.0.weight", (size_t)C_MS1 * 4 * 9);
+    auto* wp = param(n, "pan1.0.weight", (size_t)C_PAN1 * 9);
+    auto* w2 = param(n, "pan2.0.weight", (size_t)C_PAN2 * C_PAN1 * 9);
+    if (!w1 || !wp || !w2) return DMF_ERR_STATE;
+    DMF_TRY(to_device(&d->w_ms1, *w1));
+    DMF_TRY(to_device(&d->w_pan1, *wp));
+    std::vector<__nv_bfloat16> pk((size_t)9 * C_PAN1 * C_PAN2);
+    for (int tap = 0; tap < 9; ++tap)
+        for (int ci = 0; ci < C_PAN1; ++ci)
+            for (int co = 0; co < C_PAN2; ++co)
+                pk[(((size_t)tap * (C_PAN1 / 8) + ci / 8) * C_PAN2 + co) * 8 + ci % 8] =
+                    __float2bfloat16_rn((*w2)[((size_t)co * C_PAN1 + ci) * 9 + tap]);
+    DMF_TRY(to_device(&d->w_pan2, pk));
+    return DMF_OK;
+}
+
+static void dense_free_ws(DenseWs* d) {
+    __nv_bfloat16* bs[] = {d->A, d->Z, d->CAT, d->B1, d->B2, d->F};
+    for (auto* b : bs) cudaFree(b);
+    d->A = d->Z = d->CAT = d->B1 = d->B2 = d->F = nullptr;
+    d->W = d->band = 0;
+    d->bytes = 0;
+}
+
+void dense_release(dmf_net* n) {
+    if (!n->dense) return;
+    DenseWs* d = n->dense;
+    dense_free_ws(d);
+    cudaFree(d->w_ms1); cudaFree(d->w_pan1); cudaFree(d->w_pan2);
+    for (auto& e : d->ev) if (e) cudaEventDestroy(e);
+    delete d;
+    n->dense = nullptr;
+}
+
+// workspace for bands of `band` anchor rows of a scene W pixels wide
+static int dense_prepare(dmf_net* n, int W, int band) {
+    DenseWs* d = n->dense;
+    if (d->A && d->W == W && d->band == band && d->p == n->p) return DMF_OK;
+    DMF_CUDA(cudaDeviceSynchronize());
+    dense_free_ws(d);
+    const int p = n->p;
+    const size_t R1 = band + p - 1, C1 = W + p - 1, px = R1 * C1;
+    const size_t sA = px * 9 * C_MS1 * 2, sZ = px * 25 * 32 * 16, sCAT = px * 9 * C_CAT * 2, sB1 = px * 4 * 9 * C_PAN1 * 2,
+                 sB2 = px * 9 * C_PAN2 * 2, sF = px * 9 * C_FUSE * 2;
+    DMF_CUDA(cudaMalloc(&d->A, sA));
+    DMF_CUDA(cudaMalloc(&d->Z, sZ));
+    DMF_CUDA(cudaMalloc(&d->CAT, sCAT));
+    DMF_CUDA(cudaMalloc(&d->B1, sB1));
+    DMF_CUDA(cudaMalloc(&d->B2, sB2));
+    DMF_CUDA(cudaMalloc(&d->F, sF));
+    d->bytes = sA + sZ + sCAT + sB1 + sB2 + sF;
+    // positions a band never writes are only ever read into don't-care outputs; zero them once so that runs are reproducible
+    DMF_CUDA(cudaMemset(d->A, 0, sA));
+    DMF_CUDA(cudaMemset(d->Z, 0, sZ));
+    DMF_CUDA(cudaMemset(d->CAT, 0, sCAT));
+    DMF_CUDA(cudaMemset(d->B1, 0, sB1));
+    DMF_CUDA(cudaMemset(d->B2, 0, sB2));
+    DMF_CUDA(cudaMemset(d->F, 0, sF));
+    d->W = W; d->band = band; d->p = p; d->R1 = (int)R1; d->C1 = (int)C1;
+    DMF_TRY(make_dense_map(&d->mapA, d->A, 9, C_MS1 / 8, (int)R1, (int)C1, tc::kPitch, 18));
+    DMF_TRY(make_dense_map(&d->mapB1, d->B1, 9, C_PAN1 / 8, 2 * (int)R1, 2 * (int)C1, tc::kPitch, 18));
+    DMF_TRY(make_dense_map(&d->mapB1s2, d->B1, 9, C_PAN1 / 8, 2 * (int)R1, 2 * (int)C1, tc::kPitch, 33));
+    DMF_TRY(make_dense_map(&d->mapB2, d->B2, 9, C_PAN2 / 8, (int)R1, (int)C1, tc::kPitch, 18));
+    DMF_TRY(make_dense_map(&d->mapCAT, d->CAT, 9, C_CAT / 8, (int)R1, (int)C1, 32, 4));
+    for (auto& e : d->ev) if (!e) DMF_CUDA(cudaEventCreate(&e));
+    DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    return DMF_OK;
+}
+
+static int grid_for(int64_t work_items, int threads, int per_sm) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((work_items + threads - 1) / threads, (int64_t)num_sms() * per_sm));
+}
+
+int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logits_dev, uint8_t* pred_map_dev, int64_t* cm_dev, cudaStream_t st) {
+    DenseWs* d = n->dense;
+    if (!d || !d->w_ms1) { set_error("dense path: weights not packed"); return DMF_ERR_STATE; }
+    const int p = n->p, W = s->W;
+    const int band = std::max(1, std::min(n->dense_band, row1 - row0));
+    DMF_TRY(dense_prepare(n, W, band));
+    const int R1 = d->R1, C1 = d->C1, R2 = 2 * R1, C2 = 2 * C1;
+    const bool tm = n->timing;
+    int evi = 0;
+    auto mark = [&]() { if (tm && evi < 12) cudaEventRecord(d->ev[evi++], st); };
+
+    for (int b0 = row0; b0 < row1; b0 += band) {
+        const int nb = std::min(band, row1 - b0);
+        const int rows = nb + p - 1;                      // map rows this band needs (<= R1)
+        evi = 0;
+        mark();
+        // ---- MS branch
+        ms_stem_map_kernel<<<dim3(grid_for((int64_t)rows * C1, 256, 8), C_MS1 / 8), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, b0, rows, R1, C1, d->w_ms1, n->L[4].scale, n->L[4].shift, d->A);
+        DMF_LAUNCHED();
+        mark();
+        {
+            tc::DenseParams P{};
+            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_cls = 25;
+            P.out_chunks = C_MS2 / 8; P.out_chunk0 = 0;
+            P.w = n->L[0].w; P.scale = n->L[0].scale; P.shift = n->L[0].shift; P.out = d->Z;
+            for (int cr = 0; cr < 5; ++cr)
+                for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[cr * 5 + cc], cr, cc, cr * 5 + cc, 0);
+            DMF_TRY((launch_dense<C_MS1, C_MS2, 9, 1, 4>(d->mapA, P, st)));
+        }
+        mark();
+        pool_maps_kernel<1><<<grid_for((int64_t)9 * (C_MS2 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(d->Z), C_MS2 / 8, rows, R1, C1, reinterpret_cast<uint4*>(d->CAT), C_CAT / 8, 0);
+        DMF_LAUNCHED();
+        mark();
+        // ---- PAN branch
+        pan_stem_map_kernel<<<dim3(grid_for((int64_t)2 * rows * C2, 256, 8), C_PAN1 / 8), 256, 0, st>>>(
+            s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R2, C2, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
+        DMF_LAUNCHED();
+        mark();
+        {
+            tc::DenseParams P{};
+            P.rows = R2; P.cols = C2; P.tiles_x = cdiv(C2, 8); P.out_chunks = C_PAN2 / 8; P.out_chunk0 = 0;
+            P.w = d->w_pan2; P.scale = n->L[1].scale; P.shift = n->L[1].shift; P.out = d->Z;
+            // interior rows: every row of the pooled-once grid
+            P.tiles_y = cdiv(2 * rows, 16); P.n_cls = 5;
+            for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[cc], 2, cc, 2 * 5 + cc, 0);
+            DMF_TRY((launch_dense<C_PAN1, C_PAN2, 9, 1, 4>(d->mapB1, P, st)));
+            // edge rows u = 0, 2p-2 sit on even rows of the grid, u = 1, 2p-1 on odd rows: row stride 2
+            P.tiles_y = cdiv(rows, 16); P.n_cls = 20;
+            int k = 0;
+            for (int cr = 0; cr < 5; ++cr) {
+                if (cr == 2) continue;
+                for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[k++], cr, cc, cr * 5 + cc, (cr == 1 || cr == 4) ? 1 : 0);
+            }
+            DMF_TRY((launch_dense<C_PAN1, C_PAN2, 9, 2, 4>(d->mapB1s2, P, st)));
+        }
+        mark();
+        pool_maps_kernel<2><<<grid_for((int64_t)9 * (C_PAN2 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(d->Z), C_PAN2 / 8, rows, R1, C1, reinterpret_cast<uint4*>(d->B2), C_PAN2 / 8, 0);
+        DMF_LAUNCHED();
+        mark();
+        {
+            tc::DenseParams P{};
+            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_cls = 25;
+            P.out_chunks = C_PAN3 / 8; P.out_chunk0 = 0;
+            P.w = n->L[2].w; P.scale = n->L[2].scale; P.shift = n->L[2].shift; P.out = d->Z;
+            for (int cr = 0; cr < 5; ++cr)
+                for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[cr * 5 + cc], cr, cc, cr * 5 + cc, 0);
+            DMF_TRY((launch_dense<C_PAN2, C_PAN3, 9, 1, 4>(d->mapB2, P, st)));
+        }
+        mark();
+        pool_maps_kernel<1><<<grid_for((int64_t)9 * (C_PAN3 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(d->Z), C_PAN3 / 8, rows, R1, C1, reinterpret_cast<uint4*>(d->CAT), C_CAT / 8, C_MS2 / 8);
+        DMF_LAUNCHED();
+        mark();
+        // ---- fusion conv (1x1) on the 9 pooled planes
+        {
+            tc::DenseParams P{};
+            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 32); P.tiles_y = cdiv(rows, 4); P.n_cls = 9;
+            P.out_chunks = C_FUSE / 8; P.out_chunk0 = 0;
+            P.w = n->L[3].w; P.scale = n->L[3].scale; P.shift = n->L[3].shift; P.out = d->F;
+            for (int a = 0; a < 9; ++a) {
+                memset(&P.cls[a], 0, sizeof(tc::DenseCls));
+                P.cls[a].out_plane = (int16_t)a; P.cls[a].n_steps = 1; P.cls[a].in_plane[0] = (int16_t)a; P.cls[a].mask[0] = 1;
+            }
+            DMF_TRY((launch_dense<C_CAT, C_FUSE, 1, 1, 4>(d->mapCAT, P, st)));
+        }
+        mark();
+        // ---- head
+        {
+            const int n_seg = nb * ((W + 31) / 32);
+            const int64_t off = (int64_t)(b0 - row0) * W;
+            head_dense_kernel<<<std::min(n_seg, 2 * num_sms()), kDenseHeadThreads, dense_head_smem(n->C), st>>>(
+                reinterpret_cast<const uint4*>(d->F), R1, C1, p, nb, W, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, (int64_t)b0 * W, s->label,
+                logits_dev ? logits_dev + off * n->C : nullptr, reinterpret_cast<unsigned long long*>(cm_dev), pred_map_dev);
+            DMF_LAUNCHED();
+        }
+        mark();
+        if (tm) {
+            DMF_CUDA(cudaEventSynchronize(d->ev[evi - 1]));
+            for (int i = 0; i + 1 < evi; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, d->ev[i], d->ev[i + 1]);
+                d->stage_ms[i] += ms;
+            }
+            float tot = 0.f;
+            cudaEventElapsedTime(&tot, d->ev[0], d->ev[evi - 1]);
+            d->stage_ms[11] += tot;
+        }
+    }
+    return DMF_OK;
+}
+
+}  // namespace dmf
+
+using namespace dmf;
+
+extern "C" {
+
+int dmf_net_set_dense(dmf_net* n, int enabled, int band_rows) {
+    DMF_REQUIRE(n, "net_set_dense: null");
+    DMF_REQUIRE(band_rows == 0 || (band_rows >= 1 && band_rows <= 4096), "net_set_dense: band_rows must be in [1, 4096] (0 keeps the current value)");
+    n->dense_mode = enabled ? 1 : 0;
+    if (band_rows) n->dense_band = band_rows;
+    return DMF_OK;
+}
+
+int dmf_infer_scene_dense(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logits_out_dev, uint8_t* pred_map_dev, int64_t* cm_dev,
+                          void* stream) {
+    if (!n || !n->ready) { set_error("net: call dmf_net_finalize after loading all parameters"); return DMF_ERR_STATE; }
+    DMF_REQUIRE(s && row0 >= 0 && row1 >= row0 && row1 <= s->H, "infer_scene_dense: bad row band [%d,%d)", row0, row1);
+    DMF_REQUIRE(s->p == n->p, "infer_scene_dense: scene patch size %d != net patch size %d", s->p, n->p);
+    DMF_REQUIRE(!cm_dev || s->label, "infer_scene_dense: confusion matrix needs dmf_scene_set_labels");
+    if (row1 == row0) return DMF_OK;
+    return dense_infer(n, s, row0, row1, logits_out_dev, pred_map_dev, cm_dev, (cudaStream_t)stream);
+}
+
+int dmf_net_get_dense_timing(dmf_net* n, float out_ms[12], int reset) {
+    DMF_REQUIRE(n && out_ms, "net_get_dense_timing: null");
+    if (!n->dense) { memset(out_ms, 0, 12 * sizeof(float)); return DMF_OK; }
+    memcpy(out_ms, n->dense->stage_ms, 12 * sizeof(float));
+    if (reset) memset(n->dense->stage_ms, 0, sizeof(n->dense->stage_ms));
+    return DMF_OK;
+}
+
+/* test hook: device pointer + byte size of a dense-path map ("A", "Z", "CAT", "B1", "B2", "F"); dims[0..1] = R, C of the MS-resolution grid */
+int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* bytes_out, int32_t dims[2]) {
+    DMF_REQUIRE(n && name && ptr_out && bytes_out && dims, "net_dense_buffer: null");
+    DMF_REQUIRE(n->dense && n->dense->A, "net_dense_buffer: the dense path has not run yet");
+    DenseWs* d = n->dense;
+    const size_t px = (size_t)d->R1 * d->C1;
+    const std::string k(name);
+    if (k == "A") { *ptr_out = d->A; *bytes_out = px * 9 * C_MS1 * 2; }
+    else if (k == "Z") { *ptr_out = d->Z; *bytes_out = px * 25 * 32 * 16; }
+    else if (k == "CAT") { *ptr_out = d->CAT; *bytes_out = px * 9 * C_CAT * 2; }
+    else if (k == "B1") { *ptr_out = d->B1; *bytes_out = px * 4 * 9 * C_PAN1 * 2; }
+    else if (k == "B2") { *ptr_out = d->B2; *bytes_out = px * 9 * C_PAN2 * 2; }
+    else if (k == "F") { *ptr_out = d->F; *bytes_out = px * 9 * C_FUSE * 2; }
+    else { set_error("net_dense_buffer: unknown map '%s'", name); return DMF_ERR_ARG; }
+    dims[0] = d->R1; dims[1] = d->C1;
+    return DMF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+// Scene-dense convolution on tcgen05 — the tensor-core kernel of the whole-scene ("dense") inference path.
+//
+// Solver.color() / test() classify EVERY pixel of a scene (solver/mainsolver.py:167-185): patches at stride 1.  The
+// value a layer produces at patch-relative position (i, j) of the patch anchored at (x, y) depends only on the
+// ABSOLUTE position (x + i, y + j) and on how close (i, j) is to the patch border (the convs zero-pad at the patch
+// border, not at the scene border).  A 3x3 conv whose input has the 3 border variants {first, interior, last} per
+// axis has 5 output classes per axis {0, 1, interior, S-2, S-1}; the 2x2 max-pool folds them back to 3.  So every
+// layer is a small set of scene-level maps ("planes"), each computed ONCE per scene position instead of once per
+// patch: 25 x (1/256) of the per-patch MMA work at p = 16.
+//
+// This kernel computes, for a list of output classes, out[class][X][Y] = relu(bn(sum_taps W[tap] . in[plane(class,
+// tap)][X + dy][Y + dx])) over a whole map.  A tile is 16 rows x 8 columns of ONE class (row stride RS = 2 for the
+// classes of a stride-2-pooled layer that exist on one row parity only).  Its taps are grouped by the input plane they
+// read into <= 4 "steps"; every step is one TMA halo box (same C8-planar no-swizzle layout and shifted-descriptor
+// trick as conv_tc.cuh) and a masked subset of the 9 taps, all accumulating into the same TMEM accumulator.  Tiles are
+// ordered (row strip, class, column) so that the CTAs running concurrently read the same input strip (L2-resident).
+// TAPS == 1 (the 1x1 fusion conv): tile = 4 rows x 32 columns, no halo, 512-byte TMA rows.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace dmf {
+namespace tc {
+
+constexpr int kDenseMaxCls = 25, kDenseMaxSteps = 4;
+
+struct DenseCls {
+    int16_t out_plane;                    // plane of the output tensor this class writes
+    int16_t row0;                         // first output row (row parity for RS = 2)
+    int16_t n_steps;
+    int16_t pad_;
+    int16_t in_plane[kDenseMaxSteps];     // input plane of each step
+    uint16_t mask[kDenseMaxSteps];        // taps (bit dy*3+dx) that read that plane
+};
+
+struct DenseParams {
+    int rows, cols;                       // map size in positions (input and output grids coincide)
+    int tiles_x, tiles_y, n_cls, n_tiles;
+    int n_stage;
+    int out_chunks, out_chunk0;           // channel chunks of one output plane, first chunk written
+    const __nv_bfloat16* w;               // packed [tap][C_in/8][C_out][8]
+    const float* scale;
+    const float* shift;
+    __nv_bfloat16* out;                   // [plane][out_chunks][rows][cols][8]
+    DenseCls cls[kDenseMaxCls];
+};
+
+template <int C_IN, int C_OUT, int TAPS, int RS, int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __grid_constant__ CUtensorMap in_map,
+                                                                     const __grid_constant__ DenseParams P) {
+    constexpr int kThreads = 64 + 128 * G;
+    constexpr int KCH = C_IN / 8, KSTEPS = C_IN / 16;
+    constexpr uint32_t WBYTES = (uint32_t)TAPS * C_IN * C_OUT * 2;
+    constexpr uint32_t TMEM_USED = G * C_OUT;
+    constexpr uint32_t TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    static_assert(G >= 1 && G <= 4 && TMEM_USED <= 512, "epilogue groups / TMEM columns");
+    static_assert(C_IN % 16 == 0 && C_OUT % 32 == 0 && C_OUT <= 256 && (TAPS == 9 || TAPS == 1) && (RS == 1 || RS == 2), "configuration");
+    constexpr int HR = RS * 15 + 3;                                         // halo rows of a 3x3 tile
+    constexpr uint32_t A_PLANE = TAPS == 9 ? (uint32_t)HR * kPitch * 16 : 128u * 16u;
+    constexpr uint32_t SBO_A = TAPS == 9 ? (uint32_t)RS * kPitch * 16 : 128u;
+    constexpr uint32_t A_STAGE = KCH * A_PLANE;
+    static_assert(A_STAGE % 128 == 0, "stage alignment");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;
+    uint8_t* a_s = smem + WBYTES;
+    float* scale_s = reinterpret_cast<float*>(a_s + (size_t)P.n_stage * A_STAGE);
+    float* shift_s = scale_s + C_OUT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
+    // bars: [0,8) full, [8,16) empty, 16 weights, 17..20 tmem_full, 21..24 tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+    const uint32_t w_bar = bar0 + 8u * 16;
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (17 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (21 + a); };
+
+    for (int i = threadIdx.x; i < C_OUT; i += kThreads) {
+        scale_s[i] = P.scale[i];
+        shift_s[i] = P.shift[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(w_bar, 1);
+        for (int a = 0; a < G; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // tile -> (row strip ty, class c, column tile tx)
+    auto decode = [&](int tile, int& ty, int& c, int& tx) {
+        tx = tile % P.tiles_x;
+        const int r = tile / P.tiles_x;
+        c = r % P.n_cls;
+        ty = r / P.n_cls;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        const bool leader = elect_one();
+        if (leader) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
+            mbar_expect_tx(w_bar, WBYTES);
+            constexpr uint32_t CH = 16384;
+            for (uint32_t off = 0; off < WBYTES; off += CH)
+                bulk_load(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(P.w) + off, min(CH, WBYTES - off), w_bar);
+        }
+        __syncwarp();
+        int st = 0;
+        uint32_t ph = 1;
+        for (int i = 0; i < n_local; ++i) {
+            int ty, c, tx;
+            decode(blockIdx.x + i * gridDim.x, ty, c, tx);
+            const int n_steps = P.cls[c].n_steps;
+            const int row = TAPS == 9 ? P.cls[c].row0 + ty * 16 * RS - 1 : ty * 4;
+            const int col8 = TAPS == 9 ? (tx * 8 - 1) * 8 : tx * 32 * 8;
+            for (int s = 0; s < n_steps; ++s) {
+                mbar_wait(empty_bar(st), ph);
+                if (leader) {
+                    mbar_expect_tx(full_bar(st), A_STAGE);
+                    tma_load_4d(smem_u32(a_s) + (uint32_t)st * A_STAGE, &in_map, full_bar(st), col8, P.cls[c].in_plane[s], row, 0);
+                }
+                __syncwarp();
+                if (++st == P.n_stage) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+        constexpr uint32_t idesc = umma_idesc_bf16(128, C_OUT);
+        const bool leader = elect_one();
+        mbar_wait(w_bar, 0);
+        const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < n_local; ++i) {
+            int ty, c, tx;
+            decode(blockIdx.x + i * gridDim.x, ty, c, tx);
+            const int n_steps = P.cls[c].n_steps;
+            const int acc = i % G;
+            mbar_wait(tempty_bar(acc), ((i / G) & 1) ^ 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C_OUT);
+            uint32_t accumulate = 0;
+            for (int s = 0; s < n_steps; ++s) {
+                const uint32_t mask = P.cls[c].mask[s];
+                mbar_wait(full_bar(st), ph);
+                tc_fence_after();
+                const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * A_STAGE, A_PLANE, SBO_A);
+                if (leader) {
+#pragma unroll
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        if (mask & (1u << tap)) {
+                            const uint32_t tap_off = TAPS == 9 ? (uint32_t)(((tap / 3) * kPitch + (tap % 3)) * 16) : 0u;
+#pragma unroll
+                            for (int j = 0; j < KSTEPS; ++j) {
+                                const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(2 * j) * A_PLANE + tap_off) >> 4);
+                                const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((tap * KCH + 2 * j) * C_OUT * 16) >> 4);
+                                umma_bf16(d_tmem, ad, bd, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                    }
+                    umma_commit(empty_bar(st));
+                    if (s == n_steps - 1) umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++st == P.n_stage) { st = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (G groups of 4 warps): BN affine + ReLU -> bf16 -> C8-planar stores
+        const int eg = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * C_OUT);
+        const int64_t cstride = (int64_t)P.rows * P.cols * 8;
+        for (int i = eg; i < n_local; i += G) {
+            int ty, c, tx;
+            decode(blockIdx.x + i * gridDim.x, ty, c, tx);
+            int row, col;
+            if (TAPS == 9) {
+                row = P.cls[c].row0 + (ty * 16 + (m >> 3)) * RS;
+                col = tx * 8 + (m & 7);
+            } else {
+                row = ty * 4 + (m >> 5);
+                col = tx * 32 + (m & 31);
+            }
+            const bool valid = row < P.rows && col < P.cols;
+            __nv_bfloat16* const obase =
+                P.out + ((((int64_t)P.cls[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
+            mbar_wait(tfull_bar(eg), (i / G) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < C_OUT; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + c0, v);
+                uint32_t pk[16];
+                const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
+                const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 sc = sc4[k], sh = sh4[k];
+                    const float a0 = fmaxf(fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x), 0.f);
+                    const float a1 = fmaxf(fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y), 0.f);
+                    const float a2 = fmaxf(fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z), 0.f);
+                    const float a3 = fmaxf(fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w), 0.f);
+                    pk[2 * k] = pack_bf16x2(a0, a1);
+                    pk[2 * k + 1] = pack_bf16x2(a2, a3);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4)
+                        *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + s4) * cstride) =
+                            make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(eg));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace dmf

@@ -18,40 +18,10 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "net_geom.cuh"
+#include "net_types.cuh"
 #include "stem_tc.cuh"
 
-namespace dmf {
-
-constexpr int C_MS1 = 64, C_MS2 = 128, C_PAN1 = 32, C_PAN2 = 64, C_PAN3 = 128, C_CAT = 256, C_FUSE = 128, C_HID = 64;
-constexpr float BN_EPS = 1e-5f;
-
-struct ConvLayer {
-    LayerGeom g;
-    __nv_bfloat16* w = nullptr;   // packed [tap][cin/8][cout][8]
-    float* scale = nullptr;
-    float* shift = nullptr;
-    CUtensorMap map;              // over the workspace input buffer
-};
-
-}  // namespace dmf
-
 using namespace dmf;
-
-struct dmf_net {
-    int p = 0, C = 0, NB = 0;
-    std::map<std::string, std::vector<float>> params;
-    bool ready = false;
-    bool timing = false;
-    // stems / head weights
-    __nv_bfloat16* w_pan1 = nullptr;                                    // hi/lo-split PAN stem weights [4][32][8]
-    float *sc_pan1 = nullptr, *sh_pan1 = nullptr;
-    float *fc1t = nullptr, *fc1b = nullptr, *fc2t = nullptr, *fc2b = nullptr;
-    ConvLayer L[5];   // ms2, pan2, pan3, fuse, ms1 (hi/lo-split stem, 16 -> 64)
-    __nv_bfloat16 *X0 = nullptr, *A1 = nullptr, *B1 = nullptr, *B2 = nullptr, *CAT = nullptr, *F = nullptr;
-    float* gap = nullptr;     // [NB][128] per-patch channel sums when the pooling is fused into the fusion conv (p <= 16)
-    cudaEvent_t ev[8] = {};
-    float stage_ms[8] = {};
-};
 
 namespace dmf {
 
@@ -107,7 +77,6 @@ __global__ void __launch_bounds__(256) ms_prep_kernel(PatchSrc src, int p, int64
 // argmax (first maximum), confusion matrix, prediction map.  One WARP per patch, no block barriers:
 // coalesced 512-byte reads of F, an exchange-halving warp reduction for the pooling (9 shuffles per
 // 8 channels instead of 40), the two small linears from shared-memory weights, shuffle argmax.
-constexpr int kHeadWarps = 8;
 
 // GAPIN: the pooled sums come from the fusion conv's epilogue (gap [N][128] fp32) instead of F.
 template <bool GAPIN>
@@ -283,7 +252,7 @@ __global__ void direct_conv_kernel(const __nv_bfloat16* __restrict__ in, const _
 }
 
 // ------------------------------------------------------------------------------------ host side
-static const std::vector<float>* param(const dmf_net* n, const std::string& k, size_t numel) {
+const std::vector<float>* param(const dmf_net* n, const std::string& k, size_t numel) {
     auto it = n->params.find(k);
     if (it == n->params.end()) { set_error("net: parameter '%s' was not loaded", k.c_str()); return nullptr; }
     if (it->second.size() != numel) {
@@ -293,8 +262,7 @@ static const std::vector<float>* param(const dmf_net* n, const std::string& k, s
     return &it->second;
 }
 
-// eval-mode BatchNorm folded with the conv bias: y = acc*scale + shift
-static int fold_bn(const dmf_net* n, const std::string& blk, int cout, std::vector<float>& scale, std::vector<float>& shift) {
+int fold_bn(const dmf_net* n, const std::string& blk, int cout, std::vector<float>& scale, std::vector<float>& shift) {
     auto *cb = param(n, blk + ".0.bias", cout), *gw = param(n, blk + ".1.weight", cout), *gb = param(n, blk + ".1.bias", cout),
          *mu = param(n, blk + ".1.running_mean", cout), *var = param(n, blk + ".1.running_var", cout);
     if (!cb || !gw || !gb || !mu || !var) return DMF_ERR_STATE;
@@ -304,15 +272,6 @@ static int fold_bn(const dmf_net* n, const std::string& blk, int cout, std::vect
         scale[c] = s;
         shift[c] = (*gb)[c] + ((*cb)[c] - (*mu)[c]) * s;
     }
-    return DMF_OK;
-}
-
-template <typename T>
-static int to_device(T** dst, const std::vector<T>& v) {
-    if (*dst) cudaFree(*dst);
-    *dst = nullptr;
-    DMF_CUDA(cudaMalloc(dst, sizeof(T) * v.size()));
-    DMF_CUDA(cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
     return DMF_OK;
 }
 
@@ -452,7 +411,7 @@ static size_t stem_pan_smem(int p) {
     const size_t raw = 2ull * (4 * p + 2) * stem_pan_raw_pitch(p) * 4;
     return (size_t)stem_pan_stages(p) * tc::kStemStage + tc::kStemWBytes + 2 * tc::kStemCout * 4 + 20 * 8 + 16 + raw;
 }
-static size_t head_smem(int C) {
+size_t head_smem(int C) {
     return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + kHeadWarps * (C_FUSE + C_HID)) +
            sizeof(unsigned int) * C * C;
 }
@@ -561,6 +520,7 @@ int dmf_net_destroy(dmf_net* n) {
     for (auto* b : bs) cudaFree(b);
     cudaFree(n->gap);
     for (auto& e : n->ev) if (e) cudaEventDestroy(e);
+    dense_release(n);
     delete n;
     return DMF_OK;
 }
@@ -645,6 +605,7 @@ int dmf_net_finalize(dmf_net* n, void* stream) {
         DMF_CUDA(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         DMF_CUDA(cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     }
+    DMF_TRY(dense_pack(n));
     DMF_CUDA(cudaDeviceSynchronize());
     n->ready = true;
     return DMF_OK;
@@ -719,6 +680,7 @@ int dmf_net_forward_scene(dmf_net* n, const dmf_scene* s, const int64_t* flat_id
 
 int dmf_infer_scene(dmf_net* n, const dmf_scene* s, int row0, int row1, uint8_t* pred_map_dev, int64_t* cm_dev, void* stream) {
     DMF_REQUIRE(s && row0 >= 0 && row1 >= row0 && row1 <= s->H, "infer_scene: bad row band [%d,%d)", row0, row1);
+    if (n && n->dense_mode) return dmf_infer_scene_dense(n, s, row0, row1, nullptr, pred_map_dev, cm_dev, stream);
     return dmf_net_forward_scene(n, s, nullptr, (int64_t)row0 * s->W, (int64_t)(row1 - row0) * s->W, nullptr, nullptr, cm_dev,
                                  pred_map_dev, stream);
 }

@@ -259,6 +259,7 @@ class NetHandle:
         self._h = C.c_void_p()
         check(lib.dmf_net_create(C.byref(self._h), p, num_classes, max_batch))
         self.flops_per_patch = int(lib.dmf_net_flops_per_patch(self._h))
+        self.dense = True
 
     def load_state_dict(self, sd):
         with torch.cuda.device(self.device):
@@ -292,16 +293,45 @@ class NetHandle:
                                             _ptr(cm), _ptr(pred_map), _stream()))
         return logits, pred
 
-    def infer_scene(self, scene, row0=0, row1=None, pred_map=None, cm=None):
-        """Fused whole-band inference: returns (pred_map u8 [H,W], cm int64 [C,C])."""
+    def infer_scene(self, scene, row0=0, row1=None, pred_map=None, cm=None, want_logits=False):
+        """Fused whole-band inference: returns (pred_map u8 [H,W], cm int64 [C,C]) (+ logits [(row1-row0)*W, C] when asked).
+        Runs the scene-dense maps (csrc/dense.cu) unless set_dense(False) selected the per-patch kernels."""
         row1 = scene.H if row1 is None else row1
         if pred_map is None:
             pred_map = torch.zeros((scene.H, scene.W), dtype=torch.uint8, device=self.device)
         if cm is None and scene.has_labels:
             cm = torch.zeros((self.C, self.C), dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
+            if want_logits:
+                n = (row1 - row0) * scene.W
+                logits = torch.empty((n, self.C), dtype=torch.float32, device=self.device)
+                if self.dense:
+                    check(lib.dmf_infer_scene_dense(self._h, scene._h, row0, row1, _ptr(logits), _ptr(pred_map), _ptr(cm), _stream()))
+                else:
+                    check(lib.dmf_net_forward_scene(self._h, scene._h, None, row0 * scene.W, n, _ptr(logits), None, _ptr(cm),
+                                                    _ptr(pred_map), _stream()))
+                return pred_map, cm, logits
             check(lib.dmf_infer_scene(self._h, scene._h, row0, row1, _ptr(pred_map), _ptr(cm), _stream()))
         return pred_map, cm
+
+    def set_dense(self, enabled=True, band_rows=0):
+        """Whole-scene inference mode: True = scene-dense maps (every layer once per scene position and border class),
+        False = per-patch kernels.  band_rows = anchor rows per pass of the dense path (0 keeps the current value)."""
+        check(lib.dmf_net_set_dense(self._h, 1 if enabled else 0, int(band_rows)))
+        self.dense = bool(enabled)
+
+    def get_dense_timing(self, reset=True):
+        buf = (C.c_float * 12)()
+        check(lib.dmf_net_get_dense_timing(self._h, buf, 1 if reset else 0))
+        names = ['ms_stem_maps', 'conv_ms2', 'pool_ms2', 'pan_stem_maps', 'conv_pan2', 'pool_pan2', 'conv_pan3', 'pool_pan3',
+                 'conv_fuse', 'head', '_', 'total']
+        return {k: float(v) for k, v in zip(names, buf) if k != '_'}
+
+    def dense_buffer(self, name):
+        """test hook: a dense-path map as a flat bf16 tensor aliasing the library's workspace, and (rows, cols) of the MS grid"""
+        ptr, nbytes, dims = C.c_void_p(), C.c_int64(), (C.c_int32 * 2)()
+        check(lib.dmf_net_dense_buffer(self._h, name.encode(), C.byref(ptr), C.byref(nbytes), dims))
+        return _from_ptr(ptr.value, nbytes.value, self.device).view(torch.bfloat16), (int(dims[0]), int(dims[1]))
 
     def set_timing(self, on):
         check(lib.dmf_net_set_timing(self._h, 1 if on else 0))

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), 'csrc')
 LIB = os.path.join(HERE, 'libdmf_b200.so')
 OBJ = os.path.join(HERE, '_obj')
-SOURCES = ['scene.cu', 'metrics.cu', 'ihs.cu', 'net.cu', 'train.cu']
+SOURCES = ['scene.cu', 'metrics.cu', 'ihs.cu', 'net.cu', 'dense.cu', 'train.cu']
 FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC']
 
 

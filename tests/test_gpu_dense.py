@@ -1,0 +1,158 @@
+"""GPU parity of the scene-dense whole-scene path (csrc/dense.cu, csrc/dense_tc.cuh).
+
+The dense path evaluates every layer once per scene position and border class instead of once per patch
+(Solver.color()/test() visit patches at stride 1, solver/mainsolver.py:167-185).  Checks:
+  * layer by layer, in isolation: for sampled anchors the per-patch tensor gathered from the dense maps of layer L-1
+    is pushed through the fp32 torch definition of layer L (same bf16 rounding points) and compared with the tensor
+    gathered from the dense maps of layer L: <= 2 bf16 ulps + 1e-3, the tolerance of the single-layer tests in
+    test_gpu_net.py;
+  * whole scene, several bands: logits vs the per-patch kernels (bf16 summation-order noise only) and vs the fp32
+    oracle (|d| <= LOGIT_ATOL + LOGIT_RTOL*|logit|), argmax agreement >= 99.9 %, label map == argmax of the returned
+    logits, confusion matrix == oracle.confusion(pred, label) bit for bit.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dmf_oracle as orc
+from test_gpu_net import LOGIT_ATOL, LOGIT_RTOL, cfg, make_ref, rb, ref_block
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+torch.backends.cudnn.allow_tf32 = False          # the torch reference layers run on the GPU here: keep them fp32
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope='module')
+def dmf():
+    import dmf as m
+    return m
+
+
+def c3(i, S):
+    return 0 if i == 0 else (2 if i == S - 1 else 1)
+
+
+def gather_patches(buf, planes_chunks, dims, anchors, S, a, b, chunk0=0, chunks=None):
+    """Per-patch tensors [N][C][S][S] (float) out of a dense map [9][planes_chunks][rows][cols][8]: patch-relative position
+    (i, j) of the patch anchored at band-local (xl, y) sits at (a*xl + b*i, a*y + b*j) of plane (c3(i), c3(j))."""
+    rows, cols = dims
+    chunks = planes_chunks if chunks is None else chunks
+    m = buf[:9 * planes_chunks * rows * cols * 8].view(9, planes_chunks, rows, cols, 8)
+    ii = torch.arange(S, device=buf.device)
+    cls = torch.tensor([c3(i, S) for i in range(S)], device=buf.device)
+    plane = cls[:, None] * 3 + cls[None, :]                                   # [S][S]
+    out = []
+    for xl, y in anchors:
+        r = (a * xl + b * ii)[:, None].expand(S, S)
+        c = (a * y + b * ii)[None, :].expand(S, S)
+        v = m[plane, chunk0:chunk0 + chunks, r, c]                            # [S][S][chunks][8]
+        out.append(v.permute(2, 3, 0, 1).reshape(chunks * 8, S, S))
+    return torch.stack(out).float()
+
+
+def assert_close_bf16(got, want, what, ulps=2, max_bad_frac=0.0):
+    tol = ulps * 2.0 ** -8 * torch.maximum(got.abs(), want.abs()) + 1e-3
+    bad = (got - want).abs() > tol
+    frac = float(bad.float().mean())
+    assert frac <= max_bad_frac, '%s: %d of %d outside tolerance (max abs err %g, max |want| %g)' % (
+        what, int(bad.sum()), bad.numel(), float((got - want).abs().max()), float(want.abs().max()))
+
+
+def scene_and_net(dmf, p, H, W, C, seed=0):
+    ms, pan, label = orc.synthetic_scene(H, W, C - 1, seed=seed, label_seed=seed + 1)
+    sc = dmf.Scene.from_raw(ms, pan, p, DEV)
+    sc.set_labels(label)
+    ref = make_ref(p, C)
+    h = dmf.NetHandle(p, C, max_batch=2048, device=DEV)
+    h.load_state_dict(ref.state_dict())
+    return ms, pan, label, sc, ref, h
+
+
+@pytest.mark.parametrize('p,H,W,row0,nb', [(16, 21, 37, 2, 19), (8, 30, 41, 0, 30), (32, 9, 20, 1, 7)])
+def test_dense_layers_in_isolation(dmf, p, H, W, row0, nb):
+    C = 8
+    ms, pan, label, sc, ref, h = scene_and_net(dmf, p, H, W, C)
+    h.set_dense(True, band_rows=nb)
+    h.infer_scene(sc, row0, row0 + nb)
+    torch.cuda.synchronize()
+    ref = ref.to(DEV)
+    g = np.random.default_rng(5)
+    anchors = [(0, 0), (nb - 1, W - 1), (0, W - 1), (nb - 1, 0)] + [(int(g.integers(nb)), int(g.integers(W))) for _ in range(12)]
+    idx = torch.tensor([(row0 + xl) * W + y for xl, y in anchors], device=DEV)
+    pm, pp, _ = sc.gather(idx, want_target=False)
+    A, dims = h.dense_buffer('A')
+    B1, _ = h.dense_buffer('B1')
+    B2, _ = h.dense_buffer('B2')
+    CAT, _ = h.dense_buffer('CAT')
+    Fm, _ = h.dense_buffer('F')
+    R, Cc = dims
+    with torch.no_grad():
+        # stems: fp32 weights (CUDA cores), bf16-rounded output
+        got = gather_patches(A, 8, dims, anchors, p, 1, 1)
+        assert_close_bf16(got, ref_block(ref.ms1, pm, False, quant_w=False), 'ms stem maps')
+        got_b1 = gather_patches(B1, 4, (2 * R, 2 * Cc), anchors, 2 * p, 2, 1)
+        assert_close_bf16(got_b1, ref_block(ref.pan1, pp, True, quant_w=False), 'pan stem maps')
+        # tensor-core layers, each fed with the dense path's own input
+        got_ms2 = gather_patches(CAT, 32, dims, anchors, p // 2, 1, 2, 0, 16)
+        assert_close_bf16(got_ms2, ref_block(ref.ms2, got, True), 'ms2 (conv_dense + pool_s1)')
+        got_b2 = gather_patches(B2, 8, dims, anchors, p, 1, 1)
+        assert_close_bf16(got_b2, ref_block(ref.pan2, got_b1, True), 'pan2 (conv_dense RS=1,2 + pool_s2)')
+        got_p3 = gather_patches(CAT, 32, dims, anchors, p // 2, 1, 2, 16, 16)
+        assert_close_bf16(got_p3, ref_block(ref.pan3, got_b2, True), 'pan3 (conv_dense + pool_s1)')
+        got_f = gather_patches(Fm, 16, dims, anchors, p // 2, 1, 2)
+        assert_close_bf16(got_f, ref_block(ref.fuse, torch.cat([got_ms2, got_p3], 1), False), 'fuse (conv_dense 1x1)')
+    h.close()
+
+
+@pytest.mark.parametrize('p,H,W,band', [(16, 40, 52, 16), (8, 33, 70, 128), (32, 12, 40, 5)])
+def test_dense_scene_matches_patch_path_and_oracle(dmf, p, H, W, band):
+    C = 8
+    ms, pan, label, sc, ref, h = scene_and_net(dmf, p, H, W, C, seed=3)
+    h.set_dense(True, band_rows=band)
+    pm_d, cm_d, lg_d = h.infer_scene(sc, want_logits=True)
+    h.set_dense(False)
+    pm_p, cm_p, lg_p = h.infer_scene(sc, want_logits=True)
+    torch.cuda.synchronize()
+    # dense vs per-patch kernels: same bf16 rounding points, different fp32 summation order and stem arithmetic
+    d = (lg_d - lg_p).abs()
+    assert float(d.max()) <= LOGIT_ATOL + LOGIT_RTOL * float(lg_p.abs().max()), 'dense vs per-patch logits: max |d| = %g' % float(d.max())
+    # label map = first-maximum argmax of the logits it returned; matrix = confusion of that map
+    pred = lg_d.max(1)[1].to(torch.uint8).view(H, W)
+    assert torch.equal(pred, pm_d)
+    want_cm = orc.confusion(pm_d.cpu().numpy().reshape(-1), label.reshape(-1), C)
+    assert np.array_equal(cm_d.cpu().numpy().astype(np.float64), want_cm)
+    agree = float((pm_d == pm_p).float().mean())
+    assert agree >= 0.999, 'dense vs per-patch argmax agreement %.5f' % agree
+    if torch.equal(pm_d, pm_p):
+        assert torch.equal(cm_d, cm_p)
+    # vs the fp32 oracle on a sample of pixels
+    g = np.random.default_rng(11)
+    idx = torch.from_numpy(g.choice(H * W, size=min(H * W, 600), replace=False)).to(DEV)
+    a, b, _ = sc.gather(idx, want_target=False)
+    with torch.no_grad():
+        want = ref.to(DEV)(a, b)
+    got = lg_d[idx]
+    tol = LOGIT_ATOL + LOGIT_RTOL * want.abs()
+    assert bool(((got - want).abs() <= tol).all()), 'dense vs fp32 oracle: max |d| = %g' % float((got - want).abs().max())
+    margin = want.topk(2, dim=1)[0]
+    sure = (margin[:, 0] - margin[:, 1]) > 2 * (LOGIT_ATOL + LOGIT_RTOL * want.abs().max(1)[0])
+    assert bool((got.max(1)[1] == want.max(1)[1])[sure].all())
+    h.close()
+
+
+def test_dense_row_bands_add_up(dmf):
+    """Two band calls (what two ranks do) == one whole-scene call, bit for bit."""
+    p, H, W, C = 16, 37, 45, 6
+    ms, pan, label, sc, ref, h = scene_and_net(dmf, p, H, W, C, seed=7)
+    h.set_dense(True, band_rows=16)
+    pm, cm = h.infer_scene(sc)
+    pm2 = torch.zeros_like(pm)
+    cm2 = torch.zeros_like(cm)
+    h.infer_scene(sc, 0, 19, pred_map=pm2, cm=cm2)
+    h.infer_scene(sc, 19, H, pred_map=pm2, cm=cm2)
+    torch.cuda.synchronize()
+    assert torch.equal(pm, pm2) and torch.equal(cm, cm2)
+    assert int(cm.sum()) == H * W
+    h.close()

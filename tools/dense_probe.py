@@ -1,0 +1,61 @@
+"""Stage timing of the scene-dense path on a synthetic scene: python tools/dense_probe.py [H W [band [reps]]]"""
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, 'dual-modal-fusion_b200'))
+import numpy as np
+import torch
+
+import dmf
+from model.gmfnet import Net
+from oracle import dmf_oracle as orc
+
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+band = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+P, C = 16, 13
+dev = 'cuda:0'
+ms, pan, label = orc.synthetic_scene(H, W, C - 1, seed=0, label_seed=1)
+torch.manual_seed(3407)
+net = Net({'Categories_Number': C, 'patch_size': P, 'schedule': {'activate': 'Relu'}}).to(dev).eval()
+h = net.native()
+sc = dmf.Scene.from_raw(ms, pan, P, dev)
+sc.set_labels(label)
+out = {'H': H, 'W': W, 'band': band}
+h.set_dense(True, band)
+pm = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+for _ in range(2):
+    h.infer_scene(sc, pred_map=pm, cm=cm)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    h.infer_scene(sc, pred_map=pm, cm=cm)
+e1.record()
+torch.cuda.synchronize()
+msd = e0.elapsed_time(e1) / reps
+out['dense_ms'] = msd
+out['dense_Mpx_s'] = H * W / msd / 1e3
+h.set_timing(True)
+h.get_dense_timing(reset=True)
+h.infer_scene(sc, pred_map=pm, cm=cm)
+out['dense_stage_ms'] = {k: round(v, 3) for k, v in h.get_dense_timing().items()}
+h.set_timing(False)
+pm_d = pm.clone()
+if H * W <= 300000 or os.environ.get('DENSE_PROBE_PATCH'):
+    h.set_dense(False)
+    cm.zero_()
+    h.infer_scene(sc, pred_map=pm, cm=cm)
+    torch.cuda.synchronize()
+    e0.record()
+    h.infer_scene(sc, pred_map=pm, cm=cm)
+    e1.record()
+    torch.cuda.synchronize()
+    out['patch_ms'] = e0.elapsed_time(e1)
+    out['argmax_agreement'] = float((pm == pm_d).float().mean())
+print(json.dumps(out))
