@@ -171,6 +171,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default=None, choices=list(WORKLOADS))
     ap.add_argument('--max-batch', type=int, default=16384)
+    ap.add_argument('--mode', default='dense', choices=['dense', 'patch'],
+                    help='whole-scene algorithm: scene-dense maps (default) or the per-patch kernels')
+    ap.add_argument('--band', type=int, default=128, help='anchor rows per pass of the dense path')
     ap.add_argument('--cpu-budget-s', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the secondary C4 training-step measurement')
@@ -181,7 +184,7 @@ def main():
     wl_key = args.workload or ('c2' if max(world, args.gpus) == 1 else 'c3')
     wl = WORKLOADS[wl_key]
     config = {'workload': wl['name'], 'patch_size': P, 'sharding': 'row bands, scene replicated per rank',
-              'l2': 'explicit 256 MiB L2 flush between timed steps; per-step activations (0.7 GB) exceed L2 too'}
+              'l2': 'explicit 256 MiB L2 flush between timed steps; the per-step intermediates (GBs) exceed L2 too'}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -215,6 +218,9 @@ def main():
     net = Net({'Categories_Number': C, 'patch_size': P, 'schedule': {'activate': 'Relu'}, 'b200': {'max_batch': args.max_batch}})
     net = net.to(dev).eval()
     handle = net.native()
+    handle.set_dense(args.mode == 'dense', args.band)
+    config['algorithm'] = ('scene-dense: every layer evaluated once per scene position and border class (csrc/dense.cu), bands of %d rows' % args.band
+                           if args.mode == 'dense' else 'per-patch kernels, chunks of %d pixels' % args.max_batch)
     r0, r1 = row_band(H, rank, world)
     npix_total = H * W
 
@@ -296,39 +302,93 @@ def main():
     d2h = (r1 - r0) * W + C * C * 8
 
     # ---- roofline of the dominant kernel: per-stage device events inside the library (one extra pass)
-    handle.set_timing(True)
-    handle.infer_scene(scene, r0, r1)
-    stage = handle.get_timing()
-    handle.set_timing(False)
     pk, pk_src = peaks()
     n_local = (r1 - r0) * W
-    n_chunks = -(-n_local // args.max_batch)
     conv = lambda cin, cout, k, h: 2 * cin * cout * k * k * h * h
-    kernels = {   # kernel instance -> (stage keys, algorithmic FLOPs per pixel, launches per chunk)
-        'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': (['conv_ms2', 'conv_pan3'], 2 * conv(64, 128, 3, P), 2),
-        'conv_rowpair_kernel<32,G=3> (pan2, 32->64)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
-        'conv_tc_kernel<256,128,1,G=2,gap> (fuse + pooling)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
-    }
-    ncu_key = {'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': 'tc::conv_tc_kernel<64,128,9,1,3,1,0>',
-               'conv_rowpair_kernel<32,G=3> (pan2, 32->64)': 'tc::conv_rowpair_kernel<32,3>',
-               'conv_tc_kernel<256,128,1,G=2,gap> (fuse + pooling)': 'tc::conv_tc_kernel<256,128,1,0,2,1,1>'}
-    name, (keys, fl_px, per_chunk) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
-    k_ms = sum(stage[k] for k in keys)
-    achieved = fl_px * n_local / (k_ms / 1e3) / 1e12
-    traffic = None            # dram bytes per launch of this kernel from the committed ncu --set full capture
-    try:
-        prof = json.load(open(os.path.join(REPO, 'profiles', 'r01_ncu_summary.json')))
-        if wl_key == prof.get('workload') and args.max_batch == prof.get('chunk_pixels'):
-            traffic = prof['kernels'].get(ncu_key[name], {}).get('dram_bytes_per_launch')
-    except Exception:
-        pass
-    roofline = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': traffic,
+
+    def ncu_traffic(tag, key):
+        try:
+            prof = json.load(open(os.path.join(REPO, 'profiles', tag)))
+            if wl_key == prof.get('workload'):
+                return prof['kernels'].get(key, {}).get('dram_bytes_per_launch')
+        except Exception:
+            pass
+        return None
+
+    def patch_roofline():
+        handle.set_timing(True)
+        handle.infer_scene(scene, r0, r1)
+        stage = handle.get_timing()
+        handle.set_timing(False)
+        n_chunks = -(-n_local // args.max_batch)
+        kernels = {   # kernel instance -> (stage keys, algorithmic FLOPs per pixel, launches per chunk)
+            'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': (['conv_ms2', 'conv_pan3'], 2 * conv(64, 128, 3, P), 2),
+            'conv_rowpair_kernel<32,G=3> (pan2, 32->64)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
+            'conv_tc_kernel<256,128,1,G=2,gap> (fuse + pooling)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
+        }
+        ncu_key = {'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': 'tc::conv_tc_kernel<64,128,9,1,3,1,0>',
+                   'conv_rowpair_kernel<32,G=3> (pan2, 32->64)': 'tc::conv_rowpair_kernel<32,3>',
+                   'conv_tc_kernel<256,128,1,G=2,gap> (fuse + pooling)': 'tc::conv_tc_kernel<256,128,1,0,2,1,1>'}
+        name, (keys, fl_px, per_chunk) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
+        k_ms = sum(stage[k] for k in keys)
+        achieved = fl_px * n_local / (k_ms / 1e3) / 1e12
+        conv_fl = 2 * conv(64, 128, 3, P) + conv(32, 64, 3, 2 * P) + conv(256, 128, 1, P // 2)
+        conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
+        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['bf16_tflops_sustained'],
+                'traffic': ncu_traffic('r01_ncu_summary.json', ncu_key[name]) if args.max_batch == 16384 else None,
                 'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
                 'avg_launch_ms': k_ms / (n_chunks * per_chunk), 'launches': n_chunks * per_chunk,
                 'flops_per_launch': fl_px * n_local / (n_chunks * per_chunk),
                 'stage_ms': {k: round(v, 3) for k, v in stage.items()},
                 'whole_net_tflops': handle.flops_per_patch * n_local / (stage['total'] / 1e3) / 1e12}
+        util = {'achieved_TFLOPs': conv_fl * n_local / (conv_ms / 1e3) / 1e12,
+                'frac_of_sustained_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
+                'frac_of_burst_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
+                'ncu_tensor_pipe_active_pct': 'profiles/r01_ncu_summary.json'}
+        return roof, util
+
+    def dense_roofline():
+        """FLOPs the dense kernels execute: a 3x3 layer has 5 border classes per axis with 2,3,3,3,2 live tap rows (columns):
+        (13)^2 = 169 tap evaluations of 2*Cin*Cout FLOPs per map position (no credit for tile padding or don't-care rows)."""
+        handle.set_timing(True)
+        handle.get_dense_timing(reset=True)
+        handle.infer_scene(scene, r0, r1)
+        stage = handle.get_dense_timing()
+        handle.set_timing(False)
+        band = max(1, min(args.band, r1 - r0))
+        bands = [min(band, r1 - b) for b in range(r0, r1, band)]
+        pos = sum((nb + P - 1) * (W + P - 1) for nb in bands)                 # MS-resolution map positions computed
+        kernels = {   # kernel -> (stage keys, FLOPs per MS-resolution position, launches per band)
+            'conv_dense_kernel<64,128,9,RS=1,G=4> (ms2 + pan3, 25 border classes)': (['conv_ms2', 'conv_pan3'], 2 * 169 * 2 * 64 * 128, 2),
+            'conv_dense_kernel<32,64,9,RS=1|2,G=4> (pan2, 5 + 20 classes)': (['conv_pan2'], 4 * (39 + 130 / 2) * 2 * 32 * 64, 2),
+            'conv_dense_kernel<256,128,1,RS=1,G=4> (fuse, 9 classes)': (['conv_fuse'], 9 * 2 * 256 * 128, 1),
+        }
+        ncu_key = {k: 'tc::conv_dense_kernel<%s>' % v for k, v in zip(kernels, ('64,128,9,1,4', '32,64,9,1,4', '256,128,1,1,4'))}
+        name, (keys, fl_pos, per_band) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
+        k_ms = sum(stage[k] for k in keys)
+        achieved = fl_pos * pos / (k_ms / 1e3) / 1e12
+        conv_fl = sum(v[1] for v in kernels.values())
+        conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
+        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['bf16_tflops_sustained'],
+                'traffic': ncu_traffic('r01_ncu_dense_summary.json', ncu_key[name]) if args.band == 128 else None,
+                'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
+                'avg_launch_ms': k_ms / (len(bands) * per_band), 'launches': len(bands) * per_band,
+                'flops_per_launch': fl_pos * pos / (len(bands) * per_band),
+                'stage_ms': {k: round(v, 3) for k, v in stage.items()},
+                'map_positions': pos, 'flops_executed_per_pixel': conv_fl * pos / n_local,
+                'per_patch_equivalent_tflops': handle.flops_per_patch * n_local / (stage['total'] / 1e3) / 1e12,
+                'note': 'achieved = tensor-core FLOPs this kernel executes / its time; per_patch_equivalent_tflops = the per-patch '
+                        'network FLOPs (flops_per_pixel) the same result would cost / whole-step time: it exceeds the peak because '
+                        'the dense algorithm shares work between overlapping patches'}
+        util = {'achieved_TFLOPs': conv_fl * pos / (conv_ms / 1e3) / 1e12,
+                'frac_of_sustained_peak': conv_fl * pos / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
+                'frac_of_burst_peak': conv_fl * pos / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
+                'ncu_tensor_pipe_active_pct': 'profiles/r01_ncu_dense_summary.json'}
+        return roof, util
+
+    roofline, conv_util = dense_roofline() if args.mode == 'dense' else patch_roofline()
 
     # ---- secondary metrics named by BASELINE.json: K1 patch-gather GB/s and conv tensor-pipe utilisation
     gidx = torch.randint(0, H * W, (8192,), device=dev)
@@ -344,15 +404,26 @@ def main():
         torch.cuda.synchronize()
         g_ms = min(g_ms, g0.elapsed_time(g1))
     gather_gbs = 8192 * (4 * P * P + 16 * P * P) * 4 / g_ms / 1e6
-    conv_fl = 2 * conv(64, 128, 3, P) + conv(32, 64, 3, 2 * P) + conv(256, 128, 1, P // 2)
-    conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
     secondary = {'patch_gather': {'GBs_written': gather_gbs, 'frac_of_hbm_copy_peak': gather_gbs / pk['hbm_gbs'], 'batch': 8192,
                                   'bytes_per_patch': (4 * P * P + 16 * P * P) * 4,
                                   'note': 'write-only kernel; measured pure-write ceiling on this pool is 3934 GB/s (memset), copy peak counts read+write'},
-                 'conv_tensor_util': {'achieved_TFLOPs': conv_fl * n_local / (conv_ms / 1e3) / 1e12,
-                                      'frac_of_sustained_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
-                                      'frac_of_burst_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
-                                      'ncu_tensor_pipe_active_pct': 'profiles/r01_ncu_summary.json'}}
+                 'conv_tensor_util': conv_util}
+    if args.mode == 'dense':
+        # the per-patch kernels on the same band, for comparison (one warm-up pass + one timed pass)
+        handle.set_dense(False)
+        handle.infer_scene(scene, r0, r1, pred_map=pred_map)
+        pp0, pp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(1)
+        pp0.record()
+        handle.infer_scene(scene, r0, r1, pred_map=pred_map)
+        pp1.record()
+        torch.cuda.synchronize()
+        pp_roof, pp_util = patch_roofline()
+        secondary['per_patch_path'] = {'px_per_s_this_rank': n_local / pp0.elapsed_time(pp1) * 1e3, 'chunk_pixels': args.max_batch,
+                                       'dominant_kernel': pp_roof['kernel'], 'achieved_TFLOPs': pp_roof['achieved'], 'frac': pp_roof['frac'],
+                                       'whole_net_tflops': pp_roof['whole_net_tflops'], 'conv_tensor_util': pp_util,
+                                       'stage_ms': pp_roof['stage_ms']}
+        handle.set_dense(True, args.band)
 
     if not args.no_train:
         secondary['train_step'] = train_step_metric(dev, world)
@@ -363,7 +434,7 @@ def main():
         cpu_baseline = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc}
 
     if rank == 0:
-        config.update({'global_pixels': npix_total, 'chunk_pixels': args.max_batch, 'row_band_rank0': [r0, r1],
+        config.update({'global_pixels': npix_total, 'row_band_rank0': [r0, r1],
                        'flops_per_pixel': handle.flops_per_patch, 'OA_AA_Kappa': [float(result[1]), float(result[0]), float(result[2])]})
         emit(({'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                           'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,

@@ -19,6 +19,7 @@
 // with R = (r1 - r0) + p - 1 rows and C = W + p - 1 columns.  Positions a band never needs hold don't-care values
 // (they only ever feed other don't-care positions).  Results equal the per-patch path up to fp32 summation order.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,7 +34,7 @@ struct DenseWs {
     __nv_bfloat16 *A = nullptr, *Z = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr, *F = nullptr;
     float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
     __nv_bfloat16* w_pan2 = nullptr;                 // tap-major packing of pan2 (the per-patch path may use the row-pair one)
-    CUtensorMap mapA, mapB1, mapB1s2, mapB2, mapCAT;
+    CUtensorMap mapA, mapB1, mapB2, mapCAT;
     cudaEvent_t ev[12] = {};
     float stage_ms[12] = {};
     size_t bytes = 0;
@@ -104,17 +105,19 @@ __global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restri
 // PAN stem (conv3x3 1->32 + BN + ReLU + maxpool2) on the pooled grid: band-local pooled row Ul <-> pooled row u0 + Ul
 // = PAN rows 2(u0+Ul), 2(u0+Ul)+1.  The pooling grid is aligned to every patch origin (4x is even).  A pooled cell on
 // the first pooled row of a patch = max(first-row variant of its upper conv row, interior variant of its lower one).
-// w: fp32 [32][1][3][3].  grid.y = channel chunk.  out: B1[9][4][R2][C2][8].
+// w: fp32 [32][1][3][3].  grid.y = channel chunk.  out: B1[9][phase 4][4][R1][C1][8], PHASE-SEPARATED: pooled cell (U, V) is
+// stored at (U >> 1, V >> 1) of phase plane (U & 1) * 2 + (V & 1) (see conv_pool4_kernel).  rows / C2 count pooled cells.
 __global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restrict__ pan, int H4p, int W4p, int pitch, int u0, int rows,
-                                                           int R2, int C2, const float* __restrict__ w, const float* __restrict__ scale,
+                                                           int R1, int C1, const float* __restrict__ w, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ B1) {
+    const int C2 = 2 * C1;
     __shared__ float w_s[8][9], sc_s[8], sh_s[8];
     const int ch = blockIdx.y;
     for (int i = threadIdx.x; i < 72; i += blockDim.x) w_s[i / 9][i % 9] = w[ch * 72 + i];
     if (threadIdx.x < 8) { sc_s[threadIdx.x] = scale[ch * 8 + threadIdx.x]; sh_s[threadIdx.x] = shift[ch * 8 + threadIdx.x]; }
     __syncthreads();
     const int64_t total = (int64_t)rows * C2;
-    const int64_t plane = (int64_t)R2 * C2;
+    const int64_t plane = (int64_t)R1 * C1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int Ul = (int)(i / C2), PY = (int)(i % C2);
         const int PX = u0 + Ul;
@@ -154,9 +157,10 @@ __global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restri
                     else out[v][j >> 1] = bits;
                 }
         }
-        uint4* o = reinterpret_cast<uint4*>(B1) + ((int64_t)ch * R2 + Ul) * C2 + PY;
+        const int ph = (Ul & 1) * 2 + (PY & 1);                   // u0 is even: band-local and absolute row parity agree
+        uint4* o = reinterpret_cast<uint4*>(B1) + (((int64_t)ph * 4 + ch) * R1 + (Ul >> 1)) * C1 + (PY >> 1);
 #pragma unroll
-        for (int v = 0; v < 9; ++v) o[(int64_t)v * 4 * plane] = make_uint4(out[v][0], out[v][1], out[v][2], out[v][3]);
+        for (int v = 0; v < 9; ++v) o[(int64_t)v * 16 * plane] = make_uint4(out[v][0], out[v][1], out[v][2], out[v][3]);
     }
 }
 
@@ -167,14 +171,13 @@ __device__ __forceinline__ uint4 max4(uint4 a, uint4 b) {
 // conv class of the two rows (columns) a pooled cell of border class a covers: first cell -> (0, 1), interior -> (2, 2), last -> (3, 4)
 __device__ __forceinline__ int pool_cls(int a, int s) { return a == 0 ? s : a == 1 ? 2 : 3 + s; }
 
-// STRIDE 1 (ms2, pan3): out[(a,b)][ch][X][Y] = max_{s,t} Z[(pool_cls(a,s), pool_cls(b,t))][ch][X+s][Y+t], Z and out on the same grid.
-// STRIDE 2 (pan2):      out[(a,b)][ch][X][Y] = max_{s,t} Z[...][ch][2X+s][2Y+t], Z on the (2 rows) x (2 cols) grid.
-template <int STRIDE>
+// ms2, pan3: out[(a,b)][ch][X][Y] = max_{s,t} Z[(pool_cls(a,s), pool_cls(b,t))][ch][X+s][Y+t], Z and out on the same grid (the
+// pooling windows of neighbouring anchors overlap: stride 1).  pan2's aligned pooling is fused into conv_pool4_kernel.
 __global__ void __launch_bounds__(256) pool_maps_kernel(const uint4* __restrict__ Z, int zch, int rows, int R1, int C1, uint4* __restrict__ out,
                                                         int out_chunks, int out_chunk0) {
     const int64_t per_plane = (int64_t)zch * rows * C1;
     const int64_t total = 9 * per_plane;
-    const int ZR = STRIDE * R1, ZC = STRIDE * C1;
+    const int ZR = R1, ZC = C1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int Y = (int)(i % C1);
         int64_t r = i / C1;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256) pool_maps_kernel(const uint4* __restrict_
         for (int s = 0; s < 2; ++s)
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                const int zr = STRIDE * X + s, zc = STRIDE * Y + t;
+                const int zr = X + s, zc = Y + t;
                 if (zr < ZR && zc < ZC) {
                     const int cls = pool_cls(a, s) * 5 + pool_cls(b, t);
                     m = max4(m, __ldg(Z + (((int64_t)cls * zch + ch) * ZR + zr) * ZC + zc));
@@ -348,13 +351,64 @@ static void build_cls(tc::DenseCls& c, int cr, int cc, int out_plane, int row0) 
         }
 }
 
+// Pooled class (a, b) of the fused conv + aligned-pool layer (conv_pool4_kernel): per axis, input offset o = s + dy in
+// {-1, 0, 1, 2} from the cell origin has border variant kOffVariant[a][o + 1] (-1 = outside the patch), lives in phase
+// o & 1 and at cell shift floor(o / 2).  Sources = distinct (variant, phase) pairs of an axis; a box = row source x column
+// source, its origin the smallest shift any of its users needs (extent <= 17 x 9 cells).
+static const int kOffVariant[3][4] = {{-1, 0, 1, 1}, {1, 1, 1, 1}, {1, 1, 2, -1}};
+struct AxisSrc { int variant, phase, origin; };
+static int axis_sources(int a, AxisSrc* src, int* src_of_off) {
+    int n = 0;
+    for (int o = -1; o <= 2; ++o) {
+        src_of_off[o + 1] = -1;
+        const int v = kOffVariant[a][o + 1];
+        if (v < 0) continue;
+        const int ph = o & 1, sh = o < 0 ? -1 : o / 2;              // floor(o / 2): -1 -> -1, 0 -> 0, 1 -> 0, 2 -> 1
+        int k = 0;
+        while (k < n && !(src[k].variant == v && src[k].phase == ph)) ++k;
+        if (k == n) { src[n].variant = v; src[n].phase = ph; src[n].origin = sh; ++n; }
+        src[k].origin = std::min(src[k].origin, sh);
+        src_of_off[o + 1] = k;
+    }
+    return n;
+}
+static int build_pool4_cls(tc::Pool4Cls& c, int a, int b) {
+    memset(&c, 0, sizeof(c));
+    AxisSrc rs[4], cs[4];
+    int r_of[4], c_of[4];
+    const int nr = axis_sources(a, rs, r_of), nc = axis_sources(b, cs, c_of);
+    if (nr * nc > tc::kP4MaxBoxes) { set_error("pool4 class (%d,%d) needs %d boxes", a, b, nr * nc); return DMF_ERR_STATE; }
+    c.out_plane = (int16_t)(a * 3 + b);
+    c.n_boxes = (int16_t)(nr * nc);
+    for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < nc; ++j) {
+            const int k = i * nc + j;
+            c.box_plane[k] = (int16_t)((rs[i].variant * 3 + cs[j].variant) * 4 + rs[i].phase * 2 + cs[j].phase);
+            c.box_drow[k] = (int8_t)rs[i].origin;
+            c.box_dcol[k] = (int8_t)cs[j].origin;
+        }
+    auto floor2 = [](int o) { return o < 0 ? -1 : o / 2; };
+    for (int tap = 0; tap < 9; ++tap)
+        for (int sub = 0; sub < 4; ++sub) {
+            const int orow = (sub >> 1) + tap / 3 - 1, ocol = (sub & 1) + tap % 3 - 1;
+            const int i = r_of[orow + 1], j = c_of[ocol + 1];
+            if (i < 0 || j < 0) { c.off[tap * 4 + sub] = -1; continue; }
+            const int dr = floor2(orow) - rs[i].origin, dc = floor2(ocol) - cs[j].origin;
+            if (dr < 0 || dr + 16 > tc::kP4BoxRows || dc < 0 || dc + 8 > tc::kP4BoxCols) { set_error("pool4 class (%d,%d): window outside its box", a, b); return DMF_ERR_STATE; }
+            c.off[tap * 4 + sub] = (int16_t)(((uint32_t)(i * nc + j) * tc::kP4BoxSlot + (uint32_t)(dr * tc::kP4BoxCols + dc) * 16) >> 4);
+        }
+    return DMF_OK;
+}
+
 template <int CI, int CO, int TAPS, int RS, int G>
 static int launch_dense(const CUtensorMap& map, tc::DenseParams& P, cudaStream_t st) {
     constexpr int HR = RS * 15 + 3;
     constexpr size_t a_stage = (size_t)(CI / 8) * (TAPS == 9 ? HR * tc::kPitch * 16 : 128 * 16);
-    constexpr size_t fixed = (size_t)TAPS * CI * CO * 2 + 2 * CO * 4 + 26 * 8 + 16;
+    constexpr size_t fixed = (size_t)TAPS * CI * CO * 2 + 2 * CO * 4 + 28 * 8 + tc::kDenseMaxCls * sizeof(tc::DenseCls);
     static_assert(fixed + a_stage <= (size_t)kSmemLimit, "dense layer does not fit in shared memory");
     P.n_stage = (int)std::min<size_t>(8, (kSmemLimit - fixed) / a_stage);
+    static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
+    P.dbg = dbg;
     P.n_tiles = P.tiles_x * P.tiles_y * P.n_cls;
     auto kern = tc::conv_dense_kernel<CI, CO, TAPS, RS, G>;
     static bool attr_set = false;
@@ -413,7 +467,7 @@ static int dense_prepare(dmf_net* n, int W, int band) {
     dense_free_ws(d);
     const int p = n->p;
     const size_t R1 = band + p - 1, C1 = W + p - 1, px = R1 * C1;
-    const size_t sA = px * 9 * C_MS1 * 2, sZ = px * 25 * 32 * 16, sCAT = px * 9 * C_CAT * 2, sB1 = px * 4 * 9 * C_PAN1 * 2,
+    const size_t sA = px * 9 * C_MS1 * 2, sZ = px * 25 * C_MS2 * 2, sCAT = px * 9 * C_CAT * 2, sB1 = px * 4 * 9 * C_PAN1 * 2,
                  sB2 = px * 9 * C_PAN2 * 2, sF = px * 9 * C_FUSE * 2;
     DMF_CUDA(cudaMalloc(&d->A, sA));
     DMF_CUDA(cudaMalloc(&d->Z, sZ));
@@ -431,8 +485,7 @@ static int dense_prepare(dmf_net* n, int W, int band) {
     DMF_CUDA(cudaMemset(d->F, 0, sF));
     d->W = W; d->band = band; d->p = p; d->R1 = (int)R1; d->C1 = (int)C1;
     DMF_TRY(make_dense_map(&d->mapA, d->A, 9, C_MS1 / 8, (int)R1, (int)C1, tc::kPitch, 18));
-    DMF_TRY(make_dense_map(&d->mapB1, d->B1, 9, C_PAN1 / 8, 2 * (int)R1, 2 * (int)C1, tc::kPitch, 18));
-    DMF_TRY(make_dense_map(&d->mapB1s2, d->B1, 9, C_PAN1 / 8, 2 * (int)R1, 2 * (int)C1, tc::kPitch, 33));
+    DMF_TRY(make_dense_map(&d->mapB1, d->B1, 36, C_PAN1 / 8, (int)R1, (int)C1, tc::kP4BoxCols, tc::kP4BoxRows));
     DMF_TRY(make_dense_map(&d->mapB2, d->B2, 9, C_PAN2 / 8, (int)R1, (int)C1, tc::kPitch, 18));
     DMF_TRY(make_dense_map(&d->mapCAT, d->CAT, 9, C_CAT / 8, (int)R1, (int)C1, 32, 4));
     for (auto& e : d->ev) if (!e) DMF_CUDA(cudaEventCreate(&e));
@@ -450,7 +503,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
     const int p = n->p, W = s->W;
     const int band = std::max(1, std::min(n->dense_band, row1 - row0));
     DMF_TRY(dense_prepare(n, W, band));
-    const int R1 = d->R1, C1 = d->C1, R2 = 2 * R1, C2 = 2 * C1;
+    const int R1 = d->R1, C1 = d->C1, C2 = 2 * C1;
     const bool tm = n->timing;
     int evi = 0;
     auto mark = [&]() { if (tm && evi < 12) cudaEventRecord(d->ev[evi++], st); };
@@ -472,40 +525,41 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             P.w = n->L[0].w; P.scale = n->L[0].scale; P.shift = n->L[0].shift; P.out = d->Z;
             for (int cr = 0; cr < 5; ++cr)
                 for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[cr * 5 + cc], cr, cc, cr * 5 + cc, 0);
-            DMF_TRY((launch_dense<C_MS1, C_MS2, 9, 1, 4>(d->mapA, P, st)));
+            static const bool g3 = getenv("DMF_DENSE_G3") != nullptr;      // experiment: 3 epilogue groups (more registers per thread)
+            if (g3) DMF_TRY((launch_dense<C_MS1, C_MS2, 9, 1, 3>(d->mapA, P, st)));
+            else DMF_TRY((launch_dense<C_MS1, C_MS2, 9, 1, 4>(d->mapA, P, st)));
         }
         mark();
-        pool_maps_kernel<1><<<grid_for((int64_t)9 * (C_MS2 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
+        pool_maps_kernel<<<grid_for((int64_t)9 * (C_MS2 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
             reinterpret_cast<const uint4*>(d->Z), C_MS2 / 8, rows, R1, C1, reinterpret_cast<uint4*>(d->CAT), C_CAT / 8, 0);
         DMF_LAUNCHED();
         mark();
         // ---- PAN branch
         pan_stem_map_kernel<<<dim3(grid_for((int64_t)2 * rows * C2, 256, 8), C_PAN1 / 8), 256, 0, st>>>(
-            s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R2, C2, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
+            s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
         {
-            tc::DenseParams P{};
-            P.rows = R2; P.cols = C2; P.tiles_x = cdiv(C2, 8); P.out_chunks = C_PAN2 / 8; P.out_chunk0 = 0;
-            P.w = d->w_pan2; P.scale = n->L[1].scale; P.shift = n->L[1].shift; P.out = d->Z;
-            // interior rows: every row of the pooled-once grid
-            P.tiles_y = cdiv(2 * rows, 16); P.n_cls = 5;
-            for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[cc], 2, cc, 2 * 5 + cc, 0);
-            DMF_TRY((launch_dense<C_PAN1, C_PAN2, 9, 1, 4>(d->mapB1, P, st)));
-            // edge rows u = 0, 2p-2 sit on even rows of the grid, u = 1, 2p-1 on odd rows: row stride 2
-            P.tiles_y = cdiv(rows, 16); P.n_cls = 20;
-            int k = 0;
-            for (int cr = 0; cr < 5; ++cr) {
-                if (cr == 2) continue;
-                for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[k++], cr, cc, cr * 5 + cc, (cr == 1 || cr == 4) ? 1 : 0);
+            tc::Pool4Params P{};
+            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_tiles = P.tiles_x * P.tiles_y * 9;
+            P.out_chunks = C_PAN2 / 8;
+            P.w = d->w_pan2; P.scale = n->L[1].scale; P.shift = n->L[1].shift; P.out = d->B2;
+            static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;
+            P.dbg = dbg;
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) DMF_TRY(build_pool4_cls(P.cls[a * 3 + b], a, b));
+            constexpr size_t smem = 9 * C_PAN1 * C_PAN2 * 2 + (size_t)tc::kP4Stages * tc::kP4Stage + 2 * C_PAN2 * 4 + 12 * 8 + 9 * sizeof(tc::Pool4Cls);
+            static_assert(smem <= (size_t)kSmemLimit, "conv_pool4_kernel does not fit in shared memory");
+            static bool attr_set = false;
+            if (!attr_set) {
+                DMF_CUDA(cudaFuncSetAttribute(tc::conv_pool4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+                attr_set = true;
             }
-            DMF_TRY((launch_dense<C_PAN1, C_PAN2, 9, 2, 4>(d->mapB1s2, P, st)));
+            tc::conv_pool4_kernel<<<std::min(P.n_tiles, num_sms()), 320, smem, st>>>(d->mapB1, P);
+            DMF_LAUNCHED();
         }
         mark();
-        pool_maps_kernel<2><<<grid_for((int64_t)9 * (C_PAN2 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
-            reinterpret_cast<const uint4*>(d->Z), C_PAN2 / 8, rows, R1, C1, reinterpret_cast<uint4*>(d->B2), C_PAN2 / 8, 0);
-        DMF_LAUNCHED();
-        mark();
+        mark();          // (stage slot of the former separate pan2 pooling pass)
         {
             tc::DenseParams P{};
             P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_cls = 25;
@@ -513,10 +567,12 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             P.w = n->L[2].w; P.scale = n->L[2].scale; P.shift = n->L[2].shift; P.out = d->Z;
             for (int cr = 0; cr < 5; ++cr)
                 for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[cr * 5 + cc], cr, cc, cr * 5 + cc, 0);
-            DMF_TRY((launch_dense<C_PAN2, C_PAN3, 9, 1, 4>(d->mapB2, P, st)));
+            static const bool g3 = getenv("DMF_DENSE_G3") != nullptr;
+            if (g3) DMF_TRY((launch_dense<C_PAN2, C_PAN3, 9, 1, 3>(d->mapB2, P, st)));
+            else DMF_TRY((launch_dense<C_PAN2, C_PAN3, 9, 1, 4>(d->mapB2, P, st)));
         }
         mark();
-        pool_maps_kernel<1><<<grid_for((int64_t)9 * (C_PAN3 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
+        pool_maps_kernel<<<grid_for((int64_t)9 * (C_PAN3 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
             reinterpret_cast<const uint4*>(d->Z), C_PAN3 / 8, rows, R1, C1, reinterpret_cast<uint4*>(d->CAT), C_CAT / 8, C_MS2 / 8);
         DMF_LAUNCHED();
         mark();
@@ -598,7 +654,7 @@ int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* 
     const size_t px = (size_t)d->R1 * d->C1;
     const std::string k(name);
     if (k == "A") { *ptr_out = d->A; *bytes_out = px * 9 * C_MS1 * 2; }
-    else if (k == "Z") { *ptr_out = d->Z; *bytes_out = px * 25 * 32 * 16; }
+    else if (k == "Z") { *ptr_out = d->Z; *bytes_out = px * 25 * C_MS2 * 2; }
     else if (k == "CAT") { *ptr_out = d->CAT; *bytes_out = px * 9 * C_CAT * 2; }
     else if (k == "B1") { *ptr_out = d->B1; *bytes_out = px * 4 * 9 * C_PAN1 * 2; }
     else if (k == "B2") { *ptr_out = d->B2; *bytes_out = px * 9 * C_PAN2 * 2; }

@@ -37,6 +37,7 @@ struct DenseParams {
     int tiles_x, tiles_y, n_cls, n_tiles;
     int n_stage;
     int out_chunks, out_chunk0;           // channel chunks of one output plane, first chunk written
+    int dbg;                              // diagnostics only: bit0 = skip the TMA halo loads, bit1 = skip the epilogue math/stores, bit2 = no per-step commit
     const __nv_bfloat16* w;               // packed [tap][C_in/8][C_out][8]
     const float* scale;
     const float* shift;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
     // bars: [0,8) full, [8,16) empty, 16 weights, 17..20 tmem_full, 21..24 tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    DenseCls* cls_s = reinterpret_cast<DenseCls*>(bars + 28);        // class table: one LDS per field instead of indexed constant loads
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         scale_s[i] = P.scale[i];
         shift_s[i] = P.shift[i];
     }
+    for (int i = threadIdx.x; i < P.n_cls * (int)(sizeof(DenseCls) / 4); i += kThreads)
+        reinterpret_cast<uint32_t*>(cls_s)[i] = reinterpret_cast<const uint32_t*>(P.cls)[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
@@ -97,12 +101,14 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    // tile -> (row strip ty, class c, column tile tx)
-    auto decode = [&](int tile, int& ty, int& c, int& tx) {
-        tx = tile % P.tiles_x;
-        const int r = tile / P.tiles_x;
-        c = r % P.n_cls;
-        ty = r / P.n_cls;
+    // tile -> (row strip ty, class c, column tile tx); every role walks its tiles with the same incremental decode
+    int tx = (int)blockIdx.x % P.tiles_x, c = ((int)blockIdx.x / P.tiles_x) % P.n_cls, ty = ((int)blockIdx.x / P.tiles_x) / P.n_cls;
+    auto next_tile = [&]() {
+        tx += (int)gridDim.x;
+        while (tx >= P.tiles_x) {
+            tx -= P.tiles_x;
+            if (++c == P.n_cls) { c = 0; ++ty; }
+        }
     };
 
     if (warp == 0) {
@@ -118,17 +124,19 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         __syncwarp();
         int st = 0;
         uint32_t ph = 1;
-        for (int i = 0; i < n_local; ++i) {
-            int ty, c, tx;
-            decode(blockIdx.x + i * gridDim.x, ty, c, tx);
-            const int n_steps = P.cls[c].n_steps;
-            const int row = TAPS == 9 ? P.cls[c].row0 + ty * 16 * RS - 1 : ty * 4;
+        for (int i = 0; i < n_local; ++i, next_tile()) {
+            const int n_steps = cls_s[c].n_steps;
+            const int row = TAPS == 9 ? cls_s[c].row0 + ty * 16 * RS - 1 : ty * 4;
             const int col8 = TAPS == 9 ? (tx * 8 - 1) * 8 : tx * 32 * 8;
             for (int s = 0; s < n_steps; ++s) {
                 mbar_wait(empty_bar(st), ph);
                 if (leader) {
-                    mbar_expect_tx(full_bar(st), A_STAGE);
-                    tma_load_4d(smem_u32(a_s) + (uint32_t)st * A_STAGE, &in_map, full_bar(st), col8, P.cls[c].in_plane[s], row, 0);
+                    if (P.dbg & 1) {
+                        mbar_arrive(full_bar(st));
+                    } else {
+                        mbar_expect_tx(full_bar(st), A_STAGE);
+                        tma_load_4d(smem_u32(a_s) + (uint32_t)st * A_STAGE, &in_map, full_bar(st), col8, cls_s[c].in_plane[s], row, 0);
+                    }
                 }
                 __syncwarp();
                 if (++st == P.n_stage) { st = 0; ph ^= 1; }
@@ -142,16 +150,15 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
         int st = 0;
         uint32_t ph = 0;
-        for (int i = 0; i < n_local; ++i) {
-            int ty, c, tx;
-            decode(blockIdx.x + i * gridDim.x, ty, c, tx);
-            const int n_steps = P.cls[c].n_steps;
+        for (int i = 0; i < n_local; ++i, next_tile()) {
+            const int n_steps = cls_s[c].n_steps;
+            const uint64_t masks = *reinterpret_cast<const uint64_t*>(cls_s[c].mask);
             const int acc = i % G;
             mbar_wait(tempty_bar(acc), ((i / G) & 1) ^ 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C_OUT);
             uint32_t accumulate = 0;
             for (int s = 0; s < n_steps; ++s) {
-                const uint32_t mask = P.cls[c].mask[s];
+                const uint32_t mask = (uint32_t)(masks >> (16 * s)) & 0xFFFFu;
                 mbar_wait(full_bar(st), ph);
                 tc_fence_after();
                 const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * A_STAGE, A_PLANE, SBO_A);
@@ -169,7 +176,8 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
                             }
                         }
                     }
-                    umma_commit(empty_bar(st));
+                    if (P.dbg & 4) mbar_arrive(empty_bar(st));      // diagnostics: stage released without tracking the MMAs
+                    else umma_commit(empty_bar(st));
                     if (s == n_steps - 1) umma_commit(tfull_bar(acc));
                 }
                 __syncwarp();
@@ -183,12 +191,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         const int m = q * 32 + lane;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * C_OUT);
         const int64_t cstride = (int64_t)P.rows * P.cols * 8;
-        for (int i = eg; i < n_local; i += G) {
-            int ty, c, tx;
-            decode(blockIdx.x + i * gridDim.x, ty, c, tx);
+        for (int i = 0; i < n_local; ++i, next_tile()) {
+            if (i % G != eg) continue;
             int row, col;
             if (TAPS == 9) {
-                row = P.cls[c].row0 + (ty * 16 + (m >> 3)) * RS;
+                row = cls_s[c].row0 + (ty * 16 + (m >> 3)) * RS;
                 col = tx * 8 + (m & 7);
             } else {
                 row = ty * 4 + (m >> 5);
@@ -196,11 +203,11 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
             }
             const bool valid = row < P.rows && col < P.cols;
             __nv_bfloat16* const obase =
-                P.out + ((((int64_t)P.cls[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
+                P.out + ((((int64_t)cls_s[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
             mbar_wait(tfull_bar(eg), (i / G) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < C_OUT; c0 += 32) {
+            for (int c0 = 0; c0 < ((P.dbg & 2) ? 0 : C_OUT); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(t_row + c0, v);
                 uint32_t pk[16];
@@ -234,6 +241,223 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fused conv3x3 + aligned 2x2 max-pool for the layer that sits on the pooled-once PAN grid (pan2, 32 -> 64).
+//
+// The pooled output cell (X, Y) of border class (a, b) is the max of the 4 conv outputs at grid positions
+// (2X + s, 2Y + t); conv output (s, t) reads inputs at (2X + s + dy, 2Y + t + dx), i.e. at offsets o = s + dy,
+// t + dx in {-1, 0, 1, 2} from the cell origin, and the border variant of an input depends on its offset only.
+// The input maps are stored PHASE-SEPARATED ([variant][row phase, col phase][chunk][R][C][8]): offset o lives in
+// phase o & 1 at cell shift floor(o / 2), so every (sub-position, tap) pair is a unit-stride 16 x 8 window of some
+// (variant, phase) plane.  One pipeline step = one pooled tile of 16 x 8 cells: <= 9 TMA boxes of 17 x 9 cells (one per
+// (row source) x (column source)), 4 accumulators of N = 64 in TMEM (one per sub-position, 2 tiles in flight), up to
+// 72 MMAs issued tap-major so that consecutive MMAs hit different accumulators, and an epilogue that applies BN +
+// ReLU to the 4 accumulators and keeps the thread-local maximum: the pooled map is the only thing written.
+constexpr int kP4BoxRows = 17, kP4BoxCols = 9, kP4MaxBoxes = 9;
+constexpr uint32_t kP4Plane = kP4BoxRows * kP4BoxCols * 16;              // bytes of one channel-chunk plane of a box
+constexpr int kP4Cin = 32, kP4Cout = 64;
+constexpr uint32_t kP4BoxBytes = (kP4Cin / 8) * kP4Plane;                // 9792
+constexpr uint32_t kP4BoxSlot = (kP4BoxBytes + 127) / 128 * 128;         // 9856: TMA destinations are 128-byte aligned
+constexpr uint32_t kP4Stage = kP4MaxBoxes * kP4BoxSlot;
+constexpr int kP4Stages = 2;
+
+struct Pool4Cls {
+    int16_t out_plane, n_boxes;
+    int16_t box_plane[kP4MaxBoxes];
+    int8_t box_drow[kP4MaxBoxes], box_dcol[kP4MaxBoxes];
+    int16_t off[36];                      // [tap][sub]: (byte offset of the A window inside the stage) >> 4, or -1
+};
+
+struct Pool4Params {
+    int rows, cols;                       // pooled grid = grid of every phase plane
+    int tiles_x, tiles_y, n_tiles;
+    int out_chunks;
+    int dbg;
+    const __nv_bfloat16* w;               // packed [tap][C_in/8][C_out][8]
+    const float* scale;
+    const float* shift;
+    __nv_bfloat16* out;                   // [9][out_chunks][rows][cols][8]
+    Pool4Cls cls[9];
+};
+
+__global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ Pool4Params P) {
+    constexpr int kThreads = 320, G = 2;
+    constexpr int C_IN = kP4Cin, C_OUT = kP4Cout, KCH = C_IN / 8;
+    constexpr uint32_t WBYTES = 9u * C_IN * C_OUT * 2;
+    constexpr uint32_t SBO_A = kP4BoxCols * 16;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;
+    uint8_t* a_s = smem + WBYTES;                                              // WBYTES = 36864 is a multiple of 128
+    float* scale_s = reinterpret_cast<float*>(a_s + (size_t)kP4Stages * kP4Stage);
+    float* shift_s = scale_s + C_OUT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
+    // bars: 0,1 full; 2,3 empty; 4 weights; 5,6 tmem_full; 7,8 tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    Pool4Cls* cls_s = reinterpret_cast<Pool4Cls*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
+    const uint32_t w_bar = bar0 + 8u * 4;
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (5 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (7 + a); };
+
+    for (int i = threadIdx.x; i < C_OUT; i += kThreads) {
+        scale_s[i] = P.scale[i];
+        shift_s[i] = P.shift[i];
+    }
+    for (int i = threadIdx.x; i < 9 * (int)(sizeof(Pool4Cls) / 4); i += kThreads)
+        reinterpret_cast<uint32_t*>(cls_s)[i] = reinterpret_cast<const uint32_t*>(P.cls)[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kP4Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(w_bar, 1);
+        for (int a = 0; a < G; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // tile -> (row strip ty, class c, column tile tx), walked incrementally by every role
+    int tx = (int)blockIdx.x % P.tiles_x, c = ((int)blockIdx.x / P.tiles_x) % 9, ty = ((int)blockIdx.x / P.tiles_x) / 9;
+    auto next_tile = [&]() {
+        tx += (int)gridDim.x;
+        while (tx >= P.tiles_x) {
+            tx -= P.tiles_x;
+            if (++c == 9) { c = 0; ++ty; }
+        }
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer: all boxes of a tile land on one barrier
+        const bool leader = elect_one();
+        if (leader) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
+            mbar_expect_tx(w_bar, WBYTES);
+            constexpr uint32_t CH = 12288;
+            for (uint32_t off = 0; off < WBYTES; off += CH)
+                bulk_load(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(P.w) + off, min(CH, WBYTES - off), w_bar);
+        }
+        __syncwarp();
+        for (int i = 0; i < n_local; ++i, next_tile()) {
+            const int st = i & 1;
+            mbar_wait(empty_bar(st), ((i >> 1) & 1) ^ 1);
+            if (leader) {
+                const int nbx = cls_s[c].n_boxes;
+                if (P.dbg & 1) {
+                    mbar_arrive(full_bar(st));
+                } else {
+                    mbar_expect_tx(full_bar(st), (uint32_t)nbx * kP4BoxBytes);
+                    const uint32_t dst = smem_u32(a_s) + (uint32_t)st * kP4Stage;
+                    for (int b = 0; b < nbx; ++b)
+                        tma_load_4d(dst + (uint32_t)b * kP4BoxSlot, &in_map, full_bar(st), (tx * 8 + cls_s[c].box_dcol[b]) * 8,
+                                    cls_s[c].box_plane[b], ty * 16 + cls_s[c].box_drow[b], 0);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_bf16(128, C_OUT);
+        const bool leader = elect_one();
+        mbar_wait(w_bar, 0);
+        const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
+        for (int i = 0; i < n_local; ++i, next_tile()) {
+            const int st = i & 1, buf = i & 1;
+            mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);
+            mbar_wait(full_bar(st), (i >> 1) & 1);
+            tc_fence_after();
+            const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * kP4Stage, kP4Plane, SBO_A);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 4 * C_OUT);
+            if (leader) {
+                const int16_t* off = cls_s[c].off;
+                uint32_t started = 0;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const int o = off[tap * 4 + sub];
+                        if (o >= 0) {
+#pragma unroll
+                            for (int j = 0; j < KCH / 2; ++j) {
+                                const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)o + (uint64_t)(((uint32_t)(2 * j) * kP4Plane) >> 4);
+                                const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((tap * KCH + 2 * j) * C_OUT * 16) >> 4);
+                                umma_bf16(d_tmem + (uint32_t)(sub * C_OUT), ad, bd, idesc, ((started >> sub) & 1u) | (uint32_t)j);
+                            }
+                            started |= 1u << sub;
+                        }
+                    }
+                }
+                umma_commit(empty_bar(st));
+                umma_commit(tfull_bar(buf));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------ epilogue: BN + ReLU on the 4 sub-position accumulators, thread-local max
+        const int eg = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * 4 * C_OUT);
+        const int64_t cstride = (int64_t)P.rows * P.cols * 8;
+        for (int i = 0; i < n_local; ++i, next_tile()) {
+            if ((i & 1) != eg) continue;
+            const int row = ty * 16 + (m >> 3), col = tx * 8 + (m & 7);
+            const bool valid = row < P.rows && col < P.cols;
+            __nv_bfloat16* const obase = P.out + (((int64_t)cls_s[c].out_plane * P.out_chunks * P.rows + row) * P.cols + col) * 8;
+            mbar_wait(tfull_bar(eg), (i >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < ((P.dbg & 2) ? 0 : C_OUT); c0 += 32) {
+                uint32_t pk[16];
+                const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
+                const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+#pragma unroll
+                for (int sub = 0; sub < 4; ++sub) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + (uint32_t)(sub * C_OUT + c0), v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 sc = sc4[k], sh = sh4[k];
+                        const float a0 = fmaxf(fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x), 0.f);
+                        const float a1 = fmaxf(fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y), 0.f);
+                        const float a2 = fmaxf(fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z), 0.f);
+                        const float a3 = fmaxf(fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w), 0.f);
+                        const uint32_t p0 = pack_bf16x2(a0, a1), p1 = pack_bf16x2(a2, a3);
+                        pk[2 * k] = sub == 0 ? p0 : max_bf16x2(pk[2 * k], p0);
+                        pk[2 * k + 1] = sub == 0 ? p1 : max_bf16x2(pk[2 * k + 1], p1);
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4)
+                        *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + s4) * cstride) =
+                            make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(eg));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 

@@ -7,7 +7,10 @@
 Inference (eval mode, no grad) runs on the hand-written sm_100a kernels of libdmf_b200: fp32
 CUDA-core stems, tcgen05/TMEM implicit-GEMM convolutions fed by TMA, fused head.  The packed bf16
 weights are rebuilt whenever a parameter changes.  ``infer_scene`` is the fused whole-scene path
-(gather + network + argmax + confusion matrix without materialising patches).
+(gather + network + argmax + confusion matrix without materialising patches); by default it runs the
+scene-dense evaluation (csrc/dense.cu: patches at stride 1 share every layer output that sits at the
+same scene position with the same border class), ``b200.dense: false`` in the config selects the
+per-patch kernels.
 
 Training (train mode, or grad enabled) also runs on libdmf_b200 (csrc/train.cu): ``forward`` returns
 logits attached to a torch.autograd.Function whose backward is the native backward pass (BatchNorm
@@ -63,6 +66,9 @@ class Net(nn.Module):
         b200 = args.get('b200') if isinstance(args.get('b200'), dict) else {}
         self.max_batch = int(b200.get('max_batch', 16384))
         self.max_train_batch = int(b200.get('max_train_batch', max(512, int(args.get('batchsize', 0) or 0))))
+        # whole-scene inference: scene-dense maps (default) or the per-patch kernels; anchor rows per dense pass
+        self.dense = bool(b200.get('dense', True))
+        self.dense_band = int(b200.get('dense_band', 128))
         for name, (cin, cout) in WIDTHS.items():
             setattr(self, name, _conv_bn(cin, cout, 3))
         self.fuse = _conv_bn(128 + 128, C_FUSE, 1)
@@ -89,6 +95,7 @@ class Net(nn.Module):
         key = (str(dev),) + self._weights_key()
         if self._native is None or self._native.device != str(dev):
             self._native = dmf.NetHandle(self.patch, self.num_classes, self.max_batch, str(dev))
+            self._native.set_dense(self.dense, self.dense_band)
             self._native_key = None
         if key != self._native_key:
             self._native.load_state_dict(self.state_dict())

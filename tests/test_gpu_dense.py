@@ -52,6 +52,24 @@ def gather_patches(buf, planes_chunks, dims, anchors, S, a, b, chunk0=0, chunks=
     return torch.stack(out).float()
 
 
+def gather_patches_b1(buf, dims, anchors, p):
+    """The PAN stem maps are phase-separated ([variant][row phase * 2 + col phase][chunk][rows][cols][8]): pooled-once position
+    (U, V) = (2*xl + u, 2*y + v) sits at (U >> 1, V >> 1) of phase plane (U & 1, V & 1)."""
+    rows, cols = dims
+    S = 2 * p
+    m = buf[:9 * 4 * 4 * rows * cols * 8].view(9, 4, 4, rows, cols, 8)
+    ii = torch.arange(S, device=buf.device)
+    cls = torch.tensor([c3(i, S) for i in range(S)], device=buf.device)
+    variant = cls[:, None] * 3 + cls[None, :]
+    out = []
+    for xl, y in anchors:
+        r = (2 * xl + ii)[:, None].expand(S, S)
+        c = (2 * y + ii)[None, :].expand(S, S)
+        v = m[variant, (r & 1) * 2 + (c & 1), :, r >> 1, c >> 1]               # [S][S][4][8]
+        out.append(v.permute(2, 3, 0, 1).reshape(32, S, S))
+    return torch.stack(out).float()
+
+
 def assert_close_bf16(got, want, what, ulps=2, max_bad_frac=0.0):
     tol = ulps * 2.0 ** -8 * torch.maximum(got.abs(), want.abs()) + 1e-3
     bad = (got - want).abs() > tol
@@ -92,13 +110,13 @@ def test_dense_layers_in_isolation(dmf, p, H, W, row0, nb):
         # stems: fp32 weights (CUDA cores), bf16-rounded output
         got = gather_patches(A, 8, dims, anchors, p, 1, 1)
         assert_close_bf16(got, ref_block(ref.ms1, pm, False, quant_w=False), 'ms stem maps')
-        got_b1 = gather_patches(B1, 4, (2 * R, 2 * Cc), anchors, 2 * p, 2, 1)
+        got_b1 = gather_patches_b1(B1, dims, anchors, p)
         assert_close_bf16(got_b1, ref_block(ref.pan1, pp, True, quant_w=False), 'pan stem maps')
         # tensor-core layers, each fed with the dense path's own input
         got_ms2 = gather_patches(CAT, 32, dims, anchors, p // 2, 1, 2, 0, 16)
         assert_close_bf16(got_ms2, ref_block(ref.ms2, got, True), 'ms2 (conv_dense + pool_s1)')
         got_b2 = gather_patches(B2, 8, dims, anchors, p, 1, 1)
-        assert_close_bf16(got_b2, ref_block(ref.pan2, got_b1, True), 'pan2 (conv_dense RS=1,2 + pool_s2)')
+        assert_close_bf16(got_b2, ref_block(ref.pan2, got_b1, True), 'pan2 (conv_pool4: conv + aligned 2x2 max fused)')
         got_p3 = gather_patches(CAT, 32, dims, anchors, p // 2, 1, 2, 16, 16)
         assert_close_bf16(got_p3, ref_block(ref.pan3, got_b2, True), 'pan3 (conv_dense + pool_s1)')
         got_f = gather_patches(Fm, 16, dims, anchors, p // 2, 1, 2)

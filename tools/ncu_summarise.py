@@ -1,7 +1,9 @@
 """Turn an ncu report (.ncu-rep, read with the local ncu CLI) and a launch-list CSV into the small
-tracked summaries under profiles/.  Usage: python tools/ncu_summarise.py <rep> <launches.csv> <round-tag> <chunk_pixels>"""
+tracked summaries under profiles/.  Usage: python tools/ncu_summarise.py <rep> <launches.csv> <round-tag> <chunk_pixels> [<profiled command> [<launch-list command>]]"""
 import collections, csv, json, re, subprocess, sys
 rep, launches, tag, chunk = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
+prof_cmd = sys.argv[5] if len(sys.argv) > 5 else 'tools/perf_probe.py 1000 1000 %d 40' % chunk
+list_cmd = sys.argv[6] if len(sys.argv) > 6 else 'python bench.py --steps 1 --warmup 3 --no-cpu-baseline'
 
 def short(name):
     name = re.sub(r'\(CUtensorMap.*|\(dmf.*|\(const.*|\(tc::.*|\(PatchSrc.*', '', name)
@@ -25,7 +27,7 @@ for r in rows[2:]:
     e['tensor'].append(float(r[idx[K['tensor']]])); e['dram'].append(float(r[idx[K['dram']]]))
     e['mhz'].append(float(r[idx[K['cyc']]]) / float(r[idx[K['dur']]]))
     e['meta'] = [r[idx[K[k]]] for k in ('regs', 'grid', 'block', 'smem')]
-out = {'source': 'ncu --set full --clock-control none --import-source on; tools/perf_probe.py 1000 1000 %d 40; round %s' % (chunk, tag),
+out = {'source': 'ncu --set full --clock-control none --import-source on; %s; round %s' % (prof_cmd, tag),
        'workload': 'c2', 'chunk_pixels': chunk, 'kernels': {}}
 for k, e in agg.items():
     n = len(e['dur'])
@@ -43,8 +45,8 @@ for r in rows:
     us = v / 1000 if u.startswith('n') else v if u.startswith('u') else v * 1000
     a = agg.setdefault(short(r['Kernel Name']), [0, 0.0]); a[0] += 1; a[1] += us
 tot = sum(a[1] for a in agg.values())
-lines = ['# ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400  python bench.py --steps 1 --warmup 3 --no-cpu-baseline',
-         '# round %s, B200, chunks of %d px; per-launch times are cold-cache and serialised: compare SHARES with bench.py roofline.stage_ms' % (tag, chunk),
+lines = ['# ncu --metrics gpu__time_duration.sum --clock-control none  ' + list_cmd,
+         '# round %s, B200, chunk / band parameter %d; per-launch times are cold-cache and serialised: compare SHARES with bench.py roofline.stage_ms' % (tag, chunk),
          '%-48s %8s %12s %7s' % ('kernel', 'launches', 'total_us', 'share')]
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append('%-48s %8d %12.1f %6.1f%%' % (k, n, us, 100 * us / tot))
