@@ -349,8 +349,10 @@ def main():
         return roof, util
 
     def dense_roofline():
-        """FLOPs the dense kernels execute: a 3x3 layer has 5 border classes per axis with 2,3,3,3,2 live tap rows (columns):
-        (13)^2 = 169 tap evaluations of 2*Cin*Cout FLOPs per map position (no credit for tile padding or don't-care rows)."""
+        """FLOPs the dense kernels execute.  A fused conv + pool layer evaluates, per map position and pooled border class
+        (first / interior / last per axis), the 4 conv outputs of the pooling window with 2,3 / 3,3 / 3,2 live tap rows
+        (columns): (5 + 6 + 5)^2 = 256 tap evaluations of 2*Cin*Cout FLOPs per position (no credit for tile padding, skipped
+        taps or don't-care rows)."""
         handle.set_timing(True)
         handle.get_dense_timing(reset=True)
         handle.infer_scene(scene, r0, r1)
@@ -360,11 +362,13 @@ def main():
         bands = [min(band, r1 - b) for b in range(r0, r1, band)]
         pos = sum((nb + P - 1) * (W + P - 1) for nb in bands)                 # MS-resolution map positions computed
         kernels = {   # kernel -> (stage keys, FLOPs per MS-resolution position, launches per band)
-            'conv_dense_kernel<64,128,9,RS=1,G=4> (ms2 + pan3, 25 border classes)': (['conv_ms2', 'conv_pan3'], 2 * 169 * 2 * 64 * 128, 2),
-            'conv_dense_kernel<32,64,9,RS=1|2,G=4> (pan2, 5 + 20 classes)': (['conv_pan2'], 4 * (39 + 130 / 2) * 2 * 32 * 64, 2),
-            'conv_dense_kernel<256,128,1,RS=1,G=4> (fuse, 9 classes)': (['conv_fuse'], 9 * 2 * 256 * 128, 1),
+            'conv_pool4_kernel<64,128,KQ=2,3 stages> (ms2 + pan3: conv + stride-1 2x2 max, 9 pooled classes)':
+                (['conv_ms2', 'conv_pan3'], 2 * 256 * 2 * 64 * 128, 2),
+            'conv_pool4_kernel<32,64,KQ=4,2 stages> (pan2: conv + aligned 2x2 max)': (['conv_pan2'], 256 * 2 * 32 * 64, 1),
+            'conv_dense_kernel<256,128,1,RS=1,G=4> (fuse, 9 planes)': (['conv_fuse'], 9 * 2 * 256 * 128, 1),
         }
-        ncu_key = {k: 'tc::conv_dense_kernel<%s>' % v for k, v in zip(kernels, ('64,128,9,1,4', '32,64,9,1,4', '256,128,1,1,4'))}
+        ncu_key = {k: v for k, v in zip(kernels, ('tc::conv_pool4_kernel<64,128,2,3,19,11,1>', 'tc::conv_pool4_kernel<32,64,4,2,17,9,2>',
+                                                  'tc::conv_dense_kernel<256,128,1,1,4>'))}
         name, (keys, fl_pos, per_band) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
         k_ms = sum(stage[k] for k in keys)
         achieved = fl_pos * pos / (k_ms / 1e3) / 1e12

@@ -6,14 +6,12 @@
 // U = 2x + u, V = 2y + v (u, v in [0, 2p)).  A layer's value at a patch-relative position depends on the absolute
 // position and on the position's border class only (see dense_tc.cuh), so per row band [r0, r1) of anchors:
 //
-//   scene --ms_stem_map--> A  [9 ][ 8][R][C][8]     9  = {first, interior, last}^2 of the 3x3/pad-1 stem conv
-//   A  --conv_dense 25 cls--> Z [25][16][R][C][8]   25 = {0, 1, interior, p-2, p-1}^2
-//   Z  --pool_s1-----------> CAT[9 ][0..15]         2x2 max over (X..X+1, Y..Y+1); pooled cell k = 0 reads classes (0,1), ...
-//   scene --pan_stem_map--> B1 [9 ][ 4][2R][2C][8]  stem conv + pool, on the pooled-once grid
-//   B1 --conv_dense 5+20 cls--> Z [25][8][2R][2C][8]  (edge row classes exist on one row parity: row stride 2)
-//   Z  --pool_s2-----------> B2 [9 ][ 8][R][C][8]   aligned 2x2 max (the pooled-once grid moves 2 cells per pixel)
-//   B2 --conv_dense 25 cls--> Z --pool_s1--> CAT[9][16..31]
-//   CAT --conv_dense 1x1, 9 cls--> F [9][16][R][C][8]
+//   scene --ms_stem_map--> A  [9 ][ 8][R][C][8]        9 = {first, interior, last}^2 of the 3x3/pad-1 stem conv
+//   A  --conv_pool4 (stride-1 pool)--> CAT[9][0..15]     conv 64->128 + BN + ReLU + 2x2 max over (X..X+1, Y..Y+1), 9 pooled classes
+//   scene --pan_stem_map--> B1 [9 ][4 phases][4][R][C][8]  stem conv + pool on the pooled-once grid, stored phase-separated
+//   B1 --conv_pool4 (aligned pool)--> B2 [9][8][R][C][8]  conv 32->64 + aligned 2x2 max (the pooled-once grid moves 2 cells per pixel)
+//   B2 --conv_pool4 (stride-1 pool)--> CAT[9][16..31]
+//   CAT --conv_dense 1x1, 9 planes--> F [9][16][R][C][8]
 //   F  --head_dense--> per pixel: mean over the (p/2)^2 strided samples F[cls(k),cls(l)][x+2k][y+2l], 2 linears,
 //                      argmax, confusion matrix, label map
 // with R = (r1 - r0) + p - 1 rows and C = W + p - 1 columns.  Positions a band never needs hold don't-care values
@@ -31,10 +29,10 @@ namespace dmf {
 
 struct DenseWs {
     int W = 0, band = 0, p = 0, R1 = 0, C1 = 0;
-    __nv_bfloat16 *A = nullptr, *Z = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr, *F = nullptr;
+    __nv_bfloat16 *A = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr, *F = nullptr;
     float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
     __nv_bfloat16* w_pan2 = nullptr;                 // tap-major packing of pan2 (the per-patch path may use the row-pair one)
-    CUtensorMap mapA, mapB1, mapB2, mapCAT;
+    CUtensorMap mapA, mapB1, mapB2s, mapCAT;
     cudaEvent_t ev[12] = {};
     float stage_ms[12] = {};
     size_t bytes = 0;
@@ -164,42 +162,6 @@ __global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restri
     }
 }
 
-// ---------------------------------------------------------------------------------------------- pooling between maps
-__device__ __forceinline__ uint4 max4(uint4 a, uint4 b) {
-    return make_uint4(tc::max_bf16x2(a.x, b.x), tc::max_bf16x2(a.y, b.y), tc::max_bf16x2(a.z, b.z), tc::max_bf16x2(a.w, b.w));
-}
-// conv class of the two rows (columns) a pooled cell of border class a covers: first cell -> (0, 1), interior -> (2, 2), last -> (3, 4)
-__device__ __forceinline__ int pool_cls(int a, int s) { return a == 0 ? s : a == 1 ? 2 : 3 + s; }
-
-// ms2, pan3: out[(a,b)][ch][X][Y] = max_{s,t} Z[(pool_cls(a,s), pool_cls(b,t))][ch][X+s][Y+t], Z and out on the same grid (the
-// pooling windows of neighbouring anchors overlap: stride 1).  pan2's aligned pooling is fused into conv_pool4_kernel.
-__global__ void __launch_bounds__(256) pool_maps_kernel(const uint4* __restrict__ Z, int zch, int rows, int R1, int C1, uint4* __restrict__ out,
-                                                        int out_chunks, int out_chunk0) {
-    const int64_t per_plane = (int64_t)zch * rows * C1;
-    const int64_t total = 9 * per_plane;
-    const int ZR = R1, ZC = C1;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int Y = (int)(i % C1);
-        int64_t r = i / C1;
-        const int X = (int)(r % rows); r /= rows;
-        const int ch = (int)(r % zch);
-        const int ab = (int)(r / zch);
-        const int a = ab / 3, b = ab % 3;
-        uint4 m = make_uint4(0u, 0u, 0u, 0u);                      // post-ReLU values are >= 0
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int zr = X + s, zc = Y + t;
-                if (zr < ZR && zc < ZC) {
-                    const int cls = pool_cls(a, s) * 5 + pool_cls(b, t);
-                    m = max4(m, __ldg(Z + (((int64_t)cls * zch + ch) * ZR + zr) * ZC + zc));
-                }
-            }
-        out[(((int64_t)ab * out_chunks + out_chunk0 + ch) * R1 + X) * C1 + Y] = m;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------- head
 // One block = 32 consecutive pixels of one anchor row.  Phase 1: warp w = channel chunk w, lane = pixel: the global
 // average pool is a strided gather from the 9 F planes (512-byte coalesced warp loads, (p/2)^2 of them).  Phase 2:
@@ -320,50 +282,32 @@ __global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const uin
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int make_dense_map(CUtensorMap* m, const void* base, int planes, int kch, int rows, int cols, int box_cols, int box_rows) {
+static int make_dense_map(CUtensorMap* m, const void* base, int planes, int kch, int rows, int cols, int box_cols, int box_rows, int box_kch) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DMF_ERR_CUDA; }
     cuuint64_t dims[4] = {8ull * cols, (cuuint64_t)planes, (cuuint64_t)rows, (cuuint64_t)kch};
     cuuint64_t strides[3] = {(cuuint64_t)kch * rows * cols * 16, (cuuint64_t)cols * 16, (cuuint64_t)rows * cols * 16};
-    cuuint32_t box[4] = {(cuuint32_t)(8 * box_cols), 1, (cuuint32_t)box_rows, (cuuint32_t)kch}, es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(8 * box_cols), 1, (cuuint32_t)box_rows, (cuuint32_t)box_kch}, es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (dense map %dx%d, %d planes) failed: CUresult %d", rows, cols, planes, (int)r); return DMF_ERR_CUDA; }
     return DMF_OK;
 }
 
-// variant of the input row read by tap dy (0..2) of an output row of class c (0, 1, interior, S-2, S-1); -1 = outside the patch
-static const int kTapVariant[5][3] = {{-1, 0, 1}, {0, 1, 1}, {1, 1, 1}, {1, 1, 2}, {1, 2, -1}};
-
-static void build_cls(tc::DenseCls& c, int cr, int cc, int out_plane, int row0) {
-    memset(&c, 0, sizeof(c));
-    c.out_plane = (int16_t)out_plane;
-    c.row0 = (int16_t)row0;
-    for (int dy = 0; dy < 3; ++dy)
-        for (int dx = 0; dx < 3; ++dx) {
-            const int vr = kTapVariant[cr][dy], vc = kTapVariant[cc][dx];
-            if (vr < 0 || vc < 0) continue;
-            const int plane = vr * 3 + vc;
-            int s = 0;
-            while (s < c.n_steps && c.in_plane[s] != plane) ++s;
-            if (s == c.n_steps) { c.in_plane[s] = (int16_t)plane; c.mask[s] = 0; ++c.n_steps; }
-            c.mask[s] |= (uint16_t)(1u << (dy * 3 + dx));
-        }
-}
-
-// Pooled class (a, b) of the fused conv + aligned-pool layer (conv_pool4_kernel): per axis, input offset o = s + dy in
-// {-1, 0, 1, 2} from the cell origin has border variant kOffVariant[a][o + 1] (-1 = outside the patch), lives in phase
-// o & 1 and at cell shift floor(o / 2).  Sources = distinct (variant, phase) pairs of an axis; a box = row source x column
-// source, its origin the smallest shift any of its users needs (extent <= 17 x 9 cells).
+// Pooled class (a, b) of a fused conv + pool layer (conv_pool4_kernel): per axis, input offset o = s + dy in {-1, 0, 1, 2}
+// from the cell origin has border variant kOffVariant[a][o + 1] (-1 = outside the patch).  ALIGNED pooling (phase-separated
+// input): offset o lives in phase o & 1 at cell shift floor(o / 2); stride-1 pooling: phase 0, shift o.  Sources = distinct
+// (variant, phase) pairs of an axis; a box = row source x column source, its origin the smallest shift any user needs.
 static const int kOffVariant[3][4] = {{-1, 0, 1, 1}, {1, 1, 1, 1}, {1, 1, 2, -1}};
 struct AxisSrc { int variant, phase, origin; };
-static int axis_sources(int a, AxisSrc* src, int* src_of_off) {
+static int axis_sources(int a, bool aligned, AxisSrc* src, int* src_of_off, int* shift_of_off) {
     int n = 0;
     for (int o = -1; o <= 2; ++o) {
         src_of_off[o + 1] = -1;
         const int v = kOffVariant[a][o + 1];
         if (v < 0) continue;
-        const int ph = o & 1, sh = o < 0 ? -1 : o / 2;              // floor(o / 2): -1 -> -1, 0 -> 0, 1 -> 0, 2 -> 1
+        const int ph = aligned ? (o & 1) : 0, sh = aligned ? (o < 0 ? -1 : o / 2) : o;
+        shift_of_off[o + 1] = sh;
         int k = 0;
         while (k < n && !(src[k].variant == v && src[k].phase == ph)) ++k;
         if (k == n) { src[n].variant = v; src[n].phase = ph; src[n].origin = sh; ++n; }
@@ -372,31 +316,56 @@ static int axis_sources(int a, AxisSrc* src, int* src_of_off) {
     }
     return n;
 }
-static int build_pool4_cls(tc::Pool4Cls& c, int a, int b) {
+static int build_pool4_cls(tc::Pool4Cls& c, int a, int b, bool aligned, int box_rows, int box_cols, int max_boxes, uint32_t box_slot) {
     memset(&c, 0, sizeof(c));
     AxisSrc rs[4], cs[4];
-    int r_of[4], c_of[4];
-    const int nr = axis_sources(a, rs, r_of), nc = axis_sources(b, cs, c_of);
-    if (nr * nc > tc::kP4MaxBoxes) { set_error("pool4 class (%d,%d) needs %d boxes", a, b, nr * nc); return DMF_ERR_STATE; }
+    int r_of[4], c_of[4], r_sh[4], c_sh[4];
+    const int nr = axis_sources(a, aligned, rs, r_of, r_sh), nc = axis_sources(b, aligned, cs, c_of, c_sh);
+    if (nr * nc > max_boxes) { set_error("pool4 class (%d,%d) needs %d boxes", a, b, nr * nc); return DMF_ERR_STATE; }
     c.out_plane = (int16_t)(a * 3 + b);
     c.n_boxes = (int16_t)(nr * nc);
     for (int i = 0; i < nr; ++i)
         for (int j = 0; j < nc; ++j) {
             const int k = i * nc + j;
-            c.box_plane[k] = (int16_t)((rs[i].variant * 3 + cs[j].variant) * 4 + rs[i].phase * 2 + cs[j].phase);
+            const int variant = rs[i].variant * 3 + cs[j].variant;
+            c.box_plane[k] = (int16_t)(aligned ? variant * 4 + rs[i].phase * 2 + cs[j].phase : variant);
             c.box_drow[k] = (int8_t)rs[i].origin;
             c.box_dcol[k] = (int8_t)cs[j].origin;
         }
-    auto floor2 = [](int o) { return o < 0 ? -1 : o / 2; };
     for (int tap = 0; tap < 9; ++tap)
         for (int sub = 0; sub < 4; ++sub) {
             const int orow = (sub >> 1) + tap / 3 - 1, ocol = (sub & 1) + tap % 3 - 1;
             const int i = r_of[orow + 1], j = c_of[ocol + 1];
             if (i < 0 || j < 0) { c.off[tap * 4 + sub] = -1; continue; }
-            const int dr = floor2(orow) - rs[i].origin, dc = floor2(ocol) - cs[j].origin;
-            if (dr < 0 || dr + 16 > tc::kP4BoxRows || dc < 0 || dc + 8 > tc::kP4BoxCols) { set_error("pool4 class (%d,%d): window outside its box", a, b); return DMF_ERR_STATE; }
-            c.off[tap * 4 + sub] = (int16_t)(((uint32_t)(i * nc + j) * tc::kP4BoxSlot + (uint32_t)(dr * tc::kP4BoxCols + dc) * 16) >> 4);
+            const int dr = r_sh[orow + 1] - rs[i].origin, dc = c_sh[ocol + 1] - cs[j].origin;
+            if (dr < 0 || dr + 16 > box_rows || dc < 0 || dc + 8 > box_cols) { set_error("pool4 class (%d,%d): window outside its box", a, b); return DMF_ERR_STATE; }
+            c.off[tap * 4 + sub] = (int16_t)(((uint32_t)(i * nc + j) * box_slot + (uint32_t)(dr * box_cols + dc) * 16) >> 4);
         }
+    return DMF_OK;
+}
+
+// conv + pool of one layer over the band: in = 9 (x 4 phases) planes, out = 9 pooled planes
+template <int CI, int CO, int KQ, int STAGES, int BR, int BC, int NBUF>
+static int launch_pool4(const CUtensorMap& map, bool aligned, const __nv_bfloat16* w, const float* scale, const float* shift, __nv_bfloat16* out,
+                        int out_chunks, int out_chunk0, int rows, int R1, int C1, cudaStream_t st) {
+    using Cfg = tc::Pool4Cfg<CI, CO, KQ, STAGES, BR, BC, NBUF>;
+    static_assert(Cfg::SMEM <= (size_t)kSmemLimit, "conv_pool4_kernel does not fit in shared memory");
+    tc::Pool4Params P{};
+    P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_tiles = P.tiles_x * P.tiles_y * 9;
+    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0;
+    P.w = w; P.scale = scale; P.shift = shift; P.out = out;
+    static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
+    P.dbg = dbg;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) DMF_TRY(build_pool4_cls(P.cls[a * 3 + b], a, b, aligned, BR, BC, Cfg::MAX_BOXES, Cfg::BOX_SLOT));
+    auto kern = tc::conv_pool4_kernel<CI, CO, KQ, STAGES, BR, BC, NBUF>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr_set = true;
+    }
+    kern<<<std::min(P.n_tiles, num_sms()), 320, Cfg::SMEM, st>>>(map, P);
+    DMF_LAUNCHED();
     return DMF_OK;
 }
 
@@ -442,9 +411,9 @@ int dense_pack(dmf_net* n) {
 }
 
 static void dense_free_ws(DenseWs* d) {
-    __nv_bfloat16* bs[] = {d->A, d->Z, d->CAT, d->B1, d->B2, d->F};
+    __nv_bfloat16* bs[] = {d->A, d->CAT, d->B1, d->B2, d->F};
     for (auto* b : bs) cudaFree(b);
-    d->A = d->Z = d->CAT = d->B1 = d->B2 = d->F = nullptr;
+    d->A = d->CAT = d->B1 = d->B2 = d->F = nullptr;
     d->W = d->band = 0;
     d->bytes = 0;
 }
@@ -467,27 +436,25 @@ static int dense_prepare(dmf_net* n, int W, int band) {
     dense_free_ws(d);
     const int p = n->p;
     const size_t R1 = band + p - 1, C1 = W + p - 1, px = R1 * C1;
-    const size_t sA = px * 9 * C_MS1 * 2, sZ = px * 25 * C_MS2 * 2, sCAT = px * 9 * C_CAT * 2, sB1 = px * 4 * 9 * C_PAN1 * 2,
+    const size_t sA = px * 9 * C_MS1 * 2, sCAT = px * 9 * C_CAT * 2, sB1 = px * 4 * 9 * C_PAN1 * 2,
                  sB2 = px * 9 * C_PAN2 * 2, sF = px * 9 * C_FUSE * 2;
     DMF_CUDA(cudaMalloc(&d->A, sA));
-    DMF_CUDA(cudaMalloc(&d->Z, sZ));
     DMF_CUDA(cudaMalloc(&d->CAT, sCAT));
     DMF_CUDA(cudaMalloc(&d->B1, sB1));
     DMF_CUDA(cudaMalloc(&d->B2, sB2));
     DMF_CUDA(cudaMalloc(&d->F, sF));
-    d->bytes = sA + sZ + sCAT + sB1 + sB2 + sF;
+    d->bytes = sA + sCAT + sB1 + sB2 + sF;
     // positions a band never writes are only ever read into don't-care outputs; zero them once so that runs are reproducible
     DMF_CUDA(cudaMemset(d->A, 0, sA));
-    DMF_CUDA(cudaMemset(d->Z, 0, sZ));
     DMF_CUDA(cudaMemset(d->CAT, 0, sCAT));
     DMF_CUDA(cudaMemset(d->B1, 0, sB1));
     DMF_CUDA(cudaMemset(d->B2, 0, sB2));
     DMF_CUDA(cudaMemset(d->F, 0, sF));
     d->W = W; d->band = band; d->p = p; d->R1 = (int)R1; d->C1 = (int)C1;
-    DMF_TRY(make_dense_map(&d->mapA, d->A, 9, C_MS1 / 8, (int)R1, (int)C1, tc::kPitch, 18));
-    DMF_TRY(make_dense_map(&d->mapB1, d->B1, 36, C_PAN1 / 8, (int)R1, (int)C1, tc::kP4BoxCols, tc::kP4BoxRows));
-    DMF_TRY(make_dense_map(&d->mapB2, d->B2, 9, C_PAN2 / 8, (int)R1, (int)C1, tc::kPitch, 18));
-    DMF_TRY(make_dense_map(&d->mapCAT, d->CAT, 9, C_CAT / 8, (int)R1, (int)C1, 32, 4));
+    DMF_TRY(make_dense_map(&d->mapA, d->A, 9, C_MS1 / 8, (int)R1, (int)C1, 11, 19, 2));
+    DMF_TRY(make_dense_map(&d->mapB1, d->B1, 36, C_PAN1 / 8, (int)R1, (int)C1, 9, 17, C_PAN1 / 8));
+    DMF_TRY(make_dense_map(&d->mapB2s, d->B2, 9, C_PAN2 / 8, (int)R1, (int)C1, 11, 19, 2));
+    DMF_TRY(make_dense_map(&d->mapCAT, d->CAT, 9, C_CAT / 8, (int)R1, (int)C1, 32, 4, C_CAT / 8));
     for (auto& e : d->ev) if (!e) DMF_CUDA(cudaEventCreate(&e));
     DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     return DMF_OK;
@@ -518,63 +485,19 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, b0, rows, R1, C1, d->w_ms1, n->L[4].scale, n->L[4].shift, d->A);
         DMF_LAUNCHED();
         mark();
-        {
-            tc::DenseParams P{};
-            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_cls = 25;
-            P.out_chunks = C_MS2 / 8; P.out_chunk0 = 0;
-            P.w = n->L[0].w; P.scale = n->L[0].scale; P.shift = n->L[0].shift; P.out = d->Z;
-            for (int cr = 0; cr < 5; ++cr)
-                for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[cr * 5 + cc], cr, cc, cr * 5 + cc, 0);
-            static const bool g3 = getenv("DMF_DENSE_G3") != nullptr;      // experiment: 3 epilogue groups (more registers per thread)
-            if (g3) DMF_TRY((launch_dense<C_MS1, C_MS2, 9, 1, 3>(d->mapA, P, st)));
-            else DMF_TRY((launch_dense<C_MS1, C_MS2, 9, 1, 4>(d->mapA, P, st)));
-        }
+        DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1>(d->mapA, false, n->L[0].w, n->L[0].scale, n->L[0].shift, d->CAT, C_CAT / 8, 0, rows, R1, C1, st)));
         mark();
-        pool_maps_kernel<<<grid_for((int64_t)9 * (C_MS2 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
-            reinterpret_cast<const uint4*>(d->Z), C_MS2 / 8, rows, R1, C1, reinterpret_cast<uint4*>(d->CAT), C_CAT / 8, 0);
-        DMF_LAUNCHED();
-        mark();
+        mark();          // (stage slot of the former separate pooling pass)
         // ---- PAN branch
         pan_stem_map_kernel<<<dim3(grid_for((int64_t)2 * rows * C2, 256, 8), C_PAN1 / 8), 256, 0, st>>>(
             s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
-        {
-            tc::Pool4Params P{};
-            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_tiles = P.tiles_x * P.tiles_y * 9;
-            P.out_chunks = C_PAN2 / 8;
-            P.w = d->w_pan2; P.scale = n->L[1].scale; P.shift = n->L[1].shift; P.out = d->B2;
-            static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;
-            P.dbg = dbg;
-            for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < 3; ++b) DMF_TRY(build_pool4_cls(P.cls[a * 3 + b], a, b));
-            constexpr size_t smem = 9 * C_PAN1 * C_PAN2 * 2 + (size_t)tc::kP4Stages * tc::kP4Stage + 2 * C_PAN2 * 4 + 12 * 8 + 9 * sizeof(tc::Pool4Cls);
-            static_assert(smem <= (size_t)kSmemLimit, "conv_pool4_kernel does not fit in shared memory");
-            static bool attr_set = false;
-            if (!attr_set) {
-                DMF_CUDA(cudaFuncSetAttribute(tc::conv_pool4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-                attr_set = true;
-            }
-            tc::conv_pool4_kernel<<<std::min(P.n_tiles, num_sms()), 320, smem, st>>>(d->mapB1, P);
-            DMF_LAUNCHED();
-        }
+        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2>(d->mapB1, true, d->w_pan2, n->L[1].scale, n->L[1].shift, d->B2, C_PAN2 / 8, 0, rows, R1, C1, st)));
         mark();
-        mark();          // (stage slot of the former separate pan2 pooling pass)
-        {
-            tc::DenseParams P{};
-            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_cls = 25;
-            P.out_chunks = C_PAN3 / 8; P.out_chunk0 = 0;
-            P.w = n->L[2].w; P.scale = n->L[2].scale; P.shift = n->L[2].shift; P.out = d->Z;
-            for (int cr = 0; cr < 5; ++cr)
-                for (int cc = 0; cc < 5; ++cc) build_cls(P.cls[cr * 5 + cc], cr, cc, cr * 5 + cc, 0);
-            static const bool g3 = getenv("DMF_DENSE_G3") != nullptr;
-            if (g3) DMF_TRY((launch_dense<C_PAN2, C_PAN3, 9, 1, 3>(d->mapB2, P, st)));
-            else DMF_TRY((launch_dense<C_PAN2, C_PAN3, 9, 1, 4>(d->mapB2, P, st)));
-        }
         mark();
-        pool_maps_kernel<<<grid_for((int64_t)9 * (C_PAN3 / 8) * rows * C1, 256, 8), 256, 0, st>>>(
-            reinterpret_cast<const uint4*>(d->Z), C_PAN3 / 8, rows, R1, C1, reinterpret_cast<uint4*>(d->CAT), C_CAT / 8, C_MS2 / 8);
-        DMF_LAUNCHED();
+        DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1>(d->mapB2s, false, n->L[2].w, n->L[2].scale, n->L[2].shift, d->CAT, C_CAT / 8, C_MS2 / 8, rows, R1, C1, st)));
+        mark();
         mark();
         // ---- fusion conv (1x1) on the 9 pooled planes
         {
@@ -646,7 +569,7 @@ int dmf_net_get_dense_timing(dmf_net* n, float out_ms[12], int reset) {
     return DMF_OK;
 }
 
-/* test hook: device pointer + byte size of a dense-path map ("A", "Z", "CAT", "B1", "B2", "F"); dims[0..1] = R, C of the MS-resolution grid */
+/* test hook: device pointer + byte size of a dense-path map ("A", "CAT", "B1", "B2", "F"); dims[0..1] = R, C of the MS-resolution grid */
 int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* bytes_out, int32_t dims[2]) {
     DMF_REQUIRE(n && name && ptr_out && bytes_out && dims, "net_dense_buffer: null");
     DMF_REQUIRE(n->dense && n->dense->A, "net_dense_buffer: the dense path has not run yet");
@@ -654,7 +577,6 @@ int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* 
     const size_t px = (size_t)d->R1 * d->C1;
     const std::string k(name);
     if (k == "A") { *ptr_out = d->A; *bytes_out = px * 9 * C_MS1 * 2; }
-    else if (k == "Z") { *ptr_out = d->Z; *bytes_out = px * 25 * C_MS2 * 2; }
     else if (k == "CAT") { *ptr_out = d->CAT; *bytes_out = px * 9 * C_CAT * 2; }
     else if (k == "B1") { *ptr_out = d->B1; *bytes_out = px * 4 * 9 * C_PAN1 * 2; }
     else if (k == "B2") { *ptr_out = d->B2; *bytes_out = px * 9 * C_PAN2 * 2; }

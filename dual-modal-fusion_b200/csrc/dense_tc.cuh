@@ -246,36 +246,36 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
 
 
 // ------------------------------------------------------------------------------------------------
-// Fused conv3x3 + aligned 2x2 max-pool for the layer that sits on the pooled-once PAN grid (pan2, 32 -> 64).
+// Fused conv3x3 + 2x2 max-pool: the pooled maps are the only thing written.
 //
-// The pooled output cell (X, Y) of border class (a, b) is the max of the 4 conv outputs at grid positions
-// (2X + s, 2Y + t); conv output (s, t) reads inputs at (2X + s + dy, 2Y + t + dx), i.e. at offsets o = s + dy,
-// t + dx in {-1, 0, 1, 2} from the cell origin, and the border variant of an input depends on its offset only.
-// The input maps are stored PHASE-SEPARATED ([variant][row phase, col phase][chunk][R][C][8]): offset o lives in
-// phase o & 1 at cell shift floor(o / 2), so every (sub-position, tap) pair is a unit-stride 16 x 8 window of some
-// (variant, phase) plane.  One pipeline step = one pooled tile of 16 x 8 cells: <= 9 TMA boxes of 17 x 9 cells (one per
-// (row source) x (column source)), 4 accumulators of N = 64 in TMEM (one per sub-position, 2 tiles in flight), up to
-// 72 MMAs issued tap-major so that consecutive MMAs hit different accumulators, and an epilogue that applies BN +
-// ReLU to the 4 accumulators and keeps the thread-local maximum: the pooled map is the only thing written.
-constexpr int kP4BoxRows = 17, kP4BoxCols = 9, kP4MaxBoxes = 9;
-constexpr uint32_t kP4Plane = kP4BoxRows * kP4BoxCols * 16;              // bytes of one channel-chunk plane of a box
-constexpr int kP4Cin = 32, kP4Cout = 64;
-constexpr uint32_t kP4BoxBytes = (kP4Cin / 8) * kP4Plane;                // 9792
-constexpr uint32_t kP4BoxSlot = (kP4BoxBytes + 127) / 128 * 128;         // 9856: TMA destinations are 128-byte aligned
-constexpr uint32_t kP4Stage = kP4MaxBoxes * kP4BoxSlot;
-constexpr int kP4Stages = 2;
+// The pooled output cell (X, Y) of border class (a, b) is the max of 4 conv outputs ("sub-positions" (s, t)); conv output
+// (s, t) reads inputs at offsets o = s + dy, t + dx in {-1, 0, 1, 2} from the cell origin, and the border variant of an
+// input depends on its offset only (first cell: {outside, first, interior, interior}; interior: all interior; last cell:
+// {interior, interior, last, outside}).
+//   * ALIGNED pooling (pan2, on the pooled-once PAN grid, which moves 2 cells per pixel): the input maps are stored
+//     PHASE-SEPARATED ([variant][row phase, col phase][chunk][R][C][8]); offset o lives in phase o & 1 at cell shift
+//     floor(o / 2), so every (sub-position, tap) pair is a unit-stride 16 x 8 window of some (variant, phase) plane.
+//   * STRIDE-1 pooling (ms2, pan3: the pooling windows of neighbouring anchors overlap): offset o is simply cell shift o.
+// A "source" of an axis = a distinct (variant, phase); a TMA box = (row source) x (column source), BR x BC cells, placed at
+// the smallest shift any of its users needs.  One pooled tile = 16 x 8 cells = 4 accumulators of N = C_OUT in TMEM and
+// (C_IN / 8) / KQ pipeline steps of KQ channel chunks (all boxes of a step land on one mbarrier); MMAs are issued
+// tap-major so that consecutive instructions hit different accumulators (no accumulate read-after-write stall).
+// NBUF = 2 (4 x C_OUT <= 256 columns): two tiles in flight, two epilogue groups of 4 warps.  NBUF = 1 (C_OUT = 128: the
+// 4 accumulators fill TMEM): 8 epilogue warps split the channels, the next tile's MMAs wait for them.
+// Epilogue: BN affine + ReLU on the 4 accumulators, thread-local maximum, 16-byte stores in the C8-planar layout.
+constexpr int kP4MaxBoxes = 9;
 
 struct Pool4Cls {
     int16_t out_plane, n_boxes;
     int16_t box_plane[kP4MaxBoxes];
     int8_t box_drow[kP4MaxBoxes], box_dcol[kP4MaxBoxes];
-    int16_t off[36];                      // [tap][sub]: (byte offset of the A window inside the stage) >> 4, or -1
+    int16_t off[36];                      // [tap][sub]: (byte offset of the A window inside a stage) >> 4, or -1
 };
 
 struct Pool4Params {
-    int rows, cols;                       // pooled grid = grid of every phase plane
+    int rows, cols;                       // grid of the pooled output = grid of every input plane
     int tiles_x, tiles_y, n_tiles;
-    int out_chunks;
+    int out_chunks, out_chunk0;
     int dbg;
     const __nv_bfloat16* w;               // packed [tap][C_in/8][C_out][8]
     const float* scale;
@@ -284,29 +284,43 @@ struct Pool4Params {
     Pool4Cls cls[9];
 };
 
+template <int C_IN, int C_OUT, int KQ, int STAGES, int BR, int BC, int NBUF>
+struct Pool4Cfg {
+    static constexpr int KCH = C_IN / 8, NSTEP = KCH / KQ;
+    static constexpr uint32_t PLANE = BR * BC * 16;                          // bytes of one channel-chunk plane of a box
+    static constexpr uint32_t BOX_BYTES = KQ * PLANE;
+    static constexpr uint32_t BOX_SLOT = (BOX_BYTES + 127) / 128 * 128;      // TMA destinations are 128-byte aligned
+    static constexpr int MAX_BOXES = BC == 9 ? 9 : 4;                        // aligned: 3 x 3 sources, stride-1: 2 x 2
+    static constexpr uint32_t STAGE = MAX_BOXES * BOX_SLOT;
+    static constexpr uint32_t WBYTES = 9u * C_IN * C_OUT * 2;
+    static constexpr size_t SMEM = WBYTES + (size_t)STAGES * STAGE + 2 * C_OUT * 4 + (2 * STAGES + 8) * 8 + 9 * sizeof(Pool4Cls);
+    static_assert(KCH % KQ == 0 && KQ % 2 == 0 && NBUF * 4 * C_OUT <= 512 && WBYTES % 128 == 0, "pool4 configuration");
+};
+
+template <int C_IN, int C_OUT, int KQ, int STAGES, int BR, int BC, int NBUF>
 __global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ Pool4Params P) {
-    constexpr int kThreads = 320, G = 2;
-    constexpr int C_IN = kP4Cin, C_OUT = kP4Cout, KCH = C_IN / 8;
-    constexpr uint32_t WBYTES = 9u * C_IN * C_OUT * 2;
-    constexpr uint32_t SBO_A = kP4BoxCols * 16;
+    using Cfg = Pool4Cfg<C_IN, C_OUT, KQ, STAGES, BR, BC, NBUF>;
+    constexpr int kThreads = 320;
+    constexpr int KCH = Cfg::KCH, NSTEP = Cfg::NSTEP;
+    constexpr uint32_t WBYTES = Cfg::WBYTES, SBO_A = BC * 16;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
-    uint8_t* a_s = smem + WBYTES;                                              // WBYTES = 36864 is a multiple of 128
-    float* scale_s = reinterpret_cast<float*>(a_s + (size_t)kP4Stages * kP4Stage);
+    uint8_t* a_s = smem + WBYTES;
+    float* scale_s = reinterpret_cast<float*>(a_s + (size_t)STAGES * Cfg::STAGE);
     float* shift_s = scale_s + C_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
-    // bars: 0,1 full; 2,3 empty; 4 weights; 5,6 tmem_full; 7,8 tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    Pool4Cls* cls_s = reinterpret_cast<Pool4Cls*>(bars + 12);
+    // bars: [0,S) full; [S,2S) empty; 2S weights; 2S+1.. tmem_full[NBUF]; 2S+3.. tmem_empty[NBUF]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    Pool4Cls* cls_s = reinterpret_cast<Pool4Cls*>(bars + 2 * STAGES + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
-    const uint32_t w_bar = bar0 + 8u * 4;
-    auto tfull_bar = [&](int a) { return bar0 + 8u * (5 + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (7 + a); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    const uint32_t w_bar = bar0 + 8u * (2 * STAGES);
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 1 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 3 + a); };
 
     for (int i = threadIdx.x; i < C_OUT; i += kThreads) {
         scale_s[i] = P.scale[i];
@@ -315,9 +329,9 @@ __global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constan
     for (int i = threadIdx.x; i < 9 * (int)(sizeof(Pool4Cls) / 4); i += kThreads)
         reinterpret_cast<uint32_t*>(cls_s)[i] = reinterpret_cast<const uint32_t*>(P.cls)[i];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kP4Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
-        for (int a = 0; a < G; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < NBUF; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NBUF == 2 ? 4 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -341,7 +355,7 @@ __global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constan
     };
 
     if (warp == 0) {
-        // ------------------------------------------------ TMA producer: all boxes of a tile land on one barrier
+        // ------------------------------------------------ TMA producer: all boxes of a step land on one barrier
         const bool leader = elect_one();
         if (leader) {
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
@@ -351,22 +365,26 @@ __global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constan
                 bulk_load(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(P.w) + off, min(CH, WBYTES - off), w_bar);
         }
         __syncwarp();
+        int st = 0;
+        uint32_t ph = 1;
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            const int st = i & 1;
-            mbar_wait(empty_bar(st), ((i >> 1) & 1) ^ 1);
-            if (leader) {
-                const int nbx = cls_s[c].n_boxes;
-                if (P.dbg & 1) {
-                    mbar_arrive(full_bar(st));
-                } else {
-                    mbar_expect_tx(full_bar(st), (uint32_t)nbx * kP4BoxBytes);
-                    const uint32_t dst = smem_u32(a_s) + (uint32_t)st * kP4Stage;
-                    for (int b = 0; b < nbx; ++b)
-                        tma_load_4d(dst + (uint32_t)b * kP4BoxSlot, &in_map, full_bar(st), (tx * 8 + cls_s[c].box_dcol[b]) * 8,
-                                    cls_s[c].box_plane[b], ty * 16 + cls_s[c].box_drow[b], 0);
+            const int nbx = cls_s[c].n_boxes;
+            for (int kq = 0; kq < NSTEP; ++kq) {
+                mbar_wait(empty_bar(st), ph);
+                if (leader) {
+                    if (P.dbg & 1) {
+                        mbar_arrive(full_bar(st));
+                    } else {
+                        mbar_expect_tx(full_bar(st), (uint32_t)nbx * Cfg::BOX_BYTES);
+                        const uint32_t dst = smem_u32(a_s) + (uint32_t)st * Cfg::STAGE;
+                        for (int b = 0; b < nbx; ++b)
+                            tma_load_4d(dst + (uint32_t)b * Cfg::BOX_SLOT, &in_map, full_bar(st), (tx * 8 + cls_s[c].box_dcol[b]) * 8,
+                                        cls_s[c].box_plane[b], ty * 16 + cls_s[c].box_drow[b], kq * KQ);
+                    }
                 }
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1; }
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
@@ -374,53 +392,64 @@ __global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constan
         const bool leader = elect_one();
         mbar_wait(w_bar, 0);
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
+        int st = 0;
+        uint32_t ph = 0;
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            const int st = i & 1, buf = i & 1;
-            mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);
-            mbar_wait(full_bar(st), (i >> 1) & 1);
-            tc_fence_after();
-            const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * kP4Stage, kP4Plane, SBO_A);
+            const int buf = NBUF == 2 ? (i & 1) : 0;
+            const int use = NBUF == 2 ? (i >> 1) : i;
+            mbar_wait(tempty_bar(buf), (use & 1) ^ 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 4 * C_OUT);
-            if (leader) {
-                const int16_t* off = cls_s[c].off;
-                uint32_t started = 0;
+            const int16_t* off = cls_s[c].off;
+            uint32_t started = 0;
+            for (int kq = 0; kq < NSTEP; ++kq) {
+                mbar_wait(full_bar(st), ph);
+                tc_fence_after();
+                const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * Cfg::STAGE, Cfg::PLANE, SBO_A);
+                if (leader) {
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) {
-                        const int o = off[tap * 4 + sub];
-                        if (o >= 0) {
+                        for (int sub = 0; sub < 4; ++sub) {
+                            const int o = off[tap * 4 + sub];
+                            if (o >= 0) {
 #pragma unroll
-                            for (int j = 0; j < KCH / 2; ++j) {
-                                const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)o + (uint64_t)(((uint32_t)(2 * j) * kP4Plane) >> 4);
-                                const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((tap * KCH + 2 * j) * C_OUT * 16) >> 4);
-                                umma_bf16(d_tmem + (uint32_t)(sub * C_OUT), ad, bd, idesc, ((started >> sub) & 1u) | (uint32_t)j);
+                                for (int j = 0; j < KQ / 2; ++j) {
+                                    const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)o + (uint64_t)(((uint32_t)(2 * j) * Cfg::PLANE) >> 4);
+                                    const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((tap * KCH + kq * KQ + 2 * j) * C_OUT * 16) >> 4);
+                                    umma_bf16(d_tmem + (uint32_t)(sub * C_OUT), ad, bd, idesc, ((started >> sub) & 1u) | (uint32_t)j);
+                                }
+                                started |= 1u << sub;
                             }
-                            started |= 1u << sub;
                         }
                     }
+                    umma_commit(empty_bar(st));
+                    if (kq == NSTEP - 1) umma_commit(tfull_bar(buf));
                 }
-                umma_commit(empty_bar(st));
-                umma_commit(tfull_bar(buf));
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1; }
             }
-            __syncwarp();
         }
     } else {
         // ------------------------------------------------ epilogue: BN + ReLU on the 4 sub-position accumulators, thread-local max
-        const int eg = (warp - 2) >> 2;
+        const int eg = (warp - 2) >> 2;                    // NBUF = 2: tile parity this group drains; NBUF = 1: channel half
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * 4 * C_OUT);
+        constexpr int C_SPAN = NBUF == 2 ? C_OUT : C_OUT / 2;
+        const int c_lo = NBUF == 2 ? 0 : eg * C_SPAN;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(NBUF == 2 ? eg * 4 * C_OUT : 0);
         const int64_t cstride = (int64_t)P.rows * P.cols * 8;
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            if ((i & 1) != eg) continue;
+            if (NBUF == 2 && (i & 1) != eg) continue;
+            const int buf = NBUF == 2 ? eg : 0;
+            const int use = NBUF == 2 ? (i >> 1) : i;
             const int row = ty * 16 + (m >> 3), col = tx * 8 + (m & 7);
             const bool valid = row < P.rows && col < P.cols;
-            __nv_bfloat16* const obase = P.out + (((int64_t)cls_s[c].out_plane * P.out_chunks * P.rows + row) * P.cols + col) * 8;
-            mbar_wait(tfull_bar(eg), (i >> 1) & 1);
+            __nv_bfloat16* const obase =
+                P.out + ((((int64_t)cls_s[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
+            mbar_wait(tfull_bar(buf), use & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < ((P.dbg & 2) ? 0 : C_OUT); c0 += 32) {
+            for (int c0 = c_lo; c0 < ((P.dbg & 2) ? 0 : c_lo + C_SPAN); c0 += 32) {
                 uint32_t pk[16];
                 const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
                 const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
@@ -449,7 +478,7 @@ __global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(eg));
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
     }
 
