@@ -30,6 +30,7 @@ namespace dmf {
 struct DenseWs {
     int W = 0, band = 0, p = 0, R1 = 0, C1 = 0;
     __nv_bfloat16 *A = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr, *F = nullptr;
+    float* S = nullptr;                              // row sums of F for the separable average pool [3][16][R][W][8]
     float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
     __nv_bfloat16* w_pan2 = nullptr;                 // tap-major packing of pan2 (the per-patch path may use the row-pair one)
     CUtensorMap mapA, mapB1, mapB2s, mapCAT;
@@ -163,17 +164,61 @@ __global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------- head
-// One block = 32 consecutive pixels of one anchor row.  Phase 1: warp w = channel chunk w, lane = pixel: the global
-// average pool is a strided gather from the 9 F planes (512-byte coalesced warp loads, (p/2)^2 of them).  Phase 2:
-// warp per pixel, the two linears from shared-memory weights, first-maximum argmax, confusion matrix (per-block
-// shared histogram -> 64-bit global atomics), label map.
-constexpr int kDenseHeadThreads = 512;
+// The global average pool of pixel (x, y) is a strided gather from the 9 F planes,
+//     g = 1/(p/2)^2 * sum_{k,l} F[cls(k), cls(l)][x + 2k][y + 2l],      cls = first / interior / last cell,
+// evaluated separably: gap_rows_kernel forms the inner sums S[a][X][y] = sum_l F[a, cls(l)][X][y + 2l] once per map row
+// and row class a (fp32, [3][16][rows][W][8]); head_dense_kernel adds the p/2 rows S[cls(k)][x + 2k][y] of a pixel and
+// runs the two linears, the first-maximum argmax, the confusion matrix (per-block shared histogram -> 64-bit global
+// atomics) and the label map.  Summation order: l ascending inside a row, then k ascending.
+template <int P2>
+__global__ void __launch_bounds__(256) gap_rows_kernel(const uint4* __restrict__ F, int R1, int C1, int rows, int W, float4* __restrict__ S) {
+    const int64_t total = (int64_t)3 * 16 * rows * W;
+    const int64_t bstride = (int64_t)16 * R1 * C1;                // next column class
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i % W);
+        int64_t r = i / W;
+        const int X = (int)(r % rows); r /= rows;
+        const int ch = (int)(r % 16);
+        const int a = (int)(r / 16);
+        const uint4* rowp = F + (((int64_t)(a * 3) * 16 + ch) * R1 + X) * C1 + y;
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int l0 = 0; l0 < P2; l0 += 8) {
+            uint4 v[8];                                            // 8 independent 16-byte loads in flight
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int l = l0 + e;
+                if (l < P2) v[e] = __ldg(rowp + (l == 0 ? 0 : (l == P2 - 1 ? 2 : 1)) * bstride + 2 * l);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (l0 + e < P2) {
+                    const uint32_t u[4] = {v[e].x, v[e].y, v[e].z, v[e].w};
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        s[2 * h] += __uint_as_float(u[h] << 16);             // bf16 -> fp32 is a shift
+                        s[2 * h + 1] += __uint_as_float(u[h] & 0xFFFF0000u);
+                    }
+                }
+            }
+        }
+        float4* o = S + ((((int64_t)a * 16 + ch) * rows + X) * W + y) * 2;
+        o[0] = make_float4(s[0], s[1], s[2], s[3]);
+        o[1] = make_float4(s[4], s[5], s[6], s[7]);
+    }
+}
+
+// One block = 64 consecutive pixels of one anchor row.  Phase 1: warp w = channel chunk w, lane = pixel (two passes of 32
+// pixels): the p/2 row sums are added.  Phase 2: warp w owns pixels 4w..4w+3: both linears with the weights in shared
+// memory, each weight load shared by the 4 pixels (11 instructions per 8 FMAs).
+constexpr int kDenseHeadThreads = 512, kHeadPx = 64;
 static size_t dense_head_smem(int C) {
-    return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + C_FUSE * 32 + (kDenseHeadThreads / 32) * C_HID) +
+    return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + C_FUSE * kHeadPx + (kDenseHeadThreads / 32) * C_HID * 4) +
            sizeof(unsigned int) * C * C;
 }
 
-__global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const uint4* __restrict__ F, int R1, int C1, int p, int nb, int W, int C,
+template <int P2>
+__global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const float4* __restrict__ S, int rows, int nb, int W, int C,
                                                                        const float* __restrict__ fc1t, const float* __restrict__ fc1b,
                                                                        const float* __restrict__ fc2t, const float* __restrict__ fc2b,
                                                                        int64_t pix0 /* flat index of the band's first pixel */,
@@ -184,9 +229,9 @@ __global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const uin
     float* w2 = w1 + C_FUSE * C_HID;                  // [64][C]
     float* b1 = w2 + C_HID * C;
     float* b2 = b1 + C_HID;
-    float* gbuf = b2 + ((C + 3) & ~3);                // [128 channels][32 pixels]
-    float* hidb = gbuf + C_FUSE * 32;                 // per warp [64]
-    unsigned int* hist = reinterpret_cast<unsigned int*>(hidb + (kDenseHeadThreads / 32) * C_HID);
+    float* gbuf = b2 + ((C + 3) & ~3);                // [128 channels][64 pixels]
+    float* hidb = gbuf + C_FUSE * kHeadPx;            // per warp [64 hidden][4 pixels]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(hidb + (kDenseHeadThreads / 32) * C_HID * 4);
     for (int i = threadIdx.x; i < C_FUSE * C_HID; i += blockDim.x) w1[i] = fc1t[i];
     for (int i = threadIdx.x; i < C_HID * C; i += blockDim.x) w2[i] = fc2t[i];
     if (threadIdx.x < C_HID) b1[threadIdx.x] = fc1b[threadIdx.x];
@@ -194,85 +239,111 @@ __global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const uin
     for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int P2 = p >> 1;
     const float inv = 1.0f / (float)(P2 * P2);
-    const int segs = (W + 31) >> 5;
+    const int segs = (W + kHeadPx - 1) / kHeadPx;
     const int n_seg = nb * segs;
-    float* hid = hidb + warp * C_HID;
+    float* hid = hidb + warp * C_HID * 4;
     for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
-        const int xl = seg / segs, y0 = (seg - xl * segs) << 5;
-        {
-            const int y = y0 + lane;
+        const int xl = seg / segs, y0 = (seg - xl * segs) * kHeadPx;
+        // ---- phase 1: column sums of the row sums
+#pragma unroll
+        for (int half = 0; half < kHeadPx / 32; ++half) {
+            const int px = half * 32 + lane, y = y0 + px;
             float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (y < W) {
-                for (int k = 0; k < P2; ++k) {
-                    const int a = k == 0 ? 0 : (k == P2 - 1 ? 2 : 1);
-                    for (int l = 0; l < P2; ++l) {
-                        const int b = l == 0 ? 0 : (l == P2 - 1 ? 2 : 1);
-                        const uint4 v = __ldg(F + ((((int64_t)(a * 3 + b) * 16 + warp) * R1 + xl + 2 * k) * C1 + y + 2 * l));
-                        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
-                            s[2 * e] += f.x;
-                            s[2 * e + 1] += f.y;
-                        }
+                for (int k0 = 0; k0 < P2; k0 += 4) {
+                    float4 v[4][2];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = k0 + e, a = k == 0 ? 0 : (k == P2 - 1 ? 2 : 1);
+                        const float4* q = S + ((((int64_t)a * 16 + warp) * rows + xl + 2 * k) * W + y) * 2;
+                        v[e][0] = __ldg(q);
+                        v[e][1] = __ldg(q + 1);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s[0] += v[e][0].x; s[1] += v[e][0].y; s[2] += v[e][0].z; s[3] += v[e][0].w;
+                        s[4] += v[e][1].x; s[5] += v[e][1].y; s[6] += v[e][1].z; s[7] += v[e][1].w;
                     }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gbuf[(warp * 8 + j) * 32 + lane] = s[j] * inv;
+            for (int j = 0; j < 8; ++j) gbuf[(warp * 8 + j) * kHeadPx + px] = s[j] * inv;
         }
         __syncthreads();
-        for (int q = 0; q < 2; ++q) {
-            const int px = warp * 2 + q;
-            const int y = y0 + px;
-            if (y >= W) break;                                    // warp-uniform
-            float h0 = b1[lane], h1 = b1[lane + 32];
-#pragma unroll 8
+        // ---- phase 2: pixels 4*warp .. 4*warp+3
+        if (y0 + 4 * warp < W) {
+            float h0[4], h1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { h0[e] = b1[lane]; h1[e] = b1[lane + 32]; }
+#pragma unroll 4
             for (int k = 0; k < C_FUSE; ++k) {
-                const float g = gbuf[k * 32 + px];
-                h0 = fmaf(g, w1[k * C_HID + lane], h0);
-                h1 = fmaf(g, w1[k * C_HID + lane + 32], h1);
+                const float4 g = *reinterpret_cast<const float4*>(gbuf + k * kHeadPx + 4 * warp);
+                const float wa = w1[k * C_HID + lane], wb = w1[k * C_HID + lane + 32];
+                h0[0] = fmaf(g.x, wa, h0[0]); h1[0] = fmaf(g.x, wb, h1[0]);
+                h0[1] = fmaf(g.y, wa, h0[1]); h1[1] = fmaf(g.y, wb, h1[1]);
+                h0[2] = fmaf(g.z, wa, h0[2]); h1[2] = fmaf(g.z, wb, h1[2]);
+                h0[3] = fmaf(g.w, wa, h0[3]); h1[3] = fmaf(g.w, wb, h1[3]);
             }
-            hid[lane] = fmaxf(h0, 0.f);
-            hid[lane + 32] = fmaxf(h1, 0.f);
+            *reinterpret_cast<float4*>(hid + lane * 4) = make_float4(fmaxf(h0[0], 0.f), fmaxf(h0[1], 0.f), fmaxf(h0[2], 0.f), fmaxf(h0[3], 0.f));
+            *reinterpret_cast<float4*>(hid + (lane + 32) * 4) = make_float4(fmaxf(h1[0], 0.f), fmaxf(h1[1], 0.f), fmaxf(h1[2], 0.f), fmaxf(h1[3], 0.f));
             __syncwarp();
-            const int64_t n = (int64_t)xl * W + y;                // pixel index inside the band
-            float l0 = -INFINITY, l1 = -INFINITY;
+            // logits: classes lane and lane + 32 (C <= 64) of the 4 pixels
+            float l0[4], l1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { l0[e] = -INFINITY; l1[e] = -INFINITY; }
             if (lane < C) {
-                float a = b2[lane];
+                float a[4] = {b2[lane], b2[lane], b2[lane], b2[lane]};
 #pragma unroll 8
-                for (int k = 0; k < C_HID; ++k) a = fmaf(hid[k], w2[k * C + lane], a);
-                l0 = a;
-                if (logits_out) logits_out[n * C + lane] = a;
+                for (int k = 0; k < C_HID; ++k) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hid + k * 4);
+                    const float w = w2[k * C + lane];
+                    a[0] = fmaf(hv.x, w, a[0]); a[1] = fmaf(hv.y, w, a[1]); a[2] = fmaf(hv.z, w, a[2]); a[3] = fmaf(hv.w, w, a[3]);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) l0[e] = a[e];
             }
             if (lane + 32 < C) {
-                float a = b2[lane + 32];
+                float a[4] = {b2[lane + 32], b2[lane + 32], b2[lane + 32], b2[lane + 32]};
 #pragma unroll 8
-                for (int k = 0; k < C_HID; ++k) a = fmaf(hid[k], w2[k * C + lane + 32], a);
-                l1 = a;
-                if (logits_out) logits_out[n * C + lane + 32] = a;
-            }
-            // argmax with torch.max semantics: the first (lowest) index among equal maxima
-            float bv = l0;
-            int bi = lane;
-            if (l1 > bv) { bv = l1; bi = lane + 32; }
+                for (int k = 0; k < C_HID; ++k) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hid + k * 4);
+                    const float w = w2[k * C + lane + 32];
+                    a[0] = fmaf(hv.x, w, a[0]); a[1] = fmaf(hv.y, w, a[1]); a[2] = fmaf(hv.z, w, a[2]); a[3] = fmaf(hv.w, w, a[3]);
+                }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                for (int e = 0; e < 4; ++e) l1[e] = a[e];
             }
-            if (lane == 0) {
-                const int64_t kflat = pix0 + n;
-                if (pred_map) pred_map[kflat] = (uint8_t)bi;
-                if (cm) {
-                    const int lab = label[kflat];
-                    if (lab < C) atomicAdd(&hist[bi * C + lab], 1u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int y = y0 + 4 * warp + e;
+                if (y < W) {                                                  // warp-uniform
+                    const int64_t n = (int64_t)xl * W + y;                    // pixel index inside the band
+                    if (logits_out) {
+                        if (lane < C) logits_out[n * C + lane] = l0[e];
+                        if (lane + 32 < C) logits_out[n * C + lane + 32] = l1[e];
+                    }
+                    // argmax with torch.max semantics: the first (lowest) index among equal maxima
+                    float bv = l0[e];
+                    int bi = lane;
+                    if (l1[e] > bv) { bv = l1[e]; bi = lane + 32; }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (lane == 0) {
+                        const int64_t kflat = pix0 + n;
+                        if (pred_map) pred_map[kflat] = (uint8_t)bi;
+                        if (cm) {
+                            const int lab = label[kflat];
+                            if (lab < C) atomicAdd(&hist[bi * C + lab], 1u);
+                        }
+                    }
                 }
             }
-            __syncwarp();
         }
         __syncthreads();
     }
@@ -413,6 +484,8 @@ int dense_pack(dmf_net* n) {
 static void dense_free_ws(DenseWs* d) {
     __nv_bfloat16* bs[] = {d->A, d->CAT, d->B1, d->B2, d->F};
     for (auto* b : bs) cudaFree(b);
+    cudaFree(d->S);
+    d->S = nullptr;
     d->A = d->CAT = d->B1 = d->B2 = d->F = nullptr;
     d->W = d->band = 0;
     d->bytes = 0;
@@ -443,7 +516,9 @@ static int dense_prepare(dmf_net* n, int W, int band) {
     DMF_CUDA(cudaMalloc(&d->B1, sB1));
     DMF_CUDA(cudaMalloc(&d->B2, sB2));
     DMF_CUDA(cudaMalloc(&d->F, sF));
-    d->bytes = sA + sCAT + sB1 + sB2 + sF;
+    const size_t sS = R1 * (size_t)W * 3 * C_FUSE * sizeof(float);
+    DMF_CUDA(cudaMalloc(&d->S, sS));
+    d->bytes = sA + sCAT + sB1 + sB2 + sF + sS;
     // positions a band never writes are only ever read into don't-care outputs; zero them once so that runs are reproducible
     DMF_CUDA(cudaMemset(d->A, 0, sA));
     DMF_CUDA(cudaMemset(d->CAT, 0, sCAT));
@@ -456,7 +531,9 @@ static int dense_prepare(dmf_net* n, int W, int band) {
     DMF_TRY(make_dense_map(&d->mapB2s, d->B2, 9, C_PAN2 / 8, (int)R1, (int)C1, 11, 19, 2));
     DMF_TRY(make_dense_map(&d->mapCAT, d->CAT, 9, C_CAT / 8, (int)R1, (int)C1, 32, 4, C_CAT / 8));
     for (auto& e : d->ev) if (!e) DMF_CUDA(cudaEventCreate(&e));
-    DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     return DMF_OK;
 }
 
@@ -514,10 +591,15 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
         mark();
         // ---- head
         {
-            const int n_seg = nb * ((W + 31) / 32);
+            const int64_t work = (int64_t)3 * 16 * rows * W;
+            auto rk = p == 8 ? gap_rows_kernel<4> : p == 16 ? gap_rows_kernel<8> : gap_rows_kernel<16>;
+            rk<<<grid_for(work, 256, 16), 256, 0, st>>>(reinterpret_cast<const uint4*>(d->F), R1, C1, rows, W, reinterpret_cast<float4*>(d->S));
+            DMF_LAUNCHED();
+            const int n_seg = nb * ((W + kHeadPx - 1) / kHeadPx);
             const int64_t off = (int64_t)(b0 - row0) * W;
-            head_dense_kernel<<<std::min(n_seg, 2 * num_sms()), kDenseHeadThreads, dense_head_smem(n->C), st>>>(
-                reinterpret_cast<const uint4*>(d->F), R1, C1, p, nb, W, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, (int64_t)b0 * W, s->label,
+            auto kern = p == 8 ? head_dense_kernel<4> : p == 16 ? head_dense_kernel<8> : head_dense_kernel<16>;
+            kern<<<std::min(n_seg, num_sms()), kDenseHeadThreads, dense_head_smem(n->C), st>>>(
+                reinterpret_cast<const float4*>(d->S), rows, nb, W, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, (int64_t)b0 * W, s->label,
                 logits_dev ? logits_dev + off * n->C : nullptr, reinterpret_cast<unsigned long long*>(cm_dev), pred_map_dev);
             DMF_LAUNCHED();
         }
