@@ -43,7 +43,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled every 100 ms during the timed region (pynvml)."""
+    """SM clock + throttle reasons sampled every 10 ms during the timed region (pynvml)."""
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
@@ -65,7 +65,7 @@ class ClockSampler:
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.reasons.update(k for k, bit in names.items() if r & bit)
-                time.sleep(0.1)
+                time.sleep(0.01)
         except Exception as e:               # clocks are evidence, not a dependency
             self.reasons.add('unavailable: %s' % type(e).__name__)
 
@@ -166,7 +166,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default=None, choices=list(WORKLOADS))
@@ -376,7 +376,7 @@ def main():
         conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
         roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['bf16_tflops_sustained'],
-                'traffic': ncu_traffic('r01_ncu_dense_summary.json', ncu_key[name]) if args.band == 256 else None,
+                'traffic': ncu_traffic('r01_dense_ncu_summary.json', ncu_key[name]) if args.band == 256 else None,
                 'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
                 'avg_launch_ms': k_ms / (len(bands) * per_band), 'launches': len(bands) * per_band,
                 'flops_per_launch': fl_pos * pos / (len(bands) * per_band),
@@ -389,7 +389,7 @@ def main():
         util = {'achieved_TFLOPs': conv_fl * pos / (conv_ms / 1e3) / 1e12,
                 'frac_of_sustained_peak': conv_fl * pos / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
                 'frac_of_burst_peak': conv_fl * pos / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
-                'ncu_tensor_pipe_active_pct': 'profiles/r01_ncu_dense_summary.json'}
+                'ncu_tensor_pipe_active_pct': 'profiles/r01_dense_ncu_summary.json'}
         return roof, util
 
     roofline, conv_util = dense_roofline() if args.mode == 'dense' else patch_roofline()

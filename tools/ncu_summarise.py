@@ -14,6 +14,8 @@ rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+to_us = {'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3, 'second': 1e6, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}
+dur_scale = to_us[units[idx['gpu__time_duration.sum']]]
 K = {'dur': 'gpu__time_duration.sum', 'rd': 'dram__bytes_read.sum', 'wr': 'dram__bytes_write.sum',
      'tensor': 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'dram': 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
      'regs': 'launch__registers_per_thread', 'grid': 'launch__grid_size', 'block': 'launch__block_size', 'smem': 'launch__shared_mem_per_block_dynamic',
@@ -21,11 +23,11 @@ K = {'dur': 'gpu__time_duration.sum', 'rd': 'dram__bytes_read.sum', 'wr': 'dram_
 agg = collections.OrderedDict()
 for r in rows[2:]:
     e = agg.setdefault(short(r[idx['Kernel Name']]), collections.defaultdict(list))
-    e['dur'].append(float(r[idx[K['dur']]]))
+    e['dur'].append(float(r[idx[K['dur']]]) * dur_scale)
     e['bytes'].append(float(r[idx[K['rd']]]) * mult[units[idx[K['rd']]]] + float(r[idx[K['wr']]]) * mult[units[idx[K['wr']]]])
     e['rd'].append(float(r[idx[K['rd']]]) * mult[units[idx[K['rd']]]])
     e['tensor'].append(float(r[idx[K['tensor']]])); e['dram'].append(float(r[idx[K['dram']]]))
-    e['mhz'].append(float(r[idx[K['cyc']]]) / float(r[idx[K['dur']]]))
+    e['mhz'].append(float(r[idx[K['cyc']]]) / (float(r[idx[K['dur']]]) * dur_scale))
     e['meta'] = [r[idx[K[k]]] for k in ('regs', 'grid', 'block', 'smem')]
 out = {'source': 'ncu --set full --clock-control none --import-source on; %s; round %s' % (prof_cmd, tag),
        'workload': 'c2', 'chunk_pixels': chunk, 'kernels': {}}
