@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const flo
             float h0[4], h1[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) { h0[e] = b1[lane]; h1[e] = b1[lane + 32]; }
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < C_FUSE; ++k) {
                 const float4 g = *reinterpret_cast<const float4*>(gbuf + k * kHeadPx + 4 * warp);
                 const float wa = w1[k * C_HID + lane], wb = w1[k * C_HID + lane + 32];
@@ -598,7 +598,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             const int n_seg = nb * ((W + kHeadPx - 1) / kHeadPx);
             const int64_t off = (int64_t)(b0 - row0) * W;
             auto kern = p == 8 ? head_dense_kernel<4> : p == 16 ? head_dense_kernel<8> : head_dense_kernel<16>;
-            kern<<<std::min(n_seg, num_sms()), kDenseHeadThreads, dense_head_smem(n->C), st>>>(
+            kern<<<std::min(n_seg, 2 * num_sms()), kDenseHeadThreads, dense_head_smem(n->C), st>>>(      // 2 blocks per SM (86 KB each)
                 reinterpret_cast<const float4*>(d->S), rows, nb, W, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, (int64_t)b0 * W, s->label,
                 logits_dev ? logits_dev + off * n->C : nullptr, reinterpret_cast<unsigned long long*>(cm_dev), pred_map_dev);
             DMF_LAUNCHED();

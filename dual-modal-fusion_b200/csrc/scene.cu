@@ -121,17 +121,30 @@ __global__ void __launch_bounds__(256) normalize_pad_kernel(const T* __restrict_
 }
 
 template <typename T>
-static int normalize_pad_t(const T* raw, int H, int W, int bands, int P, void* out, int out_dtype,
-                           int64_t out_pitch, cudaStream_t st) {
-    const int64_t n = (int64_t)H * W * bands;
+static int minmax_t(const T* raw, int64_t n, double* lohi_dev, cudaStream_t st) {
     const int nblk = (int)std::min<int64_t>(num_sms() * 8, (n + 255) / 256);
     double* scratch = nullptr;
-    DMF_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (2 * nblk + 2), st));
-    double* lohi = scratch + 2 * nblk;
+    DMF_CUDA(cudaMallocAsync(&scratch, sizeof(double) * 2 * nblk, st));
     minmax_partial_kernel<T><<<nblk, 256, 0, st>>>(raw, n, scratch);
     DMF_LAUNCHED();
-    minmax_final_kernel<<<1, 32, 0, st>>>(scratch, nblk, lohi);
+    minmax_final_kernel<<<1, 32, 0, st>>>(scratch, nblk, lohi_dev);
     DMF_LAUNCHED();
+    DMF_CUDA(cudaFreeAsync(scratch, st));
+    return DMF_OK;
+}
+
+// lohi_given: device {min, max} to normalise with (a band of a larger raster), or null = this raster's own range
+template <typename T>
+static int normalize_pad_t(const T* raw, int H, int W, int bands, int P, void* out, int out_dtype,
+                           int64_t out_pitch, const double* lohi_given, cudaStream_t st) {
+    const int64_t n = (int64_t)H * W * bands;
+    double* scratch = nullptr;
+    DMF_CUDA(cudaMallocAsync(&scratch, sizeof(double) * 2, st));
+    const double* lohi = lohi_given;
+    if (!lohi) {
+        DMF_TRY(minmax_t(raw, n, scratch, st));
+        lohi = scratch;
+    }
     const int Hp = H + P - 1, Wp = W + P - 1;
     const dim3 grid((unsigned)std::min<int64_t>(((int64_t)Wp * bands + 255) / 256, 64), (unsigned)std::min(Hp, 65535));
     if (out_dtype == DMF_F32)
@@ -144,14 +157,14 @@ static int normalize_pad_t(const T* raw, int H, int W, int bands, int P, void* o
 }
 
 static int normalize_pad_any(const void* raw, int dt, int H, int W, int bands, int P, void* out, int out_dtype,
-                             int64_t out_pitch, cudaStream_t st) {
+                             int64_t out_pitch, cudaStream_t st, const double* lohi_given = nullptr) {
     DMF_REQUIRE(raw && out && H > 0 && W > 0 && bands > 0 && P > 0, "normalize_pad: bad shape/pointer");
     DMF_REQUIRE(out_dtype == DMF_F32 || out_dtype == DMF_F64, "normalize_pad: out_dtype must be f32/f64");
     switch (dt) {
-        case DMF_U8: return normalize_pad_t((const uint8_t*)raw, H, W, bands, P, out, out_dtype, out_pitch, st);
-        case DMF_U16: return normalize_pad_t((const uint16_t*)raw, H, W, bands, P, out, out_dtype, out_pitch, st);
-        case DMF_F32: return normalize_pad_t((const float*)raw, H, W, bands, P, out, out_dtype, out_pitch, st);
-        case DMF_F64: return normalize_pad_t((const double*)raw, H, W, bands, P, out, out_dtype, out_pitch, st);
+        case DMF_U8: return normalize_pad_t((const uint8_t*)raw, H, W, bands, P, out, out_dtype, out_pitch, lohi_given, st);
+        case DMF_U16: return normalize_pad_t((const uint16_t*)raw, H, W, bands, P, out, out_dtype, out_pitch, lohi_given, st);
+        case DMF_F32: return normalize_pad_t((const float*)raw, H, W, bands, P, out, out_dtype, out_pitch, lohi_given, st);
+        case DMF_F64: return normalize_pad_t((const double*)raw, H, W, bands, P, out, out_dtype, out_pitch, lohi_given, st);
     }
     set_error("normalize_pad: unknown dtype %d", dt);
     return DMF_ERR_ARG;
@@ -298,14 +311,14 @@ int dmf_normalize_pad(const void* raw_dev, int raw_dtype, int H, int W, int band
 }
 
 static int scene_fill_raw(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int on_device,
-                          cudaStream_t st) {
+                          cudaStream_t st, const double* ms_lohi = nullptr, const double* pan_lohi = nullptr) {
     const int H = s->H, W = s->W, p = s->p;
     void *t1 = nullptr, *t2 = nullptr;
     const void *dms, *dpan;
     int rc = upload(ms, dtype_size(ms_dtype) * 4 * (size_t)H * W, on_device, st, &t1, &dms);
     if (rc == DMF_OK) rc = upload(pan, dtype_size(pan_dtype) * 16 * (size_t)H * W, on_device, st, &t2, &dpan);
-    if (rc == DMF_OK) rc = normalize_pad_any(dms, ms_dtype, H, W, 4, p, s->ms, DMF_F32, (int64_t)s->Wp * 4, st);
-    if (rc == DMF_OK) rc = normalize_pad_any(dpan, pan_dtype, 4 * H, 4 * W, 1, 4 * p, s->pan, DMF_F32, s->pan_pitch, st);
+    if (rc == DMF_OK) rc = normalize_pad_any(dms, ms_dtype, H, W, 4, p, s->ms, DMF_F32, (int64_t)s->Wp * 4, st, ms_lohi);
+    if (rc == DMF_OK) rc = normalize_pad_any(dpan, pan_dtype, 4 * H, 4 * W, 1, 4 * p, s->pan, DMF_F32, s->pan_pitch, st, pan_lohi);
     if (t1) cudaFreeAsync(t1, st);
     if (t2) cudaFreeAsync(t2, st);
     return rc;
@@ -326,6 +339,25 @@ int dmf_scene_update_raw(dmf_scene* s, const void* ms, int ms_dtype, const void*
                          void* stream) {
     DMF_REQUIRE(s && ms && pan, "scene_update_raw: bad argument");
     return scene_fill_raw(s, ms, ms_dtype, pan, pan_dtype, on_device, (cudaStream_t)stream);
+}
+
+int dmf_raster_minmax(const void* raw_dev, int dtype, int64_t n, double* lohi_out_dev, void* stream) {
+    DMF_REQUIRE(raw_dev && lohi_out_dev && n > 0, "raster_minmax: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case DMF_U8: return minmax_t((const uint8_t*)raw_dev, n, lohi_out_dev, st);
+        case DMF_U16: return minmax_t((const uint16_t*)raw_dev, n, lohi_out_dev, st);
+        case DMF_F32: return minmax_t((const float*)raw_dev, n, lohi_out_dev, st);
+        case DMF_F64: return minmax_t((const double*)raw_dev, n, lohi_out_dev, st);
+    }
+    set_error("raster_minmax: unknown dtype %d", dtype);
+    return DMF_ERR_ARG;
+}
+
+int dmf_scene_update_raw_range(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int on_device,
+                               const double* ms_lohi_dev, const double* pan_lohi_dev, void* stream) {
+    DMF_REQUIRE(s && ms && pan && ms_lohi_dev && pan_lohi_dev, "scene_update_raw_range: bad argument");
+    return scene_fill_raw(s, ms, ms_dtype, pan, pan_dtype, on_device, (cudaStream_t)stream, ms_lohi_dev, pan_lohi_dev);
 }
 
 static int copy_padded(const void* src, int dtype, int rows, int64_t row_elems, int64_t pitch, float* dst,

@@ -84,19 +84,31 @@ class Scene:
                     torch.cuda.current_stream().synchronize()
         return cls(h, H, W, p, device)
 
-    def update_raw(self, ms, pan):
-        """Re-fill this scene from new rasters of the same shape (pinned CPU or CUDA tensors, or ndarrays)."""
+    def update_raw(self, ms, pan, ms_range=None, pan_range=None):
+        """Re-fill this scene from new rasters of the same shape (pinned CPU or CUDA tensors, or ndarrays).
+        ms_range / pan_range: float64 CUDA tensors {min, max} to normalise with instead of the rasters' own ranges (row-band
+        scenes: the all-reduced ranges of the whole scene, see band_slice / raster_minmax)."""
         code = {torch.uint8: U8, torch.int16: U16, torch.uint16: U16, torch.float32: F32, torch.float64: F64}
+        ranged = ms_range is not None
+        assert ranged == (pan_range is not None), 'give both ranges or neither'
         with torch.cuda.device(self.device):
             if isinstance(ms, np.ndarray):
                 a, b = np.ascontiguousarray(ms), np.ascontiguousarray(pan)
-                check(lib.dmf_scene_update_raw(self._h, a.ctypes.data_as(C.c_void_p), np_dtype_code(a),
-                                               b.ctypes.data_as(C.c_void_p), np_dtype_code(b), 0, _stream()))
+                if ranged:
+                    check(lib.dmf_scene_update_raw_range(self._h, a.ctypes.data_as(C.c_void_p), np_dtype_code(a),
+                                                         b.ctypes.data_as(C.c_void_p), np_dtype_code(b), 0, _ptr(ms_range), _ptr(pan_range), _stream()))
+                else:
+                    check(lib.dmf_scene_update_raw(self._h, a.ctypes.data_as(C.c_void_p), np_dtype_code(a),
+                                                   b.ctypes.data_as(C.c_void_p), np_dtype_code(b), 0, _stream()))
                 torch.cuda.current_stream().synchronize()
             else:
                 a, b = ms.contiguous(), pan.contiguous()
                 assert tuple(a.shape) == (self.H, self.W, 4) and tuple(b.shape) == (4 * self.H, 4 * self.W)
-                check(lib.dmf_scene_update_raw(self._h, _ptr(a), code[a.dtype], _ptr(b), code[b.dtype], 1 if a.is_cuda else 0, _stream()))
+                if ranged:
+                    check(lib.dmf_scene_update_raw_range(self._h, _ptr(a), code[a.dtype], _ptr(b), code[b.dtype], 1 if a.is_cuda else 0,
+                                                         _ptr(ms_range), _ptr(pan_range), _stream()))
+                else:
+                    check(lib.dmf_scene_update_raw(self._h, _ptr(a), code[a.dtype], _ptr(b), code[b.dtype], 1 if a.is_cuda else 0, _stream()))
                 if not a.is_cuda and not (a.is_pinned() and b.is_pinned()):
                     torch.cuda.current_stream().synchronize()
         return self
@@ -171,6 +183,26 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+
+def band_slice(H, p, r0, r1):
+    """Scene rows [s0, s1) a rank needs to classify the anchors of rows [r0, r1) from a band-local Scene: the band, the next
+    band's first p-1 rows (every window reaches p-1 rows down) and, for the last band, enough rows above it for the bottom
+    reflect padding to be the band's own (BORDER_REFLECT_101 of function/function.py:104-110 reaches p-1 rows up from the
+    scene's last row).  The anchors are rows [r0 - s0, r1 - s0) of the band scene."""
+    s1 = min(H, r1 + p - 1)
+    s0 = r0 if s1 < H else max(0, min(r0, H - p))
+    return s0, s1
+
+
+def raster_minmax(t):
+    """{min, max} of a CUDA raster as a float64 CUDA tensor [2] (asynchronous; all-reduce it across the bands of a scene)."""
+    code = {torch.uint8: U8, torch.int16: U16, torch.uint16: U16, torch.float32: F32, torch.float64: F64}
+    assert t.is_cuda and t.is_contiguous()
+    out = torch.empty((2,), dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        check(lib.dmf_raster_minmax(_ptr(t), code[t.dtype], t.numel(), _ptr(out), _stream()))
+    return out
 
 
 def normalize_pad(array, P, out_dtype=np.float64, device='cuda:0'):

@@ -21,6 +21,8 @@ SIGNATURES = {
     'dmf_normalize_pad': (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     'dmf_scene_create_raw': (i32, [C.POINTER(vp), vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     'dmf_scene_update_raw': (i32, [vp, vp, i32, vp, i32, i32, vp]),
+    'dmf_raster_minmax': (i32, [vp, i32, i64, vp, vp]),
+    'dmf_scene_update_raw_range': (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp]),
     'dmf_scene_create_padded': (i32, [C.POINTER(vp), vp, vp, i32, i32, i32, i32, i32, vp]),
     'dmf_scene_set_mspan': (i32, [vp, vp, i32, i32, vp]),
     'dmf_scene_set_labels': (i32, [vp, vp, i32, vp]),

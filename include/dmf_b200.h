@@ -78,6 +78,13 @@ int dmf_scene_create_raw(dmf_scene** out, const void* ms, int ms_dtype, const vo
  * loop, e.g. tiles of a mosaic). */
 int dmf_scene_update_raw(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype,
                          int on_device, void* stream);
+/* Row-band scenes (one band of a larger scene per GPU): min / max of a raw raster on the device (lohi_out_dev = 2 doubles),
+ * and a re-fill that normalises with GIVEN ranges (device {min, max} pairs, e.g. the all-reduced ranges of all bands) instead of
+ * the band's own.  A band made of scene rows [s0, s1) with s1 = min(H, r1 + p - 1) reproduces the whole scene's windows for the
+ * anchors of rows [r0, r1): interior bands carry the next band's first p-1 rows, the last band's reflect padding is its own. */
+int dmf_raster_minmax(const void* raw_dev, int dtype, int64_t n, double* lohi_out_dev, void* stream);
+int dmf_scene_update_raw_range(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int on_device,
+                               const double* ms_lohi_dev, const double* pan_lohi_dev, void* stream);
 /* Build a device scene from ALREADY normalised+padded rasters as data_padding() returns them:
  * ms_pad[H+p-1][W+p-1][4], pan_pad[4H+4p-1][4W+4p-1]; dtype DMF_F32 or DMF_F64 (cast to f32 with
  * round-to-nearest, the cast dataset_dual applies per patch, train/dataset.py:183-184). */

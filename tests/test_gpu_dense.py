@@ -174,3 +174,43 @@ def test_dense_row_bands_add_up(dmf):
     assert torch.equal(pm, pm2) and torch.equal(cm, cm2)
     assert int(cm.sum()) == H * W
     h.close()
+
+
+@pytest.mark.parametrize('H,world', [(45, 3), (20, 2), (33, 1)])
+def test_band_scene_equals_whole_scene(dmf, H, world):
+    """A rank that uploads only its band (+ p-1 halo rows) and normalises with the all-reduced scene range sees the same
+    windows and produces the same label rows / matrix as the whole-scene object (bench.py e2e arm at N > 1)."""
+    from solver.mainsolver import row_band
+    p, W, C = 16, 30, 6
+    ms, pan, label = orc.synthetic_scene(H, W, C - 1, seed=9, label_seed=10)
+    whole = dmf.Scene.from_raw(ms, pan, p, DEV)
+    whole.set_labels(label)
+    ref = make_ref(p, C)
+    h = dmf.NetHandle(p, C, max_batch=1024, device=DEV)
+    h.load_state_dict(ref.state_dict())
+    pm_w, cm_w = h.infer_scene(whole)
+    ms_t = torch.from_numpy(ms.view(np.int16)).to(DEV)
+    pan_t = torch.from_numpy(pan.view(np.int16)).to(DEV)
+    bands = [row_band(H, r, world) for r in range(world)]
+    # what the MIN all-reduce of {lo, -hi} yields
+    rm = torch.stack([dmf.raster_minmax(ms_t[a:b].contiguous()) for a, b in bands])
+    rp = torch.stack([dmf.raster_minmax(pan_t[4 * a:4 * b].contiguous()) for a, b in bands])
+    ms_rng = torch.stack([rm[:, 0].min(), rm[:, 1].max()])
+    pan_rng = torch.stack([rp[:, 0].min(), rp[:, 1].max()])
+    assert float(ms_rng[0]) == ms.min() and float(ms_rng[1]) == ms.max() and float(pan_rng[1]) == pan.max()
+    cm_sum = torch.zeros_like(cm_w)
+    for r0, r1 in bands:
+        s0, s1 = dmf.band_slice(H, p, r0, r1)
+        a, b = ms_t[s0:s1].contiguous(), pan_t[4 * s0:4 * s1].contiguous()
+        band = dmf.Scene.from_raw(a, b, p, DEV)
+        band.update_raw(a, b, ms_rng, pan_rng)
+        band.set_labels(label[s0:s1])
+        idx_w = torch.arange(r0 * W, r1 * W, device=DEV)
+        idx_b = idx_w - s0 * W
+        gw, gb = whole.gather(idx_w, want_target=False), band.gather(idx_b, want_target=False)
+        assert torch.equal(gw[0], gb[0]) and torch.equal(gw[1], gb[1]), 'band windows differ from the whole scene'
+        pm_b, cm_b = h.infer_scene(band, r0 - s0, r1 - s0)
+        assert torch.equal(pm_b[r0 - s0:r1 - s0], pm_w[r0:r1])
+        cm_sum += cm_b
+    assert torch.equal(cm_sum, cm_w)
+    h.close()
