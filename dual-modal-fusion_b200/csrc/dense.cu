@@ -11,7 +11,7 @@
 //   scene --pan_stem_map--> B1 [9 ][4 phases][4][R][C][8]  stem conv + pool on the pooled-once grid, stored phase-separated
 //   B1 --conv_pool4 (aligned pool)--> B2 [9][8][R][C][8]  conv 32->64 + aligned 2x2 max (the pooled-once grid moves 2 cells per pixel)
 //   B2 --conv_pool4 (stride-1 pool)--> CAT[9][16..31]
-//   CAT --conv_dense 1x1, 9 planes--> F [9][16][R][C][8]
+//   CAT --conv1x1_planes, 9 planes--> F [9][16][R][C][8]
 //   F  --head_dense--> per pixel: mean over the (p/2)^2 strided samples F[cls(k),cls(l)][x+2k][y+2l], 2 linears,
 //                      argmax, confusion matrix, label map
 // with R = (r1 - r0) + p - 1 rows and C = W + p - 1 columns.  Positions a band never needs hold don't-care values
@@ -440,17 +440,16 @@ static int launch_pool4(const CUtensorMap& map, bool aligned, const __nv_bfloat1
     return DMF_OK;
 }
 
-template <int CI, int CO, int TAPS, int RS, int G>
-static int launch_dense(const CUtensorMap& map, tc::DenseParams& P, cudaStream_t st) {
-    constexpr int HR = RS * 15 + 3;
-    constexpr size_t a_stage = (size_t)(CI / 8) * (TAPS == 9 ? HR * tc::kPitch * 16 : 128 * 16);
-    constexpr size_t fixed = (size_t)TAPS * CI * CO * 2 + 2 * CO * 4 + 28 * 8 + tc::kDenseMaxCls * sizeof(tc::DenseCls);
-    static_assert(fixed + a_stage <= (size_t)kSmemLimit, "dense layer does not fit in shared memory");
+template <int CI, int CO, int G>
+static int launch_planes(const CUtensorMap& map, tc::PlanesParams& P, cudaStream_t st) {
+    constexpr size_t a_stage = (size_t)(CI / 8) * 128 * 16;
+    constexpr size_t fixed = (size_t)CI * CO * 2 + 2 * CO * 4 + 28 * 8;
+    static_assert(fixed + a_stage <= (size_t)kSmemLimit, "1x1 plane layer does not fit in shared memory");
     P.n_stage = (int)std::min<size_t>(8, (kSmemLimit - fixed) / a_stage);
+    P.n_tiles = P.tiles_x * P.tiles_y * P.n_planes;
     static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
     P.dbg = dbg;
-    P.n_tiles = P.tiles_x * P.tiles_y * P.n_cls;
-    auto kern = tc::conv_dense_kernel<CI, CO, TAPS, RS, G>;
+    auto kern = tc::conv1x1_planes_kernel<CI, CO, G>;
     static bool attr_set = false;
     if (!attr_set) {
         DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -578,15 +577,11 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
         mark();
         // ---- fusion conv (1x1) on the 9 pooled planes
         {
-            tc::DenseParams P{};
-            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 32); P.tiles_y = cdiv(rows, 4); P.n_cls = 9;
-            P.out_chunks = C_FUSE / 8; P.out_chunk0 = 0;
+            tc::PlanesParams P{};
+            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 32); P.tiles_y = cdiv(rows, 4); P.n_planes = 9;
+            P.out_chunks = C_FUSE / 8;
             P.w = n->L[3].w; P.scale = n->L[3].scale; P.shift = n->L[3].shift; P.out = d->F;
-            for (int a = 0; a < 9; ++a) {
-                memset(&P.cls[a], 0, sizeof(tc::DenseCls));
-                P.cls[a].out_plane = (int16_t)a; P.cls[a].n_steps = 1; P.cls[a].in_plane[0] = (int16_t)a; P.cls[a].mask[0] = 1;
-            }
-            DMF_TRY((launch_dense<C_CAT, C_FUSE, 1, 1, 4>(d->mapCAT, P, st)));
+            DMF_TRY((launch_planes<C_CAT, C_FUSE, 4>(d->mapCAT, P, st)));
         }
         mark();
         // ---- head

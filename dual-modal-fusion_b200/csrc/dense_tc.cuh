@@ -1,65 +1,47 @@
-// Scene-dense convolution on tcgen05 — the tensor-core kernel of the whole-scene ("dense") inference path.
+// Scene-dense layers on tcgen05 — the tensor-core kernels of the whole-scene ("dense") inference path.
 //
 // Solver.color() / test() classify EVERY pixel of a scene (solver/mainsolver.py:167-185): patches at stride 1.  The
 // value a layer produces at patch-relative position (i, j) of the patch anchored at (x, y) depends only on the
 // ABSOLUTE position (x + i, y + j) and on how close (i, j) is to the patch border (the convs zero-pad at the patch
-// border, not at the scene border).  A 3x3 conv whose input has the 3 border variants {first, interior, last} per
-// axis has 5 output classes per axis {0, 1, interior, S-2, S-1}; the 2x2 max-pool folds them back to 3.  So every
-// layer is a small set of scene-level maps ("planes"), each computed ONCE per scene position instead of once per
-// patch: 25 x (1/256) of the per-patch MMA work at p = 16.
-//
-// This kernel computes, for a list of output classes, out[class][X][Y] = relu(bn(sum_taps W[tap] . in[plane(class,
-// tap)][X + dy][Y + dx])) over a whole map.  A tile is 16 rows x 8 columns of ONE class (row stride RS = 2 for the
-// classes of a stride-2-pooled layer that exist on one row parity only).  Its taps are grouped by the input plane they
-// read into <= 4 "steps"; every step is one TMA halo box (same C8-planar no-swizzle layout and shifted-descriptor
-// trick as conv_tc.cuh) and a masked subset of the 9 taps, all accumulating into the same TMEM accumulator.  Tiles are
-// ordered (row strip, class, column) so that the CTAs running concurrently read the same input strip (L2-resident).
-// TAPS == 1 (the 1x1 fusion conv): tile = 4 rows x 32 columns, no halo, 512-byte TMA rows.
+// border, not at the scene border): a 3x3/pad-1 conv output has 3 border variants per axis {first, interior, last},
+// and a conv + 2x2 max-pool on such an input again has 3.  So every layer is 9 scene-level maps ("planes"), each
+// computed ONCE per scene position instead of once per patch.  Two kernels:
+//   conv1x1_planes_kernel   the 1x1 fusion conv, plane by plane
+//   conv_pool4_kernel       conv3x3 + BN + ReLU + 2x2 max-pool, 9 pooled planes out of 9 (x 4 phases) input planes
+// Both use the C8-planar no-swizzle operand layout and the warp roles of conv_tc.cuh.
 #pragma once
 #include "conv_tc.cuh"
 
 namespace dmf {
 namespace tc {
 
-constexpr int kDenseMaxCls = 25, kDenseMaxSteps = 4;
-
-struct DenseCls {
-    int16_t out_plane;                    // plane of the output tensor this class writes
-    int16_t row0;                         // first output row (row parity for RS = 2)
-    int16_t n_steps;
-    int16_t pad_;
-    int16_t in_plane[kDenseMaxSteps];     // input plane of each step
-    uint16_t mask[kDenseMaxSteps];        // taps (bit dy*3+dx) that read that plane
-};
-
-struct DenseParams {
-    int rows, cols;                       // map size in positions (input and output grids coincide)
-    int tiles_x, tiles_y, n_cls, n_tiles;
+struct PlanesParams {
+    int rows, cols;                       // map size in positions
+    int tiles_x, tiles_y, n_planes, n_tiles;
     int n_stage;
-    int out_chunks, out_chunk0;           // channel chunks of one output plane, first chunk written
-    int dbg;                              // diagnostics only: bit0 = skip the TMA halo loads, bit1 = skip the epilogue math/stores, bit2 = no per-step commit
-    const __nv_bfloat16* w;               // packed [tap][C_in/8][C_out][8]
+    int out_chunks;                       // channel chunks of one output plane
+    int dbg;                              // diagnostics only: bit0 = skip the TMA loads, bit1 = skip the epilogue math/stores
+    const __nv_bfloat16* w;               // packed [C_in/8][C_out][8]
     const float* scale;
     const float* shift;
     __nv_bfloat16* out;                   // [plane][out_chunks][rows][cols][8]
-    DenseCls cls[kDenseMaxCls];
 };
 
-template <int C_IN, int C_OUT, int TAPS, int RS, int G>
-__global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __grid_constant__ CUtensorMap in_map,
-                                                                     const __grid_constant__ DenseParams P) {
+// out[plane][X][Y] = relu(bn(W . in[plane][X][Y])) for every plane.  Tile = 4 rows x 32 columns of one plane (512-byte TMA
+// rows, no halo); tiles ordered (row strip, plane, column).  M = 128 positions, N = C_OUT, C_IN / 16 MMAs per tile; G epilogue
+// groups of 4 warps drain G accumulators.
+template <int C_IN, int C_OUT, int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1) conv1x1_planes_kernel(const __grid_constant__ CUtensorMap in_map,
+                                                                         const __grid_constant__ PlanesParams P) {
     constexpr int kThreads = 64 + 128 * G;
     constexpr int KCH = C_IN / 8, KSTEPS = C_IN / 16;
-    constexpr uint32_t WBYTES = (uint32_t)TAPS * C_IN * C_OUT * 2;
+    constexpr uint32_t WBYTES = (uint32_t)C_IN * C_OUT * 2;
     constexpr uint32_t TMEM_USED = G * C_OUT;
     constexpr uint32_t TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static_assert(G >= 1 && G <= 4 && TMEM_USED <= 512, "epilogue groups / TMEM columns");
-    static_assert(C_IN % 16 == 0 && C_OUT % 32 == 0 && C_OUT <= 256 && (TAPS == 9 || TAPS == 1) && (RS == 1 || RS == 2), "configuration");
-    constexpr int HR = RS * 15 + 3;                                         // halo rows of a 3x3 tile
-    constexpr uint32_t A_PLANE = TAPS == 9 ? (uint32_t)HR * kPitch * 16 : 128u * 16u;
-    constexpr uint32_t SBO_A = TAPS == 9 ? (uint32_t)RS * kPitch * 16 : 128u;
+    static_assert(C_IN % 16 == 0 && C_OUT % 32 == 0 && C_OUT <= 256, "channel counts");
+    constexpr uint32_t A_PLANE = 128u * 16u, SBO_A = 128u;
     constexpr uint32_t A_STAGE = KCH * A_PLANE;
-    static_assert(A_STAGE % 128 == 0, "stage alignment");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
@@ -69,7 +51,6 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
     // bars: [0,8) full, [8,16) empty, 16 weights, 17..20 tmem_full, 21..24 tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
-    DenseCls* cls_s = reinterpret_cast<DenseCls*>(bars + 28);        // class table: one LDS per field instead of indexed constant loads
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -83,8 +64,6 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         scale_s[i] = P.scale[i];
         shift_s[i] = P.shift[i];
     }
-    for (int i = threadIdx.x; i < P.n_cls * (int)(sizeof(DenseCls) / 4); i += kThreads)
-        reinterpret_cast<uint32_t*>(cls_s)[i] = reinterpret_cast<const uint32_t*>(P.cls)[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
@@ -101,13 +80,13 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    // tile -> (row strip ty, class c, column tile tx); every role walks its tiles with the same incremental decode
-    int tx = (int)blockIdx.x % P.tiles_x, c = ((int)blockIdx.x / P.tiles_x) % P.n_cls, ty = ((int)blockIdx.x / P.tiles_x) / P.n_cls;
+    // tile -> (row strip ty, plane c, column tile tx); every role walks its tiles with the same incremental decode
+    int tx = (int)blockIdx.x % P.tiles_x, c = ((int)blockIdx.x / P.tiles_x) % P.n_planes, ty = ((int)blockIdx.x / P.tiles_x) / P.n_planes;
     auto next_tile = [&]() {
         tx += (int)gridDim.x;
         while (tx >= P.tiles_x) {
             tx -= P.tiles_x;
-            if (++c == P.n_cls) { c = 0; ++ty; }
+            if (++c == P.n_planes) { c = 0; ++ty; }
         }
     };
 
@@ -125,22 +104,17 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         int st = 0;
         uint32_t ph = 1;
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            const int n_steps = cls_s[c].n_steps;
-            const int row = TAPS == 9 ? cls_s[c].row0 + ty * 16 * RS - 1 : ty * 4;
-            const int col8 = TAPS == 9 ? (tx * 8 - 1) * 8 : tx * 32 * 8;
-            for (int s = 0; s < n_steps; ++s) {
-                mbar_wait(empty_bar(st), ph);
-                if (leader) {
-                    if (P.dbg & 1) {
-                        mbar_arrive(full_bar(st));
-                    } else {
-                        mbar_expect_tx(full_bar(st), A_STAGE);
-                        tma_load_4d(smem_u32(a_s) + (uint32_t)st * A_STAGE, &in_map, full_bar(st), col8, cls_s[c].in_plane[s], row, 0);
-                    }
+            mbar_wait(empty_bar(st), ph);
+            if (leader) {
+                if (P.dbg & 1) {
+                    mbar_arrive(full_bar(st));
+                } else {
+                    mbar_expect_tx(full_bar(st), A_STAGE);
+                    tma_load_4d(smem_u32(a_s) + (uint32_t)st * A_STAGE, &in_map, full_bar(st), tx * 32 * 8, c, ty * 4, 0);
                 }
-                __syncwarp();
-                if (++st == P.n_stage) { st = 0; ph ^= 1; }
             }
+            __syncwarp();
+            if (++st == P.n_stage) { st = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
@@ -150,39 +124,25 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
         int st = 0;
         uint32_t ph = 0;
-        for (int i = 0; i < n_local; ++i, next_tile()) {
-            const int n_steps = cls_s[c].n_steps;
-            const uint64_t masks = *reinterpret_cast<const uint64_t*>(cls_s[c].mask);
+        for (int i = 0; i < n_local; ++i) {
             const int acc = i % G;
             mbar_wait(tempty_bar(acc), ((i / G) & 1) ^ 1);
+            mbar_wait(full_bar(st), ph);
+            tc_fence_after();
+            const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * A_STAGE, A_PLANE, SBO_A);
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C_OUT);
-            uint32_t accumulate = 0;
-            for (int s = 0; s < n_steps; ++s) {
-                const uint32_t mask = (uint32_t)(masks >> (16 * s)) & 0xFFFFu;
-                mbar_wait(full_bar(st), ph);
-                tc_fence_after();
-                const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * A_STAGE, A_PLANE, SBO_A);
-                if (leader) {
+            if (leader) {
 #pragma unroll
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        if (mask & (1u << tap)) {
-                            const uint32_t tap_off = TAPS == 9 ? (uint32_t)(((tap / 3) * kPitch + (tap % 3)) * 16) : 0u;
-#pragma unroll
-                            for (int j = 0; j < KSTEPS; ++j) {
-                                const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(2 * j) * A_PLANE + tap_off) >> 4);
-                                const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((tap * KCH + 2 * j) * C_OUT * 16) >> 4);
-                                umma_bf16(d_tmem, ad, bd, idesc, accumulate);
-                                accumulate = 1;
-                            }
-                        }
-                    }
-                    if (P.dbg & 4) mbar_arrive(empty_bar(st));      // diagnostics: stage released without tracking the MMAs
-                    else umma_commit(empty_bar(st));
-                    if (s == n_steps - 1) umma_commit(tfull_bar(acc));
+                for (int j = 0; j < KSTEPS; ++j) {
+                    const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(2 * j) * A_PLANE) >> 4);
+                    const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(2 * j * C_OUT * 16) >> 4);
+                    umma_bf16(d_tmem, ad, bd, idesc, j ? 1u : 0u);
                 }
-                __syncwarp();
-                if (++st == P.n_stage) { st = 0; ph ^= 1; }
+                umma_commit(empty_bar(st));
+                umma_commit(tfull_bar(acc));
             }
+            __syncwarp();
+            if (++st == P.n_stage) { st = 0; ph ^= 1; }
         }
     } else {
         // ------------------------------------------------ epilogue (G groups of 4 warps): BN affine + ReLU -> bf16 -> C8-planar stores
@@ -193,17 +153,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         const int64_t cstride = (int64_t)P.rows * P.cols * 8;
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (i % G != eg) continue;
-            int row, col;
-            if (TAPS == 9) {
-                row = cls_s[c].row0 + (ty * 16 + (m >> 3)) * RS;
-                col = tx * 8 + (m & 7);
-            } else {
-                row = ty * 4 + (m >> 5);
-                col = tx * 32 + (m & 31);
-            }
+            const int row = ty * 4 + (m >> 5), col = tx * 32 + (m & 31);
             const bool valid = row < P.rows && col < P.cols;
-            __nv_bfloat16* const obase =
-                P.out + ((((int64_t)cls_s[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
+            __nv_bfloat16* const obase = P.out + ((((int64_t)c * P.out_chunks) * P.rows + row) * P.cols + col) * 8;
             mbar_wait(tfull_bar(eg), (i / G) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -243,7 +195,6 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_dense_kernel(const __gri
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Fused conv3x3 + 2x2 max-pool: the pooled maps are the only thing written.

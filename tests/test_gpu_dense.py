@@ -114,13 +114,13 @@ def test_dense_layers_in_isolation(dmf, p, H, W, row0, nb):
         assert_close_bf16(got_b1, ref_block(ref.pan1, pp, True, quant_w=False), 'pan stem maps')
         # tensor-core layers, each fed with the dense path's own input
         got_ms2 = gather_patches(CAT, 32, dims, anchors, p // 2, 1, 2, 0, 16)
-        assert_close_bf16(got_ms2, ref_block(ref.ms2, got, True), 'ms2 (conv_dense + pool_s1)')
+        assert_close_bf16(got_ms2, ref_block(ref.ms2, got, True), 'ms2 (conv_pool4, stride-1 pool)')
         got_b2 = gather_patches(B2, 8, dims, anchors, p, 1, 1)
         assert_close_bf16(got_b2, ref_block(ref.pan2, got_b1, True), 'pan2 (conv_pool4: conv + aligned 2x2 max fused)')
         got_p3 = gather_patches(CAT, 32, dims, anchors, p // 2, 1, 2, 16, 16)
-        assert_close_bf16(got_p3, ref_block(ref.pan3, got_b2, True), 'pan3 (conv_dense + pool_s1)')
+        assert_close_bf16(got_p3, ref_block(ref.pan3, got_b2, True), 'pan3 (conv_pool4, stride-1 pool)')
         got_f = gather_patches(Fm, 16, dims, anchors, p // 2, 1, 2)
-        assert_close_bf16(got_f, ref_block(ref.fuse, torch.cat([got_ms2, got_p3], 1), False), 'fuse (conv_dense 1x1)')
+        assert_close_bf16(got_f, ref_block(ref.fuse, torch.cat([got_ms2, got_p3], 1), False), 'fuse (conv1x1_planes)')
     h.close()
 
 

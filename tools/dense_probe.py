@@ -1,4 +1,4 @@
-"""Stage timing of the scene-dense path on a synthetic scene: python tools/dense_probe.py [H W [band [reps]]]"""
+"""Stage timing of the scene-dense path on a synthetic scene: python tools/dense_probe.py [H W [band [reps [patch]]]]"""
 import json
 import os
 import sys
@@ -17,7 +17,7 @@ H = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 band = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-P, C = 16, 13
+P, C = (int(sys.argv[5]) if len(sys.argv) > 5 else 16), 13
 dev = 'cuda:0'
 ms, pan, label = orc.synthetic_scene(H, W, C - 1, seed=0, label_seed=1)
 torch.manual_seed(3407)
@@ -25,7 +25,7 @@ net = Net({'Categories_Number': C, 'patch_size': P, 'schedule': {'activate': 'Re
 h = net.native()
 sc = dmf.Scene.from_raw(ms, pan, P, dev)
 sc.set_labels(label)
-out = {'H': H, 'W': W, 'band': band}
+out = {'H': H, 'W': W, 'band': band, 'patch': P}
 h.set_dense(True, band)
 pm = torch.zeros((H, W), dtype=torch.uint8, device=dev)
 cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
