@@ -99,7 +99,46 @@ __global__ void __launch_bounds__(256) paint_kernel(const uint8_t* __restrict__ 
 
 using namespace dmf;
 
+// cm[pred_map[k]][label_map[k]] += 1 for the listed pixels: the confusion matrix of a loader's sample set taken from
+// whole-scene maps (Solver.test() after a scene-dense pass; order of the samples is irrelevant to the counts).
+__global__ void __launch_bounds__(256) confusion_at_kernel(const uint8_t* __restrict__ pred_map, const uint8_t* __restrict__ label_map,
+                                                           const int64_t* __restrict__ idx, int64_t N, int C,
+                                                           unsigned long long* __restrict__ cm) {
+    extern __shared__ unsigned int hist[];
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_iter = (N + stride - 1) / stride;
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t i = it * stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        bool ok = i < N;
+        int key = 0;
+        if (ok) {
+            const int64_t k = idx ? idx[i] : i;
+            const int pr = pred_map[k], t = label_map[k];
+            ok = pr < C && t < C;
+            key = pr * C + t;
+        }
+        hist_add_warp(hist, key, ok);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+        if (hist[i]) atomicAdd(&cm[i], (unsigned long long)hist[i]);
+}
+
 extern "C" {
+
+int dmf_confusion_at(const uint8_t* pred_map_dev, const uint8_t* label_map_dev, const int64_t* flat_idx_dev, int64_t N, int C,
+                     int64_t* cm_dev, void* stream) {
+    DMF_REQUIRE(pred_map_dev && label_map_dev && cm_dev && N >= 0, "confusion_at: bad argument");
+    DMF_REQUIRE(C >= 1 && C <= kMaxClasses, "confusion_at: 1 <= C <= %d", kMaxClasses);
+    if (N == 0) return DMF_OK;
+    const int grid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 8);
+    confusion_at_kernel<<<grid, 256, sizeof(unsigned int) * C * C, (cudaStream_t)stream>>>(pred_map_dev, label_map_dev, flat_idx_dev, N, C,
+                                                                                         (unsigned long long*)cm_dev);
+    DMF_LAUNCHED();
+    return DMF_OK;
+}
 
 int dmf_argmax_confusion(const float* logits_dev, const void* target_dev, int target_dtype, int64_t N, int C,
                          int64_t* pred_out_dev, int64_t* cm_dev, void* stream) {

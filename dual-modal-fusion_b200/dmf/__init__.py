@@ -263,6 +263,19 @@ def argmax_confusion(logits, target, C_, cm=None, want_pred=True):
     return pred, cm
 
 
+def confusion_at(pred_map, label_map, flat_idx, C_, cm=None):
+    """cm[pred_map[k]][label_map[k]] += 1 for k in flat_idx (int64 CUDA tensor; None = every pixel); u8 maps on the device."""
+    assert pred_map.is_cuda and pred_map.dtype == torch.uint8 and label_map.dtype == torch.uint8 and label_map.is_cuda
+    pred_map, label_map = pred_map.contiguous(), label_map.contiguous()
+    if cm is None:
+        cm = torch.zeros((C_, C_), dtype=torch.int64, device=pred_map.device)
+    idx = None if flat_idx is None else torch.as_tensor(flat_idx, dtype=torch.int64).to(pred_map.device).contiguous()
+    n = pred_map.numel() if idx is None else idx.numel()
+    with torch.cuda.device(pred_map.device):
+        check(lib.dmf_confusion_at(_ptr(pred_map), _ptr(label_map), _ptr(idx), n, C_, _ptr(cm), _stream()))
+    return cm
+
+
 def scatter_labels(label_map, x, y, pred):
     """K5a: label_map u8 [H,W] CUDA; x, y, pred int64 [N] (moved to the device if needed)."""
     dev = label_map.device

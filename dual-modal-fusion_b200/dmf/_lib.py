@@ -62,6 +62,7 @@ SIGNATURES = {
     'dmf_train_set_debug': (i32, [vp, i32]),
     'dmf_train_debug_op': (i32, [vp, i32, i32, i64, vp]),
     'dmf_argmax_confusion': (i32, [vp, vp, i32, i64, i32, vp, vp, vp]),
+    'dmf_confusion_at': (i32, [vp, vp, vp, i64, i32, vp, vp]),
     'dmf_scatter_labels': (i32, [vp, vp, vp, i64, vp, i32, vp]),
     'dmf_paint_labels': (i32, [vp, i64, vp, i32, vp, vp]),
 }

@@ -123,18 +123,32 @@ class Solver(BaseSolver):
 
     # ------------------------------------------------------------------ test
     def test(self):
+        """Confusion matrix of the test loader's sample set (solver/mainsolver.py:104-141).  Large sample sets are taken out of
+        one scene-dense pass over the whole scene (the counts do not depend on the order or batching of the samples); small
+        ones, and the reference's first-batch-only behaviour, run the loader batches through the per-patch kernels."""
         t0 = time.time()
         self._load_for_eval()
         C = self.cfg['Categories_Number']
         cm = torch.zeros((C, C), dtype=torch.int64, device=self.DEVICE)
         first_only = bool(self.cfg['test'].get('first_batch_only', False))
+        sharded = dist.is_available() and dist.is_initialized() and self.cfg.get('shard_test')
+        idx = getattr(self.test_loader, 'indices', None)
+        H, W = self.scene.H, self.scene.W
+        # dense whole-scene pass ~ 10x cheaper per pixel than a per-patch evaluation
+        dense = (not first_only and not sharded and idx is not None and getattr(self.cur_model, 'dense', False)
+                 and 8 * len(idx) >= H * W)
         with torch.no_grad():
-            for data1, data2, target, _, _ in self._bar(self.test_loader):
-                out = self.cur_model(data1, data2)
-                dmf.argmax_confusion(out, target, C, cm=cm, want_pred=False)
-                if first_only:
-                    break
-        if dist.is_available() and dist.is_initialized() and self.cfg.get('shard_test'):
+            if dense:
+                pred_map, _ = self.cur_model.infer_scene(self.scene, 0, H, cm=torch.zeros_like(cm))
+                label_dev = torch.from_numpy(np.asarray(self.label_np).astype(np.uint8)).to(self.DEVICE)
+                dmf.confusion_at(pred_map, label_dev, torch.from_numpy(np.asarray(idx, dtype=np.int64)), C, cm=cm)
+            else:
+                for data1, data2, target, _, _ in self._bar(self.test_loader):
+                    out = self.cur_model(data1, data2)
+                    dmf.argmax_confusion(out, target, C, cm=cm, want_pred=False)
+                    if first_only:
+                        break
+        if sharded:
             dist.all_reduce(cm)
         self.test_time = time.time() - t0
         self.test_matrix = cm.cpu().numpy().astype(np.float64)

@@ -222,6 +222,11 @@ int dmf_train_debug_op(dmf_train* t, int op, int layer, int64_t N, void* stream)
 int dmf_argmax_confusion(const float* logits_dev, const void* target_dev, int target_dtype, int64_t N,
                          int C, int64_t* pred_out_dev, int64_t* cm_dev, void* stream);
 
+/* The same matrix from whole-scene maps: cm[pred_map[k]][label_map[k]] += 1 for k in flat_idx (NULL = the first N pixels).
+ * Lets Solver.test() take its loader's sample set out of one scene-dense pass instead of running the network per sample. */
+int dmf_confusion_at(const uint8_t* pred_map_dev, const uint8_t* label_map_dev, const int64_t* flat_idx_dev, int64_t N,
+                     int C, int64_t* cm_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K5 colouring — replaces the scatter + paint loops of Solver.color()
  * (solver/mainsolver.py:171-173, 186-189).

@@ -177,3 +177,19 @@ def test_scene_update_in_place_matches_fresh_scene(dmf):
     torch.cuda.synchronize()
     eq(sc.export(0).cpu().numpy(), orc.data_padding(ms2, p).astype(np.float32))
     eq(sc.export(1).cpu().numpy(), orc.data_padding(pan2, p).astype(np.float32))
+
+
+def test_confusion_at_matches_oracle(dmf):
+    """cm[pred_map[k]][label_map[k]] over an index list == oracle.confusion on the same samples, bit for bit."""
+    g = np.random.default_rng(3)
+    H, W, C = 57, 91, 13
+    pm = g.integers(0, C, (H, W), dtype=np.uint8)
+    lab = g.integers(0, C, (H, W), dtype=np.uint8)
+    idx = g.choice(H * W, size=3000, replace=False)
+    pm_d, lab_d = torch.from_numpy(pm).to(DEV), torch.from_numpy(lab).to(DEV)
+    cm = dmf.confusion_at(pm_d, lab_d, torch.from_numpy(idx), C)
+    assert np.array_equal(cm.cpu().numpy().astype(np.float64), orc.confusion(pm.reshape(-1)[idx], lab.reshape(-1)[idx], C))
+    cm_all = dmf.confusion_at(pm_d, lab_d, None, C)
+    assert np.array_equal(cm_all.cpu().numpy().astype(np.float64), orc.confusion(pm.reshape(-1), lab.reshape(-1), C))
+    cm2 = dmf.confusion_at(pm_d, lab_d, torch.from_numpy(idx[:0]), C, cm=cm.clone())      # empty list: unchanged
+    assert torch.equal(cm2, cm)
