@@ -173,7 +173,7 @@ def main():
     ap.add_argument('--max-batch', type=int, default=16384)
     ap.add_argument('--mode', default='dense', choices=['dense', 'patch'],
                     help='whole-scene algorithm: scene-dense maps (default) or the per-patch kernels')
-    ap.add_argument('--band', type=int, default=256, help='anchor rows per pass of the dense path')
+    ap.add_argument('--band', type=int, default=512, help='anchor rows per pass of the dense path')
     ap.add_argument('--cpu-budget-s', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the secondary C4 training-step measurement')
@@ -393,7 +393,7 @@ def main():
         conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
         roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['bf16_tflops_sustained'],
-                'traffic': ncu_traffic('r01_dense_ncu_summary.json', ncu_key[name]) if args.band == 256 else None,
+                'traffic': ncu_traffic('r01_dense_ncu_summary.json', ncu_key[name]) if args.band == 512 else None,
                 'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
                 'avg_launch_ms': k_ms / (len(bands) * per_band), 'launches': len(bands) * per_band,
                 'flops_per_launch': fl_pos * pos / (len(bands) * per_band),

@@ -33,6 +33,7 @@ struct DenseWs {
     float* S = nullptr;                              // row sums of F for the separable average pool [3][16][R][W][8]
     float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
     __nv_bfloat16* w_pan2 = nullptr;                 // tap-major packing of pan2 (the per-patch path may use the row-pair one)
+    __nv_bfloat16* w_fc1 = nullptr;                  // fc1 weight as bf16 hi / lo parts [2][16][64][8] (B operand of the head's MMA)
     CUtensorMap mapA, mapB1, mapB2s, mapCAT;
     cudaEvent_t ev[12] = {};
     float stage_ms[12] = {};
@@ -168,8 +169,8 @@ __global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restri
 //     g = 1/(p/2)^2 * sum_{k,l} F[cls(k), cls(l)][x + 2k][y + 2l],      cls = first / interior / last cell,
 // evaluated separably: gap_rows_kernel forms the inner sums S[a][X][y] = sum_l F[a, cls(l)][X][y + 2l] once per map row
 // and row class a (fp32, [3][16][rows][W][8]); head_dense_kernel adds the p/2 rows S[cls(k)][x + 2k][y] of a pixel and
-// runs the two linears, the first-maximum argmax, the confusion matrix (per-block shared histogram -> 64-bit global
-// atomics) and the label map.  Summation order: l ascending inside a row, then k ascending.
+// runs the two linears (the first one on the tensor pipe), the first-maximum argmax, the confusion matrix (per-block shared
+// histogram -> 64-bit global atomics) and the label map.  Summation order: l ascending inside a row, then k ascending.
 template <int P2>
 __global__ void __launch_bounds__(256) gap_rows_kernel(const uint4* __restrict__ F, int R1, int C1, int rows, int W, float4* __restrict__ S) {
     const int64_t total = (int64_t)3 * 16 * rows * W;
@@ -208,47 +209,86 @@ __global__ void __launch_bounds__(256) gap_rows_kernel(const uint4* __restrict__
     }
 }
 
-// One block = 64 consecutive pixels of one anchor row.  Phase 1: warp w = channel chunk w, lane = pixel (two passes of 32
-// pixels): the p/2 row sums are added.  Phase 2: warp w owns pixels 4w..4w+3: both linears with the weights in shared
-// memory, each weight load shared by the 4 pixels (11 instructions per 8 FMAs).
-constexpr int kDenseHeadThreads = 512, kHeadPx = 64;
+// One block = 128 consecutive pixels of one anchor row.
+//   phase 1 (8 warps): warp w = channel chunks w and w + 8, lane = pixel (4 passes of 32): the p/2 row sums are added, scaled and written
+//     to shared memory as the A operand of the first linear, split into bf16 hi + lo parts (g = hi + lo to ~2^-17);
+//   phase 2 (one elected thread): Linear 128->64 on the tensor pipe, 8 k-steps x 3 tcgen05.mma M128 x N64 x K16
+//     (g_hi.w_hi + g_lo.w_hi + g_hi.w_lo: fp32-grade products, fp32 accumulation in 64 TMEM columns);
+//   phase 3 (4 warps, thread = pixel = TMEM lane): + bias, ReLU, Linear 64->C from shared-memory weights (k ascending),
+//     first-maximum argmax, logits / label map / confusion matrix (warp-aggregated shared histogram).
+constexpr int kDenseHeadThreads = 256, kHeadPx = 128;        // 8 warps x <= 128 registers: two blocks per SM
+constexpr uint32_t kHeadAPlane = kHeadPx * 16;                       // one 8-channel chunk of the A operand
+constexpr uint32_t kHeadABytes = (C_FUSE / 8) * kHeadAPlane;         // 32 KB per hi / lo part
+constexpr uint32_t kHeadWBytes = (C_FUSE / 8) * C_HID * 16;          // 16 KB per hi / lo part
 static size_t dense_head_smem(int C) {
-    return sizeof(float) * (C_FUSE * C_HID + C_HID * C + C_HID + ((C + 3) & ~3) + C_FUSE * kHeadPx + (kDenseHeadThreads / 32) * C_HID * 4) +
-           sizeof(unsigned int) * C * C;
+    const int Cp = (C + 3) & ~3;
+    return 2 * kHeadABytes + 2 * kHeadWBytes + sizeof(float) * (C_HID + C_HID * Cp + Cp) + sizeof(unsigned int) * C * C + 64;
+}
+
+__device__ __forceinline__ void hist_add_warp(unsigned int* hist, int key, bool valid) {
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned peers = __match_any_sync(active, key);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[key], __popc(peers));
 }
 
 template <int P2>
-__global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const float4* __restrict__ S, int rows, int nb, int W, int C,
-                                                                       const float* __restrict__ fc1t, const float* __restrict__ fc1b,
-                                                                       const float* __restrict__ fc2t, const float* __restrict__ fc2b,
+__global__ void __launch_bounds__(kDenseHeadThreads, 2) head_dense_kernel(const float4* __restrict__ S, int rows, int nb, int W, int C,
+                                                                       const __nv_bfloat16* __restrict__ w1_hilo /* [2][16][64][8] */,
+                                                                       const float* __restrict__ fc1b, const float* __restrict__ fc2t,
+                                                                       const float* __restrict__ fc2b,
                                                                        int64_t pix0 /* flat index of the band's first pixel */,
                                                                        const uint8_t* __restrict__ label, float* __restrict__ logits_out,
                                                                        unsigned long long* __restrict__ cm, uint8_t* __restrict__ pred_map) {
-    extern __shared__ __align__(16) float hs[];
-    float* w1 = hs;                                   // [128][64]
-    float* w2 = w1 + C_FUSE * C_HID;                  // [64][C]
-    float* b1 = w2 + C_HID * C;
-    float* b2 = b1 + C_HID;
-    float* gbuf = b2 + ((C + 3) & ~3);                // [128 channels][64 pixels]
-    float* hidb = gbuf + C_FUSE * kHeadPx;            // per warp [64 hidden][4 pixels]
-    unsigned int* hist = reinterpret_cast<unsigned int*>(hidb + (kDenseHeadThreads / 32) * C_HID * 4);
-    for (int i = threadIdx.x; i < C_FUSE * C_HID; i += blockDim.x) w1[i] = fc1t[i];
-    for (int i = threadIdx.x; i < C_HID * C; i += blockDim.x) w2[i] = fc2t[i];
-    if (threadIdx.x < C_HID) b1[threadIdx.x] = fc1b[threadIdx.x];
-    if (threadIdx.x < C) b2[threadIdx.x] = fc2b[threadIdx.x];
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
+    extern __shared__ __align__(1024) uint8_t hsm[];
+    uint8_t* a_hi = hsm;                                       // [16 chunks][128 px][8] bf16 — K-major, no swizzle
+    uint8_t* a_lo = a_hi + kHeadABytes;
+    uint8_t* w_hi = a_lo + kHeadABytes;                        // [16 chunks][64 out][8] bf16
+    uint8_t* w_lo = w_hi + kHeadWBytes;
+    const int Cp = (C + 3) & ~3;
+    float* b1 = reinterpret_cast<float*>(w_lo + kHeadWBytes);
+    float* w2 = b1 + C_HID;                                    // [64][Cp]
+    float* b2 = w2 + C_HID * Cp;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(b2 + Cp);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(hist + C * C + ((C * C) & 1));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (int)(2 * kHeadWBytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(w_hi)[i] = __ldg(reinterpret_cast<const uint4*>(w1_hilo) + i);
+    if (threadIdx.x < C_HID) b1[threadIdx.x] = fc1b[threadIdx.x];
+    for (int i = threadIdx.x; i < C_HID * Cp; i += blockDim.x) {
+        const int k = i / Cp, c = i - k * Cp;
+        w2[i] = c < C ? fc2t[k * C + c] : 0.f;
+    }
+    if (threadIdx.x < Cp) b2[threadIdx.x] = threadIdx.x < C ? fc2b[threadIdx.x] : 0.f;
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+    const uint32_t bar_a = tc::smem_u32(bar);
+    if (threadIdx.x == 0) {
+        tc::mbar_init(bar_a, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the weight copies above feed the tensor pipe
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
     const float inv = 1.0f / (float)(P2 * P2);
     const int segs = (W + kHeadPx - 1) / kHeadPx;
     const int n_seg = nb * segs;
-    float* hid = hidb + warp * C_HID * 4;
+    uint32_t phase = 0;
     for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
         const int xl = seg / segs, y0 = (seg - xl * segs) * kHeadPx;
-        // ---- phase 1: column sums of the row sums
-#pragma unroll
-        for (int half = 0; half < kHeadPx / 32; ++half) {
-            const int px = half * 32 + lane, y = y0 + px;
+        // ---- phase 1: column sums of the row sums -> A operand (hi / lo)
+#pragma unroll 1
+        for (int it = 0; it < 2 * (kHeadPx / 32); ++it) {
+            const int chunk = warp + 8 * (it & 1), pass = it >> 1;
+            const int px = pass * 32 + lane, y = y0 + px;
             float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (y < W) {
 #pragma unroll
@@ -257,7 +297,7 @@ __global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const flo
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int k = k0 + e, a = k == 0 ? 0 : (k == P2 - 1 ? 2 : 1);
-                        const float4* q = S + ((((int64_t)a * 16 + warp) * rows + xl + 2 * k) * W + y) * 2;
+                        const float4* q = S + ((((int64_t)a * 16 + chunk) * rows + xl + 2 * k) * W + y) * 2;
                         v[e][0] = __ldg(q);
                         v[e][1] = __ldg(q + 1);
                     }
@@ -268,88 +308,100 @@ __global__ void __launch_bounds__(kDenseHeadThreads) head_dense_kernel(const flo
                     }
                 }
             }
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gbuf[(warp * 8 + j) * kHeadPx + px] = s[j] * inv;
-        }
-        __syncthreads();
-        // ---- phase 2: pixels 4*warp .. 4*warp+3
-        if (y0 + 4 * warp < W) {
-            float h0[4], h1[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { h0[e] = b1[lane]; h1[e] = b1[lane + 32]; }
-#pragma unroll 8
-            for (int k = 0; k < C_FUSE; ++k) {
-                const float4 g = *reinterpret_cast<const float4*>(gbuf + k * kHeadPx + 4 * warp);
-                const float wa = w1[k * C_HID + lane], wb = w1[k * C_HID + lane + 32];
-                h0[0] = fmaf(g.x, wa, h0[0]); h1[0] = fmaf(g.x, wb, h1[0]);
-                h0[1] = fmaf(g.y, wa, h0[1]); h1[1] = fmaf(g.y, wb, h1[1]);
-                h0[2] = fmaf(g.z, wa, h0[2]); h1[2] = fmaf(g.z, wb, h1[2]);
-                h0[3] = fmaf(g.w, wa, h0[3]); h1[3] = fmaf(g.w, wb, h1[3]);
+            for (int j = 0; j < 4; ++j) {
+                const float g0 = s[2 * j] * inv, g1 = s[2 * j + 1] * inv;
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1);
+                hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lo[j] = tc::pack_bf16x2(g0 - __bfloat162float(h0), g1 - __bfloat162float(h1));
             }
-            *reinterpret_cast<float4*>(hid + lane * 4) = make_float4(fmaxf(h0[0], 0.f), fmaxf(h0[1], 0.f), fmaxf(h0[2], 0.f), fmaxf(h0[3], 0.f));
-            *reinterpret_cast<float4*>(hid + (lane + 32) * 4) = make_float4(fmaxf(h1[0], 0.f), fmaxf(h1[1], 0.f), fmaxf(h1[2], 0.f), fmaxf(h1[3], 0.f));
+            *reinterpret_cast<uint4*>(a_hi + (uint32_t)chunk * kHeadAPlane + (uint32_t)px * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(a_lo + (uint32_t)chunk * kHeadAPlane + (uint32_t)px * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (tensor pipe) reads
+        __syncthreads();
+        // ---- phase 2: Linear 128 -> 64 on the tensor pipe
+        if (warp == 1) {
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                constexpr uint32_t idesc = tc::umma_idesc_bf16(128, C_HID);
+                const uint64_t ah = tc::umma_desc(tc::smem_u32(a_hi), kHeadAPlane, 128), al = tc::umma_desc(tc::smem_u32(a_lo), kHeadAPlane, 128);
+                const uint64_t wh = tc::umma_desc(tc::smem_u32(w_hi), C_HID * 16, 128), wl = tc::umma_desc(tc::smem_u32(w_lo), C_HID * 16, 128);
+#pragma unroll
+                for (int j = 0; j < C_FUSE / 16; ++j) {
+                    const uint64_t ao = (uint64_t)((2u * j * kHeadAPlane) >> 4), wo = (uint64_t)((2u * j * C_HID * 16) >> 4);
+                    tc::umma_bf16(tmem_base, ah + ao, wh + wo, idesc, j ? 1u : 0u);
+                    tc::umma_bf16(tmem_base, al + ao, wh + wo, idesc, 1u);
+                    tc::umma_bf16(tmem_base, ah + ao, wl + wo, idesc, 1u);
+                }
+                tc::umma_commit(bar_a);
+            }
             __syncwarp();
-            // logits: classes lane and lane + 32 (C <= 64) of the 4 pixels
-            float l0[4], l1[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { l0[e] = -INFINITY; l1[e] = -INFINITY; }
-            if (lane < C) {
-                float a[4] = {b2[lane], b2[lane], b2[lane], b2[lane]};
-#pragma unroll 8
-                for (int k = 0; k < C_HID; ++k) {
-                    const float4 hv = *reinterpret_cast<const float4*>(hid + k * 4);
-                    const float w = w2[k * C + lane];
-                    a[0] = fmaf(hv.x, w, a[0]); a[1] = fmaf(hv.y, w, a[1]); a[2] = fmaf(hv.z, w, a[2]); a[3] = fmaf(hv.w, w, a[3]);
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) l0[e] = a[e];
-            }
-            if (lane + 32 < C) {
-                float a[4] = {b2[lane + 32], b2[lane + 32], b2[lane + 32], b2[lane + 32]};
-#pragma unroll 8
-                for (int k = 0; k < C_HID; ++k) {
-                    const float4 hv = *reinterpret_cast<const float4*>(hid + k * 4);
-                    const float w = w2[k * C + lane + 32];
-                    a[0] = fmaf(hv.x, w, a[0]); a[1] = fmaf(hv.y, w, a[1]); a[2] = fmaf(hv.z, w, a[2]); a[3] = fmaf(hv.w, w, a[3]);
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) l1[e] = a[e];
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int y = y0 + 4 * warp + e;
-                if (y < W) {                                                  // warp-uniform
-                    const int64_t n = (int64_t)xl * W + y;                    // pixel index inside the band
-                    if (logits_out) {
-                        if (lane < C) logits_out[n * C + lane] = l0[e];
-                        if (lane + 32 < C) logits_out[n * C + lane + 32] = l1[e];
-                    }
-                    // argmax with torch.max semantics: the first (lowest) index among equal maxima
-                    float bv = l0[e];
-                    int bi = lane;
-                    if (l1[e] > bv) { bv = l1[e]; bi = lane + 32; }
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                    }
-                    if (lane == 0) {
-                        const int64_t kflat = pix0 + n;
-                        if (pred_map) pred_map[kflat] = (uint8_t)bi;
-                        if (cm) {
-                            const int lab = label[kflat];
-                            if (lab < C) atomicAdd(&hist[bi * C + lab], 1u);
-                        }
-                    }
-                }
-            }
         }
-        __syncthreads();
+        // ---- phase 3: thread = pixel
+        if (warp < 4) {
+            tc::mbar_wait(bar_a, phase);
+            tc::tc_fence_after();
+            const int px = warp * 32 + lane, y = y0 + px;
+            const bool live = y < W;
+            float hid[C_HID];
+            {
+                uint32_t v[32];
+                const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+                tc::tmem_ld32(t_row, v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) hid[k] = fmaxf(__uint_as_float(v[k]) + b1[k], 0.f);
+                tc::tmem_ld32(t_row + 32, v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) hid[32 + k] = fmaxf(__uint_as_float(v[k]) + b1[32 + k], 0.f);
+            }
+            tc::tc_fence_before();
+            const int64_t n = (int64_t)xl * W + y;                          // pixel index inside the band
+            float bv = -INFINITY;
+            int bi = 0;
+            for (int c4 = 0; c4 < C; c4 += 4) {
+                float4 a = *reinterpret_cast<const float4*>(b2 + c4);
+#pragma unroll
+                for (int k = 0; k < C_HID; ++k) {
+                    const float4 w = *reinterpret_cast<const float4*>(w2 + k * Cp + c4);
+                    a.x = fmaf(hid[k], w.x, a.x); a.y = fmaf(hid[k], w.y, a.y); a.z = fmaf(hid[k], w.z, a.z); a.w = fmaf(hid[k], w.w, a.w);
+                }
+                const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (c4 + e < C) {
+                        if (live && logits_out) logits_out[n * C + c4 + e] = av[e];
+                        if (av[e] > bv) { bv = av[e]; bi = c4 + e; }           // strict >: the first maximum (torch.max semantics)
+                    }
+                }
+            }
+            int key = 0;
+            bool count = false;
+            if (live) {
+                const int64_t kflat = pix0 + n;
+                if (pred_map) pred_map[kflat] = (uint8_t)bi;
+                if (cm) {
+                    const int lab = label[kflat];
+                    count = lab < C;
+                    key = bi * C + lab;
+                }
+            }
+            if (cm) hist_add_warp(hist, key, count);
+        }
+        phase ^= 1;
+        __syncthreads();                                                   // A operand and TMEM columns are free again
     }
+    __syncthreads();
     if (cm)
         for (int i = threadIdx.x; i < C * C; i += blockDim.x)
             if (hist[i]) atomicAdd(&cm[i], (unsigned long long)hist[i]);
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -477,6 +529,18 @@ int dense_pack(dmf_net* n) {
                 pk[(((size_t)tap * (C_PAN1 / 8) + ci / 8) * C_PAN2 + co) * 8 + ci % 8] =
                     __float2bfloat16_rn((*w2)[((size_t)co * C_PAN1 + ci) * 9 + tap]);
     DMF_TRY(to_device(&d->w_pan2, pk));
+    auto* f1 = param(n, "fc1.weight", (size_t)C_HID * C_FUSE);
+    if (!f1) return DMF_ERR_STATE;
+    std::vector<__nv_bfloat16> hl((size_t)2 * C_FUSE * C_HID);
+    for (int o = 0; o < C_HID; ++o)
+        for (int k = 0; k < C_FUSE; ++k) {
+            const float w = (*f1)[(size_t)o * C_FUSE + k];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+            const size_t at = ((size_t)(k / 8) * C_HID + o) * 8 + k % 8;
+            hl[at] = hi;
+            hl[(size_t)C_FUSE * C_HID + at] = __float2bfloat16_rn(w - __bfloat162float(hi));
+        }
+    DMF_TRY(to_device(&d->w_fc1, hl));
     return DMF_OK;
 }
 
@@ -494,7 +558,7 @@ void dense_release(dmf_net* n) {
     if (!n->dense) return;
     DenseWs* d = n->dense;
     dense_free_ws(d);
-    cudaFree(d->w_ms1); cudaFree(d->w_pan1); cudaFree(d->w_pan2);
+    cudaFree(d->w_ms1); cudaFree(d->w_pan1); cudaFree(d->w_pan2); cudaFree(d->w_fc1);
     for (auto& e : d->ev) if (e) cudaEventDestroy(e);
     delete d;
     n->dense = nullptr;
@@ -593,8 +657,8 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             const int n_seg = nb * ((W + kHeadPx - 1) / kHeadPx);
             const int64_t off = (int64_t)(b0 - row0) * W;
             auto kern = p == 8 ? head_dense_kernel<4> : p == 16 ? head_dense_kernel<8> : head_dense_kernel<16>;
-            kern<<<std::min(n_seg, 2 * num_sms()), kDenseHeadThreads, dense_head_smem(n->C), st>>>(      // 2 blocks per SM (86 KB each)
-                reinterpret_cast<const float4*>(d->S), rows, nb, W, n->C, n->fc1t, n->fc1b, n->fc2t, n->fc2b, (int64_t)b0 * W, s->label,
+            kern<<<std::min(n_seg, 2 * num_sms()), kDenseHeadThreads, dense_head_smem(n->C), st>>>(      // 2 blocks per SM (~100 KB each)
+                reinterpret_cast<const float4*>(d->S), rows, nb, W, n->C, d->w_fc1, n->fc1b, n->fc2t, n->fc2b, (int64_t)b0 * W, s->label,
                 logits_dev ? logits_dev + off * n->C : nullptr, reinterpret_cast<unsigned long long*>(cm_dev), pred_map_dev);
             DMF_LAUNCHED();
         }

@@ -41,7 +41,7 @@ struct dmf_net {
     cudaEvent_t ev[8] = {};
     float stage_ms[8] = {};
     dmf::DenseWs* dense = nullptr;
-    int dense_band = 256;     // anchor rows per band of the dense path
+    int dense_band = 512;     // anchor rows per band of the dense path
     int dense_mode = 1;       // dmf_infer_scene: 1 = scene-dense maps, 0 = per-patch kernels
 };
 

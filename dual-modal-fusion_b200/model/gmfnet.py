@@ -68,7 +68,7 @@ class Net(nn.Module):
         self.max_train_batch = int(b200.get('max_train_batch', max(512, int(args.get('batchsize', 0) or 0))))
         # whole-scene inference: scene-dense maps (default) or the per-patch kernels; anchor rows per dense pass
         self.dense = bool(b200.get('dense', True))
-        self.dense_band = int(b200.get('dense_band', 256))
+        self.dense_band = int(b200.get('dense_band', 512))
         for name, (cin, cout) in WIDTHS.items():
             setattr(self, name, _conv_bn(cin, cout, 3))
         self.fuse = _conv_bn(128 + 128, C_FUSE, 1)

@@ -146,3 +146,28 @@ def test_patch_loader_index_order_matches_reference_run(golden):
     first = next(iter(loader))
     assert np.array_equal(first // W, g['train_batch0_x']) and np.array_equal(first % W, g['train_batch0_y'])
     assert len(loader) == 2
+
+
+def test_band_slice_reproduces_whole_scene_windows():
+    """A rank that holds only rows band_slice(H, p, r0, r1) of the scene (dmf.band_slice, bench.py e2e arm at N > 1) sees, after
+    the reference's reflect padding of ITS rows, the same windows as the whole padded scene for every anchor of [r0, r1)."""
+    from dmf import band_slice
+    rng = np.random.default_rng(0)
+    for H, p, world in [(45, 16, 3), (20, 16, 2), (33, 16, 1), (10, 16, 2), (64, 8, 5), (100, 32, 3), (17, 16, 17)]:
+        W = 5
+        scene = rng.random((H, W))
+        whole = np.pad(scene, ((0, p - 1), (0, 0)), mode='reflect') if H > 1 else np.repeat(scene, p, 0)
+        covered = np.zeros(H, dtype=int)
+        for rank in range(world):
+            step = -(-H // world)
+            r0, r1 = min(H, rank * step), min(H, (rank + 1) * step)
+            if r0 == r1:
+                continue
+            s0, s1 = band_slice(H, p, r0, r1)
+            assert 0 <= s0 <= r0 and r1 <= s1 <= H
+            band = scene[s0:s1]
+            band_pad = np.pad(band, ((0, p - 1), (0, 0)), mode='reflect') if band.shape[0] > 1 else np.repeat(band, p, 0)
+            for x in range(r0, r1):
+                assert np.array_equal(band_pad[x - s0:x - s0 + p], whole[x:x + p]), (H, p, world, rank, x)
+            covered[r0:r1] += 1
+        assert (covered == 1).all()

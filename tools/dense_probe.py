@@ -15,7 +15,7 @@ from oracle import dmf_oracle as orc
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-band = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+band = int(sys.argv[3]) if len(sys.argv) > 3 else 512
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 P, C = (int(sys.argv[5]) if len(sys.argv) > 5 else 16), 13
 dev = 'cuda:0'
