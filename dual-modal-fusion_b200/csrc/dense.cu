@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restri
     const int C2 = 2 * C1;
     __shared__ float w_s[8][9], sc_s[8], sh_s[8];
     const int ch = blockIdx.y;
-    for (int i = threadIdx.x; i < 72; i += blockDim.x) w_s[i / 9][i % 9] = w[ch * 72 + i];
-    if (threadIdx.x < 8) { sc_s[threadIdx.x] = scale[ch * 8 + threadIdx.x]; sh_s[threadIdx.x] = shift[ch * 8 + threadIdx.x]; }
+    for (int i = threadIdx.x; i < 72; i += blockDim.x) w_s[i / 9][i % 9] = scale[ch * 8 + i / 9] < 0.f ? -w[ch * 72 + i] : w[ch * 72 + i];
+    if (threadIdx.x < 8) { sc_s[threadIdx.x] = fabsf(scale[ch * 8 + threadIdx.x]); sh_s[threadIdx.x] = shift[ch * 8 + threadIdx.x]; }
     __syncthreads();
     const int64_t total = (int64_t)rows * C2;
     const int64_t plane = (int64_t)R1 * C1;
@@ -129,38 +129,60 @@ __global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restri
                 const int xx = 2 * PX - 1 + a, yy = 2 * PY - 1 + b;
                 xw[a][b] = (xx >= 0 && xx < H4p && yy >= 0 && yy < W4p) ? __ldg(pan + (int64_t)xx * pitch + yy) : 0.f;
             }
-        uint32_t out[9][4];
+        const int pr = Ul & 1, pc = PY & 1;                       // u0 is even: band-local and absolute row parity agree
+        uint32_t out[4][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float s[2][2][9];            // masked sums of the 4 conv positions of this pooled cell
+            // sv[a][b][re][ce]: conv position (a, b) of the pooled cell with its row (column) taps masked as on the patch edge
+            // that position can touch (a = 0: first row, a = 1: last row) when re (ce) = 0, unmasked when 1.  A pooled variant
+            // only ever combines these 4 of the 9 border classes of a position.
+            float sv[2][2][2][2];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    float t[9];
+                    float u[3][2];                   // u[dy][ce]
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) t[k] = xw[a + k / 3][b + k % 3] * w_s[j][k];
-                    masked_sums(t, s[a][b]);
+                    for (int d = 0; d < 3; ++d) {
+                        const float t0 = xw[a + d][b] * w_s[j][3 * d], t1 = xw[a + d][b + 1] * w_s[j][3 * d + 1], t2 = xw[a + d][b + 2] * w_s[j][3 * d + 2];
+                        u[d][0] = b == 0 ? t1 + t2 : t0 + t1;          // edge column class: no dx = -1 (left) / no dx = +1 (right)
+                        u[d][1] = b == 0 ? u[d][0] + t0 : u[d][0] + t2;
+                    }
+#pragma unroll
+                    for (int ce = 0; ce < 2; ++ce) {
+                        sv[a][b][0][ce] = a == 0 ? u[1][ce] + u[2][ce] : u[0][ce] + u[1][ce];   // edge row class: no dy = -1 (top) / no dy = +1 (bottom)
+                        sv[a][b][1][ce] = a == 0 ? sv[a][b][0][ce] + u[0][ce] : sv[a][b][0][ce] + u[2][ce];
+                    }
                 }
+            // A cell on an even pooled row can only be the FIRST pooled row of a patch (u = 0) or an interior one, a cell on an odd
+            // row only the LAST (u = 2p-1) or interior; columns likewise: 2 x 2 of the 9 variants exist per phase, the others are
+            // never read (conv_pool4_kernel's class table) and are neither computed nor stored.
 #pragma unroll
-            for (int ey = 0; ey < 3; ++ey)
+            for (int er = 0; er < 2; ++er)
 #pragma unroll
-                for (int ex = 0; ex < 3; ++ex) {
-                    const int ra = ey == 0 ? 0 : 1, rb = ey == 2 ? 2 : 1, ca = ex == 0 ? 0 : 1, cb = ex == 2 ? 2 : 1;
-                    float m = fmaf(s[0][0][ra * 3 + ca], sc_s[j], sh_s[j]);
-                    m = fmaxf(m, fmaf(s[0][1][ra * 3 + cb], sc_s[j], sh_s[j]));
-                    m = fmaxf(m, fmaf(s[1][0][rb * 3 + ca], sc_s[j], sh_s[j]));
-                    m = fmaxf(m, fmaf(s[1][1][rb * 3 + cb], sc_s[j], sh_s[j]));
-                    const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(m, 0.f)));
-                    const int v = ey * 3 + ex;
-                    if (j & 1) out[v][j >> 1] |= bits << 16;
-                    else out[v][j >> 1] = bits;
+                for (int ec = 0; ec < 2; ++ec) {
+                    // er = 0: this cell's edge row variant (first if pr == 0, last if pr == 1); er = 1: interior.  The upper conv row
+                    // is masked for "first", the lower one for "last".
+                    const int r0e = (er == 0 && pr == 0) ? 0 : 1, r1e = (er == 0 && pr == 1) ? 0 : 1;
+                    const int c0e = (ec == 0 && pc == 0) ? 0 : 1, c1e = (ec == 0 && pc == 1) ? 0 : 1;
+                    const float m = fmaxf(fmaxf(r0e ? (c0e ? sv[0][0][1][1] : sv[0][0][1][0]) : (c0e ? sv[0][0][0][1] : sv[0][0][0][0]),
+                                                r0e ? (c1e ? sv[0][1][1][1] : sv[0][1][1][0]) : (c1e ? sv[0][1][0][1] : sv[0][1][0][0])),
+                                          fmaxf(r1e ? (c0e ? sv[1][0][1][1] : sv[1][0][1][0]) : (c0e ? sv[1][0][0][1] : sv[1][0][0][0]),
+                                                r1e ? (c1e ? sv[1][1][1][1] : sv[1][1][1][0]) : (c1e ? sv[1][1][0][1] : sv[1][1][0][0])));
+                    // BN after the max: the weights carry sign(scale), sc_s holds |scale| (max commutes with a non-negative scale)
+                    const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(fmaf(m, sc_s[j], sh_s[j]), 0.f)));
+                    if (j & 1) out[er * 2 + ec][j >> 1] |= bits << 16;
+                    else out[er * 2 + ec][j >> 1] = bits;
                 }
         }
-        const int ph = (Ul & 1) * 2 + (PY & 1);                   // u0 is even: band-local and absolute row parity agree
-        uint4* o = reinterpret_cast<uint4*>(B1) + (((int64_t)ph * 4 + ch) * R1 + (Ul >> 1)) * C1 + (PY >> 1);
+        uint4* o = reinterpret_cast<uint4*>(B1) + (((int64_t)(pr * 2 + pc) * 4 + ch) * R1 + (Ul >> 1)) * C1 + (PY >> 1);
 #pragma unroll
-        for (int v = 0; v < 9; ++v) o[(int64_t)v * 16 * plane] = make_uint4(out[v][0], out[v][1], out[v][2], out[v][3]);
+        for (int er = 0; er < 2; ++er)
+#pragma unroll
+            for (int ec = 0; ec < 2; ++ec) {
+                const int v = (er ? 1 : (pr ? 2 : 0)) * 3 + (ec ? 1 : (pc ? 2 : 0));
+                o[(int64_t)v * 16 * plane] = make_uint4(out[er * 2 + ec][0], out[er * 2 + ec][1], out[er * 2 + ec][2], out[er * 2 + ec][3]);
+            }
     }
 }
 
