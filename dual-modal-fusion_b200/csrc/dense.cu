@@ -589,7 +589,7 @@ void dense_release(dmf_net* n) {
 // workspace for bands of `band` anchor rows of a scene W pixels wide
 static int dense_prepare(dmf_net* n, int W, int band) {
     DenseWs* d = n->dense;
-    if (d->A && d->W == W && d->band == band && d->p == n->p) return DMF_OK;
+    if (d->A && d->W == W && band <= d->band && d->p == n->p) return DMF_OK;      // a smaller band runs inside the existing planes
     DMF_CUDA(cudaDeviceSynchronize());
     dense_free_ws(d);
     const int p = n->p;

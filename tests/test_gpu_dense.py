@@ -214,3 +214,19 @@ def test_band_scene_equals_whole_scene(dmf, H, world):
         cm_sum += cm_b
     assert torch.equal(cm_sum, cm_w)
     h.close()
+
+
+@pytest.mark.parametrize('p,H,W', [(8, 1, 1), (16, 3, 200), (16, 130, 5)])
+def test_dense_degenerate_scene_shapes(dmf, p, H, W):
+    """Scenes smaller than a tile / a head segment, single rows and columns: same label map as the per-patch kernels."""
+    C = 5
+    ms, pan, label, sc, ref, h = scene_and_net(dmf, p, H, W, C, seed=21)
+    h.set_dense(True, band_rows=64)
+    pm_d, cm_d, lg_d = h.infer_scene(sc, want_logits=True)
+    h.set_dense(False)
+    pm_p, cm_p, lg_p = h.infer_scene(sc, want_logits=True)
+    torch.cuda.synchronize()
+    assert int(cm_d.sum()) == H * W
+    assert float((lg_d - lg_p).abs().max()) <= LOGIT_ATOL + LOGIT_RTOL * float(lg_p.abs().max())
+    assert float((pm_d == pm_p).float().mean()) >= 0.999
+    h.close()
