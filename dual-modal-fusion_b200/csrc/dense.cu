@@ -32,7 +32,10 @@ struct DenseWs {
     __nv_bfloat16 *A = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr, *F = nullptr;
     float* S = nullptr;                              // row sums of F for the separable average pool [3][16][R][W][8]
     float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
-    __nv_bfloat16* w_pan2 = nullptr;                 // tap-major packing of pan2 (the per-patch path may use the row-pair one)
+    // conv + pool layers (ms2, pan2, pan3): tap-major bf16 weights with sign(BN scale) folded into every output channel, |scale|,
+    // shift — conv_pool4_kernel takes the max over the pooling window BEFORE the affine
+    __nv_bfloat16* w_cp[3] = {nullptr, nullptr, nullptr};
+    float *sc_cp[3] = {nullptr, nullptr, nullptr}, *sh_cp[3] = {nullptr, nullptr, nullptr};
     __nv_bfloat16* w_fc1 = nullptr;                  // fc1 weight as bf16 hi / lo parts [2][16][64][8] (B operand of the head's MMA)
     CUtensorMap mapA, mapB1, mapB2s, mapCAT;
     cudaEvent_t ev[12] = {};
@@ -477,14 +480,15 @@ static int build_pool4_cls(tc::Pool4Cls& c, int a, int b, bool aligned, int box_
             c.box_drow[k] = (int8_t)rs[i].origin;
             c.box_dcol[k] = (int8_t)cs[j].origin;
         }
-    for (int tap = 0; tap < 9; ++tap)
-        for (int sub = 0; sub < 4; ++sub) {
-            const int orow = (sub >> 1) + tap / 3 - 1, ocol = (sub & 1) + tap % 3 - 1;
+    // A window at offset (orow, ocol) from the cell origin, shared by every (sub-position, tap) pair that reads it
+    for (int orow = -1; orow <= 2; ++orow)
+        for (int ocol = -1; ocol <= 2; ++ocol) {
+            const int wi = (orow + 1) * 4 + ocol + 1;
             const int i = r_of[orow + 1], j = c_of[ocol + 1];
-            if (i < 0 || j < 0) { c.off[tap * 4 + sub] = -1; continue; }
+            if (i < 0 || j < 0) { c.win[wi] = -1; continue; }
             const int dr = r_sh[orow + 1] - rs[i].origin, dc = c_sh[ocol + 1] - cs[j].origin;
             if (dr < 0 || dr + 16 > box_rows || dc < 0 || dc + 8 > box_cols) { set_error("pool4 class (%d,%d): window outside its box", a, b); return DMF_ERR_STATE; }
-            c.off[tap * 4 + sub] = (int16_t)(((uint32_t)(i * nc + j) * box_slot + (uint32_t)(dr * box_cols + dc) * 16) >> 4);
+            c.win[wi] = (int16_t)(((uint32_t)(i * nc + j) * box_slot + (uint32_t)(dr * box_cols + dc) * 16) >> 4);
         }
     return DMF_OK;
 }
@@ -540,17 +544,28 @@ int dense_pack(dmf_net* n) {
     DenseWs* d = n->dense;
     auto* w1 = param(n, "ms1.0.weight", (size_t)C_MS1 * 4 * 9);
     auto* wp = param(n, "pan1.0.weight", (size_t)C_PAN1 * 9);
-    auto* w2 = param(n, "pan2.0.weight", (size_t)C_PAN2 * C_PAN1 * 9);
-    if (!w1 || !wp || !w2) return DMF_ERR_STATE;
+    if (!w1 || !wp) return DMF_ERR_STATE;
     DMF_TRY(to_device(&d->w_ms1, *w1));
     DMF_TRY(to_device(&d->w_pan1, *wp));
-    std::vector<__nv_bfloat16> pk((size_t)9 * C_PAN1 * C_PAN2);
-    for (int tap = 0; tap < 9; ++tap)
-        for (int ci = 0; ci < C_PAN1; ++ci)
-            for (int co = 0; co < C_PAN2; ++co)
-                pk[(((size_t)tap * (C_PAN1 / 8) + ci / 8) * C_PAN2 + co) * 8 + ci % 8] =
-                    __float2bfloat16_rn((*w2)[((size_t)co * C_PAN1 + ci) * 9 + tap]);
-    DMF_TRY(to_device(&d->w_pan2, pk));
+    const char* blk[3] = {"ms2", "pan2", "pan3"};
+    const int cin[3] = {C_MS1, C_PAN1, C_PAN2}, cout[3] = {C_MS2, C_PAN2, C_PAN3};
+    for (int l = 0; l < 3; ++l) {
+        auto* w = param(n, std::string(blk[l]) + ".0.weight", (size_t)cout[l] * cin[l] * 9);
+        if (!w) return DMF_ERR_STATE;
+        std::vector<float> sc, sh;
+        DMF_TRY(fold_bn(n, blk[l], cout[l], sc, sh));
+        std::vector<__nv_bfloat16> pk((size_t)9 * cin[l] * cout[l]);
+        for (int tap = 0; tap < 9; ++tap)
+            for (int ci = 0; ci < cin[l]; ++ci)
+                for (int co = 0; co < cout[l]; ++co) {
+                    const float v = (*w)[((size_t)co * cin[l] + ci) * 9 + tap];
+                    pk[(((size_t)tap * (cin[l] / 8) + ci / 8) * cout[l] + co) * 8 + ci % 8] = __float2bfloat16_rn(sc[co] < 0.f ? -v : v);
+                }
+        for (auto& v : sc) v = fabsf(v);
+        DMF_TRY(to_device(&d->w_cp[l], pk));
+        DMF_TRY(to_device(&d->sc_cp[l], sc));
+        DMF_TRY(to_device(&d->sh_cp[l], sh));
+    }
     auto* f1 = param(n, "fc1.weight", (size_t)C_HID * C_FUSE);
     if (!f1) return DMF_ERR_STATE;
     std::vector<__nv_bfloat16> hl((size_t)2 * C_FUSE * C_HID);
@@ -580,7 +595,8 @@ void dense_release(dmf_net* n) {
     if (!n->dense) return;
     DenseWs* d = n->dense;
     dense_free_ws(d);
-    cudaFree(d->w_ms1); cudaFree(d->w_pan1); cudaFree(d->w_pan2); cudaFree(d->w_fc1);
+    cudaFree(d->w_ms1); cudaFree(d->w_pan1); cudaFree(d->w_fc1);
+    for (int l = 0; l < 3; ++l) { cudaFree(d->w_cp[l]); cudaFree(d->sc_cp[l]); cudaFree(d->sh_cp[l]); }
     for (auto& e : d->ev) if (e) cudaEventDestroy(e);
     delete d;
     n->dense = nullptr;
@@ -647,7 +663,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, b0, rows, R1, C1, d->w_ms1, n->L[4].scale, n->L[4].shift, d->A);
         DMF_LAUNCHED();
         mark();
-        DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1>(d->mapA, false, n->L[0].w, n->L[0].scale, n->L[0].shift, d->CAT, C_CAT / 8, 0, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1>(d->mapA, false, d->w_cp[0], d->sc_cp[0], d->sh_cp[0], d->CAT, C_CAT / 8, 0, rows, R1, C1, st)));
         mark();
         mark();          // (stage slot of the former separate pooling pass)
         // ---- PAN branch
@@ -655,10 +671,10 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
-        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2>(d->mapB1, true, d->w_pan2, n->L[1].scale, n->L[1].shift, d->B2, C_PAN2 / 8, 0, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2>(d->mapB1, true, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, rows, R1, C1, st)));
         mark();
         mark();
-        DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1>(d->mapB2s, false, n->L[2].w, n->L[2].scale, n->L[2].shift, d->CAT, C_CAT / 8, C_MS2 / 8, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1>(d->mapB2s, false, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, rows, R1, C1, st)));
         mark();
         mark();
         // ---- fusion conv (1x1) on the 9 pooled planes

@@ -83,6 +83,10 @@ def scene_and_net(dmf, p, H, W, C, seed=0):
     sc = dmf.Scene.from_raw(ms, pan, p, DEV)
     sc.set_labels(label)
     ref = make_ref(p, C)
+    with torch.no_grad():                       # negative BatchNorm scales: the dense kernels fold sign(scale) into the weights
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight[::3] *= -1.0
     h = dmf.NetHandle(p, C, max_batch=2048, device=DEV)
     h.load_state_dict(ref.state_dict())
     return ms, pan, label, sc, ref, h
