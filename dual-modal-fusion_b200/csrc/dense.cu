@@ -494,7 +494,7 @@ static int build_pool4_cls(tc::Pool4Cls& c, int a, int b, bool aligned, int box_
 }
 
 // conv + pool of one layer over the band: in = 9 (x 4 phases) planes, out = 9 pooled planes
-template <int CI, int CO, int KQ, int STAGES, int BR, int BC, int NBUF>
+template <int CI, int CO, int KQ, int STAGES, int BR, int BC, int NBUF, int EW>
 static int launch_pool4(const CUtensorMap& map, bool aligned, const __nv_bfloat16* w, const float* scale, const float* shift, __nv_bfloat16* out,
                         int out_chunks, int out_chunk0, int rows, int R1, int C1, cudaStream_t st) {
     using Cfg = tc::Pool4Cfg<CI, CO, KQ, STAGES, BR, BC, NBUF>;
@@ -507,13 +507,13 @@ static int launch_pool4(const CUtensorMap& map, bool aligned, const __nv_bfloat1
     P.dbg = dbg;
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) DMF_TRY(build_pool4_cls(P.cls[a * 3 + b], a, b, aligned, BR, BC, Cfg::MAX_BOXES, Cfg::BOX_SLOT));
-    auto kern = tc::conv_pool4_kernel<CI, CO, KQ, STAGES, BR, BC, NBUF>;
+    auto kern = tc::conv_pool4_kernel<CI, CO, KQ, STAGES, BR, BC, NBUF, EW>;
     static bool attr_set = false;
     if (!attr_set) {
         DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
-    kern<<<std::min(P.n_tiles, num_sms()), 320, Cfg::SMEM, st>>>(map, P);
+    kern<<<std::min(P.n_tiles, num_sms()), 64 + 32 * EW, Cfg::SMEM, st>>>(map, P);
     DMF_LAUNCHED();
     return DMF_OK;
 }
@@ -663,7 +663,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, b0, rows, R1, C1, d->w_ms1, n->L[4].scale, n->L[4].shift, d->A);
         DMF_LAUNCHED();
         mark();
-        DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1>(d->mapA, false, d->w_cp[0], d->sc_cp[0], d->sh_cp[0], d->CAT, C_CAT / 8, 0, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1, 8>(d->mapA, false, d->w_cp[0], d->sc_cp[0], d->sh_cp[0], d->CAT, C_CAT / 8, 0, rows, R1, C1, st)));
         mark();
         mark();          // (stage slot of the former separate pooling pass)
         // ---- PAN branch
@@ -671,10 +671,10 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
-        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2>(d->mapB1, true, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2, 8>(d->mapB1, true, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, rows, R1, C1, st)));
         mark();
         mark();
-        DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1>(d->mapB2s, false, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1, 8>(d->mapB2s, false, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, rows, R1, C1, st)));
         mark();
         mark();
         // ---- fusion conv (1x1) on the 9 pooled planes

@@ -266,10 +266,11 @@ struct Pool4Cfg {
     static_assert(KCH % KQ == 0 && KQ % 2 == 0 && NBUF * 4 * C_OUT <= 512 && WBYTES % 128 == 0, "pool4 configuration");
 };
 
-template <int C_IN, int C_OUT, int KQ, int STAGES, int BR, int BC, int NBUF>
-__global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ Pool4Params P) {
+template <int C_IN, int C_OUT, int KQ, int STAGES, int BR, int BC, int NBUF, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ Pool4Params P) {
     using Cfg = Pool4Cfg<C_IN, C_OUT, KQ, STAGES, BR, BC, NBUF>;
-    constexpr int kThreads = 320;
+    constexpr int kThreads = 64 + 32 * EW;             // EW epilogue warps: NBUF = 2 -> two groups of EW / 2; NBUF = 1 -> EW / 4 channel slices
+    static_assert(EW % 4 == 0 && (NBUF == 1 || EW == 8), "epilogue warps");
     constexpr int KCH = Cfg::KCH, NSTEP = Cfg::NSTEP;
     constexpr uint32_t WBYTES = Cfg::WBYTES, SBO_A = BC * 16;
 
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
-        for (int a = 0; a < NBUF; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NBUF == 2 ? 4 : 8); }
+        for (int a = 0; a < NBUF; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NBUF == 2 ? 4 : EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -427,10 +428,10 @@ __global__ void __launch_bounds__(320, 1) conv_pool4_kernel(const __grid_constan
         }
     } else {
         // ------------------------------------------------ epilogue: BN + ReLU on the 4 sub-position accumulators, thread-local max
-        const int eg = (warp - 2) >> 2;                    // NBUF = 2: tile parity this group drains; NBUF = 1: channel half
+        const int eg = (warp - 2) >> 2;                    // NBUF = 2: tile parity this group drains; NBUF = 1: channel slice
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        constexpr int C_SPAN = NBUF == 2 ? C_OUT : C_OUT / 2;
+        constexpr int C_SPAN = NBUF == 2 ? C_OUT : C_OUT / (EW / 4);
         const int c_lo = NBUF == 2 ? 0 : eg * C_SPAN;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(NBUF == 2 ? eg * 4 * C_OUT : 0);
         const int64_t cstride = (int64_t)P.rows * P.cols * 8;
