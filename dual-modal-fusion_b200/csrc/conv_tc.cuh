@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv_tc_kernel(const __grid_c
                                 make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
                     }
                     if (MODE == 2) {
-                        // rows of patches beyond N come from out-of-bounds TMA boxes: all zeros, they add nothing
+                        // rows of patches beyond N come from out-of-bounds TMA boxes (train.cu encodes its maps per batch size): all zeros
                         float f[32], q2[32];
 #pragma unroll
                         for (int k = 0; k < 32; ++k) { f[k] = __uint_as_float(v[k]); q2[k] = f[k] * f[k]; }

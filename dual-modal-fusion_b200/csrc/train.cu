@@ -690,6 +690,7 @@ struct dmf_train {
     bool ready = false;
     int swap_lbo_sbo = 0;
     int64_t N = 0;             // batch of the last forward
+    int64_t maps_N = -1;       // patch count the tensor maps were encoded for
     TLayer L[L_COUNT];
     BnRefs bn[L_COUNT];
     float *fc1w = nullptr, *fc1b = nullptr, *fc2w = nullptr, *fc2b = nullptr;
@@ -889,9 +890,12 @@ static int pack_all(dmf_train* t, cudaStream_t st) {
     return DMF_OK;
 }
 
+static int train_set_maps(dmf_train* t, int64_t N);
+
 static int train_forward(dmf_train* t, const float* ms, const float* pan, int64_t N, cudaStream_t st) {
     const int p = t->p;
     t->N = N;
+    DMF_TRY(train_set_maps(t, N));
     t->pan_patches = pan;
     DMF_CUDA(cudaMemsetAsync(t->stats, 0, sizeof(double) * L_COUNT * 4 * kStatStride, st));
     DMF_TRY(pack_all(t, st));
@@ -963,6 +967,31 @@ static int train_backward(dmf_train* t, const float* dlogits, cudaStream_t st) {
     return wgrad_finish(t, all, 5, st);
 }
 
+}  // namespace dmf
+
+namespace dmf {
+// Tensor maps over the activation / gradient buffers for a batch of exactly N patches: layer inputs (forward + wgrad B operand)
+// and dZ views (dgrad A operand, wgrad A operand).  The patch dimension of every map is N, not the capacity NB: tiles that hold
+// several patches (8x8 maps: 2 per tile, the 1x1 layer up to 8) read ZEROS for the patch slots beyond the batch, so that the
+// batch statistics and the weight gradients (sums over every pixel of a tile) never see stale workspace contents.
+static int train_set_maps(dmf_train* t, int64_t N) {
+    if (t->maps_N == N) return DMF_OK;
+    const int ls[4] = {L_MS2, L_PAN2, L_PAN3, L_FUSE};
+    DMF_TRY(make_map(&t->L[L_MS1].map_in, t->L[L_MS1].g, t->X0, N));
+    DMF_TRY(make_map(&t->L[L_MS2].map_in, t->L[L_MS2].g, t->A1, N));
+    DMF_TRY(make_map(&t->L[L_PAN2].map_in, t->L[L_PAN2].g, t->B1, N));
+    DMF_TRY(make_map(&t->L[L_PAN3].map_in, t->L[L_PAN3].g, t->B2, N));
+    DMF_TRY(make_map(&t->L[L_FUSE].map_in, t->L[L_FUSE].g, t->CAT, N));
+    for (int l : ls) DMF_TRY(make_map(&t->L[l].map_dz_halo, t->L[l].gd, t->dZ, N));
+    const int lw[5] = {L_MS1, L_MS2, L_PAN2, L_PAN3, L_FUSE};
+    for (int l : lw) {
+        LayerGeom gz = t->L[l].g;         // same tiling, channel count of the layer OUTPUT
+        gz.cin = gz.cout;
+        DMF_TRY(make_map(&t->L[l].map_dz, gz, t->dZ, N, false));
+    }
+    t->maps_N = N;
+    return DMF_OK;
+}
 }  // namespace dmf
 
 extern "C" {
@@ -1095,19 +1124,7 @@ int dmf_train_finalize(dmf_train* t) {
             size_t off = 0;
             for (int l : lw) { t->L[l].wg_scratch = t->wg_all + off; off += (size_t)t->L[l].g.taps * t->L[l].g.cin * t->L[l].g.cout; }
         }
-        // tensor maps: layer inputs (forward + wgrad B operand), dZ views (dgrad A operand, wgrad A operand)
-        DMF_TRY(make_map(&t->L[L_MS1].map_in, t->L[L_MS1].g, t->X0, t->NB));
-        DMF_TRY(make_map(&t->L[L_MS2].map_in, t->L[L_MS2].g, t->A1, t->NB));
-        DMF_TRY(make_map(&t->L[L_PAN2].map_in, t->L[L_PAN2].g, t->B1, t->NB));
-        DMF_TRY(make_map(&t->L[L_PAN3].map_in, t->L[L_PAN3].g, t->B2, t->NB));
-        DMF_TRY(make_map(&t->L[L_FUSE].map_in, t->L[L_FUSE].g, t->CAT, t->NB));
-        for (int l : ls) DMF_TRY(make_map(&t->L[l].map_dz_halo, t->L[l].gd, t->dZ, t->NB));
-        const int lw[5] = {L_MS1, L_MS2, L_PAN2, L_PAN3, L_FUSE};
-        for (int l : lw) {
-            LayerGeom gz = t->L[l].g;         // same tiling, channel count of the layer OUTPUT
-            gz.cin = gz.cout;
-            DMF_TRY(make_map(&t->L[l].map_dz, gz, t->dZ, t->NB, false));
-        }
+        DMF_TRY(train_set_maps(t, t->NB));
         DMF_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         DMF_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     }
@@ -1197,6 +1214,7 @@ int dmf_train_debug_op(dmf_train* t, int op, int layer, int64_t N, void* stream)
     DMF_REQUIRE(op >= 0 && op <= 3 && layer >= 0 && layer < L_COUNT && N >= 1 && N <= t->NB, "train_debug_op: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (op == 0) return pack_all(t, st);
+    DMF_TRY(train_set_maps(t, N));
     const int S = 4 * t->p;
     if (op == 1) {
         DMF_CUDA(cudaMemsetAsync(t->bn[layer].stats, 0, sizeof(double) * 4 * kStatStride, st));

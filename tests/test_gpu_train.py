@@ -146,6 +146,10 @@ def test_stem_wgrads_exact_on_integers(dmf, p, N):
     x16[:, 0:4] = x
     x16[:, 8:12] = x
     dz = int_tensor((N, 64, p, p), -2, 2, 22, density=0.5)
+    # poison the patch slot behind the batch: 8x8 maps put 2 patches in one tile, and a batch that ends mid-tile must read zeros
+    # there (the tensor maps are encoded for exactly N patches), not whatever the workspace held
+    h.buffer('X0', torch.bfloat16, (N + 1, 2, p, p, 8), alias=True)[N].fill_(float('nan'))
+    h.buffer('dZ', torch.bfloat16, (N + 1, 8, p, p, 8), alias=True)[N].fill_(float('nan'))
     h.buffer('X0', torch.bfloat16, (N, 2, p, p, 8), alias=True).copy_(to_c8(x16))
     h.buffer('dZ', torch.bfloat16, (N, 8, p, p, 8), alias=True).copy_(to_c8(dz))
     h.flat_grad.zero_()
