@@ -11,8 +11,8 @@
 //   scene --pan_stem_map--> B1 [9 ][4 phases][4][R][C][8]  stem conv + pool on the pooled-once grid, stored phase-separated
 //   B1 --conv_pool4 (aligned pool)--> B2 [9][8][R][C][8]  conv 32->64 + aligned 2x2 max (the pooled-once grid moves 2 cells per pixel)
 //   B2 --conv_pool4 (stride-1 pool)--> CAT[9][16..31]
-//   CAT --conv1x1_planes, 9 planes--> F [9][16][R][C][8]
-//   F  --head_dense--> per pixel: mean over the (p/2)^2 strided samples F[cls(k),cls(l)][x+2k][y+2l], 2 linears,
+//   CAT --fuse_rowsum (1x1 conv + row sums of the average pool)--> S [3][16][R][W][8] fp32;  F = relu(bn(W . CAT)) stays on chip
+//   S  --head_dense--> per pixel: mean over the (p/2)^2 strided samples F[cls(k),cls(l)][x+2k][y+2l], 2 linears,
 //                      argmax, confusion matrix, label map
 // with R = (r1 - r0) + p - 1 rows and C = W + p - 1 columns.  Positions a band never needs hold don't-care values
 // (they only ever feed other don't-care positions).  Results equal the per-patch path up to fp32 summation order.
@@ -29,7 +29,7 @@ namespace dmf {
 
 struct DenseWs {
     int W = 0, band = 0, p = 0, R1 = 0, C1 = 0;
-    __nv_bfloat16 *A = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr, *F = nullptr;
+    __nv_bfloat16 *A = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr;
     float* S = nullptr;                              // row sums of F for the separable average pool [3][16][R][W][8]
     float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
     // conv + pool layers (ms2, pan2, pan3): tap-major bf16 weights with sign(BN scale) folded into every output channel, |scale|,
@@ -37,7 +37,7 @@ struct DenseWs {
     __nv_bfloat16* w_cp[3] = {nullptr, nullptr, nullptr};
     float *sc_cp[3] = {nullptr, nullptr, nullptr}, *sh_cp[3] = {nullptr, nullptr, nullptr};
     __nv_bfloat16* w_fc1 = nullptr;                  // fc1 weight as bf16 hi / lo parts [2][16][64][8] (B operand of the head's MMA)
-    CUtensorMap mapA, mapB1, mapB2s, mapCAT;
+    CUtensorMap mapA, mapB1, mapB2s;
     cudaEvent_t ev[12] = {};
     float stage_ms[12] = {};
     size_t bytes = 0;
@@ -192,48 +192,10 @@ __global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------- head
 // The global average pool of pixel (x, y) is a strided gather from the 9 F planes,
 //     g = 1/(p/2)^2 * sum_{k,l} F[cls(k), cls(l)][x + 2k][y + 2l],      cls = first / interior / last cell,
-// evaluated separably: gap_rows_kernel forms the inner sums S[a][X][y] = sum_l F[a, cls(l)][X][y + 2l] once per map row
-// and row class a (fp32, [3][16][rows][W][8]); head_dense_kernel adds the p/2 rows S[cls(k)][x + 2k][y] of a pixel and
+// evaluated separably: fuse_rowsum_kernel (dense_tc.cuh) forms the inner sums S[a][X][y] = sum_l F[a, cls(l)][X][y + 2l] once
+// per map row and row class a (fp32, [3][16][rows][W][8]) in the epilogue of the fusion conv; head_dense_kernel adds the p/2 rows S[cls(k)][x + 2k][y] of a pixel and
 // runs the two linears (the first one on the tensor pipe), the first-maximum argmax, the confusion matrix (per-block shared
 // histogram -> 64-bit global atomics) and the label map.  Summation order: l ascending inside a row, then k ascending.
-template <int P2>
-__global__ void __launch_bounds__(256) gap_rows_kernel(const uint4* __restrict__ F, int R1, int C1, int rows, int W, float4* __restrict__ S) {
-    const int64_t total = (int64_t)3 * 16 * rows * W;
-    const int64_t bstride = (int64_t)16 * R1 * C1;                // next column class
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int y = (int)(i % W);
-        int64_t r = i / W;
-        const int X = (int)(r % rows); r /= rows;
-        const int ch = (int)(r % 16);
-        const int a = (int)(r / 16);
-        const uint4* rowp = F + (((int64_t)(a * 3) * 16 + ch) * R1 + X) * C1 + y;
-        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int l0 = 0; l0 < P2; l0 += 8) {
-            uint4 v[8];                                            // 8 independent 16-byte loads in flight
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int l = l0 + e;
-                if (l < P2) v[e] = __ldg(rowp + (l == 0 ? 0 : (l == P2 - 1 ? 2 : 1)) * bstride + 2 * l);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (l0 + e < P2) {
-                    const uint32_t u[4] = {v[e].x, v[e].y, v[e].z, v[e].w};
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        s[2 * h] += __uint_as_float(u[h] << 16);             // bf16 -> fp32 is a shift
-                        s[2 * h + 1] += __uint_as_float(u[h] & 0xFFFF0000u);
-                    }
-                }
-            }
-        }
-        float4* o = S + ((((int64_t)a * 16 + ch) * rows + X) * W + y) * 2;
-        o[0] = make_float4(s[0], s[1], s[2], s[3]);
-        o[1] = make_float4(s[4], s[5], s[6], s[7]);
-    }
-}
-
 // One block = 128 consecutive pixels of one anchor row.
 //   phase 1 (8 warps): warp w = channel chunks w and w + 8, lane = pixel (4 passes of 32): the p/2 row sums are added, scaled and written
 //     to shared memory as the A operand of the first linear, split into bf16 hi + lo parts (g = hi + lo to ~2^-17);
@@ -518,27 +480,6 @@ static int launch_pool4(const CUtensorMap& map, bool aligned, const __nv_bfloat1
     return DMF_OK;
 }
 
-template <int CI, int CO, int G>
-static int launch_planes(const CUtensorMap& map, tc::PlanesParams& P, cudaStream_t st) {
-    constexpr size_t a_stage = (size_t)(CI / 8) * 128 * 16;
-    constexpr size_t fixed = (size_t)CI * CO * 2 + 2 * CO * 4 + 28 * 8;
-    static_assert(fixed + a_stage <= (size_t)kSmemLimit, "1x1 plane layer does not fit in shared memory");
-    P.n_stage = (int)std::min<size_t>(8, (kSmemLimit - fixed) / a_stage);
-    P.n_tiles = P.tiles_x * P.tiles_y * P.n_planes;
-    static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
-    P.dbg = dbg;
-    auto kern = tc::conv1x1_planes_kernel<CI, CO, G>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        attr_set = true;
-    }
-    if (P.n_tiles <= 0) return DMF_OK;
-    kern<<<std::min(P.n_tiles, num_sms()), 64 + 128 * G, fixed + (size_t)P.n_stage * a_stage, st>>>(map, P);
-    DMF_LAUNCHED();
-    return DMF_OK;
-}
-
 int dense_pack(dmf_net* n) {
     if (!n->dense) n->dense = new DenseWs();
     DenseWs* d = n->dense;
@@ -582,11 +523,11 @@ int dense_pack(dmf_net* n) {
 }
 
 static void dense_free_ws(DenseWs* d) {
-    __nv_bfloat16* bs[] = {d->A, d->CAT, d->B1, d->B2, d->F};
+    __nv_bfloat16* bs[] = {d->A, d->CAT, d->B1, d->B2};
     for (auto* b : bs) cudaFree(b);
     cudaFree(d->S);
     d->S = nullptr;
-    d->A = d->CAT = d->B1 = d->B2 = d->F = nullptr;
+    d->A = d->CAT = d->B1 = d->B2 = nullptr;
     d->W = d->band = 0;
     d->bytes = 0;
 }
@@ -610,28 +551,28 @@ static int dense_prepare(dmf_net* n, int W, int band) {
     dense_free_ws(d);
     const int p = n->p;
     const size_t R1 = band + p - 1, C1 = W + p - 1, px = R1 * C1;
-    const size_t sA = px * 9 * C_MS1 * 2, sCAT = px * 9 * C_CAT * 2, sB1 = px * 4 * 9 * C_PAN1 * 2,
-                 sB2 = px * 9 * C_PAN2 * 2, sF = px * 9 * C_FUSE * 2;
+    const size_t sA = px * 9 * C_MS1 * 2, sCAT = px * 9 * C_CAT * 2 + 2048 /* fuse_rowsum_kernel's last 2 KB row copy may run past the tensor */, sB1 = px * 4 * 9 * C_PAN1 * 2,
+                 sB2 = px * 9 * C_PAN2 * 2;
     DMF_CUDA(cudaMalloc(&d->A, sA));
     DMF_CUDA(cudaMalloc(&d->CAT, sCAT));
     DMF_CUDA(cudaMalloc(&d->B1, sB1));
     DMF_CUDA(cudaMalloc(&d->B2, sB2));
-    DMF_CUDA(cudaMalloc(&d->F, sF));
     const size_t sS = R1 * (size_t)W * 3 * C_FUSE * sizeof(float);
     DMF_CUDA(cudaMalloc(&d->S, sS));
-    d->bytes = sA + sCAT + sB1 + sB2 + sF + sS;
+    d->bytes = sA + sCAT + sB1 + sB2 + sS;
     // positions a band never writes are only ever read into don't-care outputs; zero them once so that runs are reproducible
     DMF_CUDA(cudaMemset(d->A, 0, sA));
     DMF_CUDA(cudaMemset(d->CAT, 0, sCAT));
     DMF_CUDA(cudaMemset(d->B1, 0, sB1));
     DMF_CUDA(cudaMemset(d->B2, 0, sB2));
-    DMF_CUDA(cudaMemset(d->F, 0, sF));
     d->W = W; d->band = band; d->p = p; d->R1 = (int)R1; d->C1 = (int)C1;
     DMF_TRY(make_dense_map(&d->mapA, d->A, 9, C_MS1 / 8, (int)R1, (int)C1, 11, 19, 2));
     DMF_TRY(make_dense_map(&d->mapB1, d->B1, 36, C_PAN1 / 8, (int)R1, (int)C1, 9, 17, C_PAN1 / 8));
     DMF_TRY(make_dense_map(&d->mapB2s, d->B2, 9, C_PAN2 / 8, (int)R1, (int)C1, 11, 19, 2));
-    DMF_TRY(make_dense_map(&d->mapCAT, d->CAT, 9, C_CAT / 8, (int)R1, (int)C1, 32, 4, C_CAT / 8));
     for (auto& e : d->ev) if (!e) DMF_CUDA(cudaEventCreate(&e));
+    DMF_CUDA(cudaFuncSetAttribute(tc::fuse_rowsum_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    DMF_CUDA(cudaFuncSetAttribute(tc::fuse_rowsum_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    DMF_CUDA(cudaFuncSetAttribute(tc::fuse_rowsum_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     DMF_CUDA(cudaFuncSetAttribute(head_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -677,21 +618,22 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
         DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1, 8>(d->mapB2s, false, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, rows, R1, C1, st)));
         mark();
         mark();
-        // ---- fusion conv (1x1) on the 9 pooled planes
+        // ---- fusion conv (1x1) on the 9 pooled planes + row sums of the global average pool
         {
-            tc::PlanesParams P{};
-            P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 32); P.tiles_y = cdiv(rows, 4); P.n_planes = 9;
-            P.out_chunks = C_FUSE / 8;
-            P.w = n->L[3].w; P.scale = n->L[3].scale; P.shift = n->L[3].shift; P.out = d->F;
-            DMF_TRY((launch_planes<C_CAT, C_FUSE, 4>(d->mapCAT, P, st)));
+            tc::FuseRowsParams P{};
+            const int valid = 128 - 2 * (p / 2 - 1);
+            P.rows = rows; P.W = W; P.tiles_x = cdiv(W, valid); P.n_tiles = rows * 3 * P.tiles_x; P.s_rows = rows;
+            static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
+            P.dbg = dbg;
+            P.w = n->L[3].w; P.scale = n->L[3].scale; P.shift = n->L[3].shift; P.S = reinterpret_cast<float4*>(d->S);
+            P.cat = d->CAT; P.R1 = R1; P.C1 = C1;
+            auto fk = p == 8 ? tc::fuse_rowsum_kernel<4> : p == 16 ? tc::fuse_rowsum_kernel<8> : tc::fuse_rowsum_kernel<16>;
+            fk<<<std::min(P.n_tiles, num_sms()), 320, tc::kFrSmem, st>>>(P);
+            DMF_LAUNCHED();
         }
         mark();
         // ---- head
         {
-            const int64_t work = (int64_t)3 * 16 * rows * W;
-            auto rk = p == 8 ? gap_rows_kernel<4> : p == 16 ? gap_rows_kernel<8> : gap_rows_kernel<16>;
-            rk<<<grid_for(work, 256, 16), 256, 0, st>>>(reinterpret_cast<const uint4*>(d->F), R1, C1, rows, W, reinterpret_cast<float4*>(d->S));
-            DMF_LAUNCHED();
             const int n_seg = nb * ((W + kHeadPx - 1) / kHeadPx);
             const int64_t off = (int64_t)(b0 - row0) * W;
             auto kern = p == 8 ? head_dense_kernel<4> : p == 16 ? head_dense_kernel<8> : head_dense_kernel<16>;
@@ -748,7 +690,7 @@ int dmf_net_get_dense_timing(dmf_net* n, float out_ms[12], int reset) {
     return DMF_OK;
 }
 
-/* test hook: device pointer + byte size of a dense-path map ("A", "CAT", "B1", "B2", "F"); dims[0..1] = R, C of the MS-resolution grid */
+/* test hook: device pointer + byte size of a dense-path map ("A", "CAT", "B1", "B2", "S"); dims[0..1] = R, C of the MS-resolution grid */
 int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* bytes_out, int32_t dims[2]) {
     DMF_REQUIRE(n && name && ptr_out && bytes_out && dims, "net_dense_buffer: null");
     DMF_REQUIRE(n->dense && n->dense->A, "net_dense_buffer: the dense path has not run yet");
@@ -759,7 +701,7 @@ int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* 
     else if (k == "CAT") { *ptr_out = d->CAT; *bytes_out = px * 9 * C_CAT * 2; }
     else if (k == "B1") { *ptr_out = d->B1; *bytes_out = px * 4 * 9 * C_PAN1 * 2; }
     else if (k == "B2") { *ptr_out = d->B2; *bytes_out = px * 9 * C_PAN2 * 2; }
-    else if (k == "F") { *ptr_out = d->F; *bytes_out = px * 9 * C_FUSE * 2; }
+    else if (k == "S") { *ptr_out = d->S; *bytes_out = (int64_t)d->R1 * d->W * 3 * C_FUSE * sizeof(float); }
     else { set_error("net_dense_buffer: unknown map '%s'", name); return DMF_ERR_ARG; }
     dims[0] = d->R1; dims[1] = d->C1;
     return DMF_OK;

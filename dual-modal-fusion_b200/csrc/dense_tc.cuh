@@ -6,7 +6,7 @@
 // border, not at the scene border): a 3x3/pad-1 conv output has 3 border variants per axis {first, interior, last},
 // and a conv + 2x2 max-pool on such an input again has 3.  So every layer is 9 scene-level maps ("planes"), each
 // computed ONCE per scene position instead of once per patch.  Two kernels:
-//   conv1x1_planes_kernel   the 1x1 fusion conv, plane by plane
+//   fuse_rowsum_kernel      the 1x1 fusion conv fused with the row sums of the global average pool
 //   conv_pool4_kernel       conv3x3 + BN + ReLU + 2x2 max-pool, 9 pooled planes out of 9 (x 4 phases) input planes
 // Both use the C8-planar no-swizzle operand layout and the warp roles of conv_tc.cuh.
 #pragma once
@@ -15,63 +15,72 @@
 namespace dmf {
 namespace tc {
 
-struct PlanesParams {
-    int rows, cols;                       // map size in positions
-    int tiles_x, tiles_y, n_planes, n_tiles;
-    int n_stage;
-    int out_chunks;                       // channel chunks of one output plane
-    int dbg;                              // diagnostics only: bit0 = skip the TMA loads, bit1 = skip the epilogue math/stores
+// ------------------------------------------------------------------------------------------------
+// 1x1 fusion conv + BN + ReLU fused with the inner sums of the global average pool: F never goes to HBM.
+//
+//     S[a][X][y] = sum_{l < P2} F[a, cls(l)][X][y + 2l],    F[a, b] = bf16(relu(bn(W . CAT[a, b])))    (cls = first / interior / last)
+//
+// One tile = one map row X of one row class a, 128 consecutive columns: three accumulators (column classes b = 0, 1, 2) of
+// M128 x N128, K = 256 in 3 x 4 pipeline steps of 8 channel chunks.  128 columns of one row of one chunk plane are 2 KB contiguous
+// in HBM, so a step is 8 plain bulk copies (cp.async.bulk) that land directly in the K-major no-swizzle layout (a 5-D tensor-map
+// box with a 16-byte inner dimension did the same at a third of the rate).  Epilogue, 8 warps: (1) thread = (column, channel half):
+// tcgen05.ld, affine, ReLU, bf16, into a shared-memory F tile [b][col][128 ch] (row pitch 272 B: conflict-free 16-byte
+// accesses); (2) thread = (anchor column y, channel half): the P2 strided samples are added in fp32, l ascending, S is written.  A tile yields 128 - 2 (P2 - 1)
+// anchors (the tiles overlap by the window width).  Same rounding points and summation order as a separate F tensor + row-sum
+// pass: the results are bit-identical to that formulation.
+struct FuseRowsParams {
+    int rows, W;                          // map rows of this band, anchor columns
+    int tiles_x, n_tiles;
+    int s_rows;                           // row dimension of S ([3][16][s_rows][W][8] fp32)
+    int R1, C1;                           // CAT plane geometry: [9][32 chunks][R1][C1][8] bf16 (+ 2 KB of slack behind the tensor)
+    const __nv_bfloat16* cat;
+    int dbg;
     const __nv_bfloat16* w;               // packed [C_in/8][C_out][8]
     const float* scale;
     const float* shift;
-    __nv_bfloat16* out;                   // [plane][out_chunks][rows][cols][8]
+    float4* S;
 };
 
-// out[plane][X][Y] = relu(bn(W . in[plane][X][Y])) for every plane.  Tile = 4 rows x 32 columns of one plane (512-byte TMA
-// rows, no halo); tiles ordered (row strip, plane, column).  M = 128 positions, N = C_OUT, C_IN / 16 MMAs per tile; G epilogue
-// groups of 4 warps drain G accumulators.
-template <int C_IN, int C_OUT, int G>
-__global__ void __launch_bounds__(64 + 128 * G, 1) conv1x1_planes_kernel(const __grid_constant__ CUtensorMap in_map,
-                                                                         const __grid_constant__ PlanesParams P) {
-    constexpr int kThreads = 64 + 128 * G;
-    constexpr int KCH = C_IN / 8, KSTEPS = C_IN / 16;
+constexpr int kFrKQ = 8, kFrStages = 3, kFrPitch = 272;
+constexpr uint32_t kFrStage = kFrKQ * 128 * 16;                                        // 16 KB
+constexpr size_t kFrSmem = (size_t)256 * 128 * 2 + kFrStages * kFrStage + 3 * 128 * kFrPitch + 2 * 128 * 4 + 16 * 8;
+
+template <int P2>
+__global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_constant__ FuseRowsParams P) {
+    constexpr int C_IN = 256, C_OUT = 128, KCH = C_IN / 8, NSTEP = KCH / kFrKQ;
+    constexpr int VALID = 128 - 2 * (P2 - 1);
     constexpr uint32_t WBYTES = (uint32_t)C_IN * C_OUT * 2;
-    constexpr uint32_t TMEM_USED = G * C_OUT;
-    constexpr uint32_t TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
-    static_assert(G >= 1 && G <= 4 && TMEM_USED <= 512, "epilogue groups / TMEM columns");
-    static_assert(C_IN % 16 == 0 && C_OUT % 32 == 0 && C_OUT <= 256, "channel counts");
-    constexpr uint32_t A_PLANE = 128u * 16u, SBO_A = 128u;
-    constexpr uint32_t A_STAGE = KCH * A_PLANE;
+    constexpr uint32_t A_PLANE = 128u * 16u;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
     uint8_t* a_s = smem + WBYTES;
-    float* scale_s = reinterpret_cast<float*>(a_s + (size_t)P.n_stage * A_STAGE);
+    uint8_t* f_s = a_s + kFrStages * kFrStage;                       // [3][128 cols][272 B]
+    float* scale_s = reinterpret_cast<float*>(f_s + 3 * 128 * kFrPitch);
     float* shift_s = scale_s + C_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
-    // bars: [0,8) full, [8,16) empty, 16 weights, 17..20 tmem_full, 21..24 tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    // bars: [0,3) full, [3,6) empty, 6 weights, 7 tmem_full, 8 tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
-    const uint32_t w_bar = bar0 + 8u * 16;
-    auto tfull_bar = [&](int a) { return bar0 + 8u * (17 + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (21 + a); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (3 + s); };
+    const uint32_t w_bar = bar0 + 8u * 6, tfull_bar = bar0 + 8u * 7, tempty_bar = bar0 + 8u * 8;
 
-    for (int i = threadIdx.x; i < C_OUT; i += kThreads) {
+    for (int i = threadIdx.x; i < C_OUT; i += 320) {
         scale_s[i] = P.scale[i];
         shift_s[i] = P.shift[i];
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.n_stage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kFrStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
-        for (int a = 0; a < G; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -80,13 +89,13 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv1x1_planes_kernel(const _
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    // tile -> (row strip ty, plane c, column tile tx); every role walks its tiles with the same incremental decode
-    int tx = (int)blockIdx.x % P.tiles_x, c = ((int)blockIdx.x / P.tiles_x) % P.n_planes, ty = ((int)blockIdx.x / P.tiles_x) / P.n_planes;
+    // tile -> (map row X, row class a, column tile tx), walked incrementally by every role
+    int tx = (int)blockIdx.x % P.tiles_x, a = ((int)blockIdx.x / P.tiles_x) % 3, X = ((int)blockIdx.x / P.tiles_x) / 3;
     auto next_tile = [&]() {
         tx += (int)gridDim.x;
         while (tx >= P.tiles_x) {
             tx -= P.tiles_x;
-            if (++c == P.n_planes) { c = 0; ++ty; }
+            if (++a == 3) { a = 0; ++X; }
         }
     };
 
@@ -94,30 +103,35 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv1x1_planes_kernel(const _
         // ------------------------------------------------ TMA producer
         const bool leader = elect_one();
         if (leader) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
             mbar_expect_tx(w_bar, WBYTES);
             constexpr uint32_t CH = 16384;
             for (uint32_t off = 0; off < WBYTES; off += CH)
-                bulk_load(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(P.w) + off, min(CH, WBYTES - off), w_bar);
+                bulk_load(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(P.w) + off, CH, w_bar);
         }
         __syncwarp();
         int st = 0;
         uint32_t ph = 1;
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            mbar_wait(empty_bar(st), ph);
-            if (leader) {
-                if (P.dbg & 1) {
-                    mbar_arrive(full_bar(st));
-                } else {
-                    mbar_expect_tx(full_bar(st), A_STAGE);
-                    tma_load_4d(smem_u32(a_s) + (uint32_t)st * A_STAGE, &in_map, full_bar(st), tx * 32 * 8, c, ty * 4, 0);
+            for (int step = 0; step < 3 * NSTEP; ++step) {
+                mbar_wait(empty_bar(st), ph);
+                if (leader) {
+                    if (P.dbg & 1) {
+                        mbar_arrive(full_bar(st));
+                    } else {
+                        mbar_expect_tx(full_bar(st), kFrStage);
+                        const int64_t chunk0 = (int64_t)(a * 3 + step / NSTEP) * KCH + (step % NSTEP) * kFrKQ;
+                        const __nv_bfloat16* src = P.cat + ((chunk0 * P.R1 + X) * P.C1 + tx * VALID) * 8;
+                        const int64_t cstride = (int64_t)P.R1 * P.C1 * 8;
+                        for (int ck = 0; ck < kFrKQ; ++ck)
+                            bulk_load(smem_u32(a_s) + (uint32_t)st * kFrStage + (uint32_t)ck * A_PLANE, src + ck * cstride, A_PLANE, full_bar(st));
+                    }
                 }
+                __syncwarp();
+                if (++st == kFrStages) { st = 0; ph ^= 1; }
             }
-            __syncwarp();
-            if (++st == P.n_stage) { st = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+        // ------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = umma_idesc_bf16(128, C_OUT);
         const bool leader = elect_one();
         mbar_wait(w_bar, 0);
@@ -125,66 +139,87 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv1x1_planes_kernel(const _
         int st = 0;
         uint32_t ph = 0;
         for (int i = 0; i < n_local; ++i) {
-            const int acc = i % G;
-            mbar_wait(tempty_bar(acc), ((i / G) & 1) ^ 1);
-            mbar_wait(full_bar(st), ph);
-            tc_fence_after();
-            const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * A_STAGE, A_PLANE, SBO_A);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C_OUT);
-            if (leader) {
+            mbar_wait(tempty_bar, (i & 1) ^ 1);
+            for (int step = 0; step < 3 * NSTEP; ++step) {
+                const int b = step / NSTEP, kq = step % NSTEP;
+                mbar_wait(full_bar(st), ph);
+                tc_fence_after();
+                const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * kFrStage, A_PLANE, 128);
+                if (leader) {
 #pragma unroll
-                for (int j = 0; j < KSTEPS; ++j) {
-                    const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(2 * j) * A_PLANE) >> 4);
-                    const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(2 * j * C_OUT * 16) >> 4);
-                    umma_bf16(d_tmem, ad, bd, idesc, j ? 1u : 0u);
+                    for (int j = 0; j < kFrKQ / 2; ++j) {
+                        const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(2 * j) * A_PLANE) >> 4);
+                        const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((kq * kFrKQ + 2 * j) * C_OUT * 16) >> 4);
+                        umma_bf16(tmem_base + (uint32_t)(b * C_OUT), ad, bd, idesc, (kq | j) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(st));
+                    if (step == 3 * NSTEP - 1) umma_commit(tfull_bar);
                 }
-                umma_commit(empty_bar(st));
-                umma_commit(tfull_bar(acc));
+                __syncwarp();
+                if (++st == kFrStages) { st = 0; ph ^= 1; }
             }
-            __syncwarp();
-            if (++st == P.n_stage) { st = 0; ph ^= 1; }
         }
     } else {
-        // ------------------------------------------------ epilogue (G groups of 4 warps): BN affine + ReLU -> bf16 -> C8-planar stores
-        const int eg = (warp - 2) >> 2;
-        const int q = warp & 3;
-        const int m = q * 32 + lane;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * C_OUT);
-        const int64_t cstride = (int64_t)P.rows * P.cols * 8;
+        // ------------------------------------------------ epilogue (8 warps: TMEM lane quarter q, channel half hc)
+        const int q = warp & 3, hc = (warp - 2) >> 2;
+        const int m = q * 32 + lane;                      // phase 1: column of the tile; phase 2: anchor column
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            if (i % G != eg) continue;
-            const int row = ty * 4 + (m >> 5), col = tx * 32 + (m & 31);
-            const bool valid = row < P.rows && col < P.cols;
-            __nv_bfloat16* const obase = P.out + ((((int64_t)c * P.out_chunks) * P.rows + row) * P.cols + col) * 8;
-            mbar_wait(tfull_bar(eg), (i / G) & 1);
+            mbar_wait(tfull_bar, i & 1);
             tc_fence_after();
+            if (!(P.dbg & 2)) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < ((P.dbg & 2) ? 0 : C_OUT); c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(t_row + c0, v);
-                uint32_t pk[16];
-                const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
-                const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+                for (int b = 0; b < 3; ++b) {
+#pragma unroll 1
+                    for (int c0 = hc * 64; c0 < hc * 64 + 64; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_row + (uint32_t)(b * C_OUT + c0), v);
+                        const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
+                        const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+                        uint32_t pk[16];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float4 sc = sc4[k], sh = sh4[k];
-                    const float a0 = fmaxf(fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x), 0.f);
-                    const float a1 = fmaxf(fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y), 0.f);
-                    const float a2 = fmaxf(fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z), 0.f);
-                    const float a3 = fmaxf(fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w), 0.f);
-                    pk[2 * k] = pack_bf16x2(a0, a1);
-                    pk[2 * k + 1] = pack_bf16x2(a2, a3);
-                }
-                if (valid) {
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 sc = sc4[k], sh = sh4[k];
+                            const float a0 = fmaxf(fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x), 0.f);
+                            const float a1 = fmaxf(fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y), 0.f);
+                            const float a2 = fmaxf(fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z), 0.f);
+                            const float a3 = fmaxf(fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w), 0.f);
+                            pk[2 * k] = pack_bf16x2(a0, a1);
+                            pk[2 * k + 1] = pack_bf16x2(a2, a3);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(f_s + (uint32_t)(b * 128 + m) * kFrPitch + (uint32_t)c0 * 2);
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4)
-                        *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + s4) * cstride) =
-                            make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                        for (int s4 = 0; s4 < 4; ++s4) dst[s4] = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(eg));
+            if (lane == 0) mbar_arrive(tempty_bar);                       // accumulators drained: the next tile's MMAs may start
+            asm volatile("bar.sync 1, 256;" ::: "memory");                // F tile complete
+            const int y = tx * VALID + m;
+            if (m < VALID && y < P.W && !(P.dbg & 2)) {
+                float4* o = P.S + ((((int64_t)a * 16 + hc * 8) * P.s_rows + X) * P.W + y) * 2;
+                const int64_t cstride = (int64_t)P.s_rows * P.W * 2;
+#pragma unroll 2
+                for (int ch = 0; ch < 8; ++ch) {
+                    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int l = 0; l < P2; ++l) {
+                        const int b = l == 0 ? 0 : (l == P2 - 1 ? 2 : 1);
+                        const uint4 v = *reinterpret_cast<const uint4*>(f_s + (uint32_t)(b * 128 + m + 2 * l) * kFrPitch + (uint32_t)(hc * 8 + ch) * 16);
+                        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            s[2 * h] += __uint_as_float(u[h] << 16);             // bf16 -> fp32 is a shift
+                            s[2 * h + 1] += __uint_as_float(u[h] & 0xFFFF0000u);
+                        }
+                    }
+                    o[ch * cstride] = make_float4(s[0], s[1], s[2], s[3]);
+                    o[ch * cstride + 1] = make_float4(s[4], s[5], s[6], s[7]);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");                // F tile free again
         }
     }
 
@@ -192,7 +227,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) conv1x1_planes_kernel(const _
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 

@@ -369,14 +369,16 @@ class NetHandle:
         buf = (C.c_float * 12)()
         check(lib.dmf_net_get_dense_timing(self._h, buf, 1 if reset else 0))
         names = ['ms_stem_maps', 'conv_ms2', 'pool_ms2', 'pan_stem_maps', 'conv_pan2', 'pool_pan2', 'conv_pan3', 'pool_pan3',
-                 'conv_fuse', 'head', '_', 'total']
+                 'conv_fuse', 'head', '_', 'total']      # conv_* include the fused pooling (pool_* stay 0); conv_fuse includes the row sums
         return {k: float(v) for k, v in zip(names, buf) if k != '_'}
 
     def dense_buffer(self, name):
-        """test hook: a dense-path map as a flat bf16 tensor aliasing the library's workspace, and (rows, cols) of the MS grid"""
+        """test hook: a dense-path map as a flat tensor aliasing the library's workspace (bf16; the row sums "S" are fp32), and
+        (rows, cols) of the MS grid"""
         ptr, nbytes, dims = C.c_void_p(), C.c_int64(), (C.c_int32 * 2)()
         check(lib.dmf_net_dense_buffer(self._h, name.encode(), C.byref(ptr), C.byref(nbytes), dims))
-        return _from_ptr(ptr.value, nbytes.value, self.device).view(torch.bfloat16), (int(dims[0]), int(dims[1]))
+        t = _from_ptr(ptr.value, nbytes.value, self.device)
+        return t.view(torch.float32 if name == 'S' else torch.bfloat16), (int(dims[0]), int(dims[1]))
 
     def set_timing(self, on):
         check(lib.dmf_net_set_timing(self._h, 1 if on else 0))

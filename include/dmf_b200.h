@@ -157,9 +157,9 @@ int dmf_infer_scene_dense(dmf_net* n, const dmf_scene* s, int row0, int row1, fl
                           uint8_t* pred_map_dev, int64_t* cm_dev, void* stream);
 int dmf_net_set_dense(dmf_net* n, int enabled, int band_rows);
 /* accumulated device time per stage of the dense path (needs dmf_net_set_timing(n,1)): out[0..10] = ms stem maps,
- * ms2 conv+pool, (unused), pan stem maps, pan2 conv+pool, (unused), pan3 conv+pool, (unused), fuse conv, head, -; out[11] = total */
+ * ms2 conv+pool, (unused), pan stem maps, pan2 conv+pool, (unused), pan3 conv+pool, (unused), fuse conv + row sums, head, -; out[11] = total */
 int dmf_net_get_dense_timing(dmf_net* n, float out_ms[12], int reset);
-/* test hook: device pointer of a dense-path map ("A","CAT","B1","B2","F"); dims = rows, cols of the MS grid */
+/* test hook: device pointer of a dense-path map ("A","CAT","B1","B2" bf16, "S" fp32); dims = rows, cols of the MS grid */
 int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* bytes_out, int32_t dims[2]);
 /* device time of each stage of the last forward call, in ms (synchronises): out[0..7] = stem_ms,
  * conv_ms2, stem_pan, conv_pan2, conv_pan3, conv_fuse, head, total; needs dmf_net_set_timing(n,1). */

@@ -108,7 +108,7 @@ def test_dense_layers_in_isolation(dmf, p, H, W, row0, nb):
     B1, _ = h.dense_buffer('B1')
     B2, _ = h.dense_buffer('B2')
     CAT, _ = h.dense_buffer('CAT')
-    Fm, _ = h.dense_buffer('F')
+    Sm, _ = h.dense_buffer('S')
     R, Cc = dims
     with torch.no_grad():
         # stems: fp32 weights (CUDA cores), bf16-rounded output
@@ -123,8 +123,16 @@ def test_dense_layers_in_isolation(dmf, p, H, W, row0, nb):
         assert_close_bf16(got_b2, ref_block(ref.pan2, got_b1, True), 'pan2 (conv_pool4: conv + aligned 2x2 max fused)')
         got_p3 = gather_patches(CAT, 32, dims, anchors, p // 2, 1, 2, 16, 16)
         assert_close_bf16(got_p3, ref_block(ref.pan3, got_b2, True), 'pan3 (conv_pool4, stride-1 pool)')
-        got_f = gather_patches(Fm, 16, dims, anchors, p // 2, 1, 2)
-        assert_close_bf16(got_f, ref_block(ref.fuse, torch.cat([got_ms2, got_p3], 1), False), 'fuse (conv1x1_planes)')
+        # fusion conv + row sums (fuse_rowsum_kernel): F stays on chip; S[a][ch][X][y][8] = sum_l F[a, cls(l)][X][y + 2l] in fp32.
+        # The patch sum of the reference fusion output must equal sum_k S[cls(k)][xl + 2k][y].
+        want_f = ref_block(ref.fuse, torch.cat([got_ms2, got_p3], 1), False)           # [N][128][P2][P2], bf16-rounded
+        P2, rows_b = p // 2, nb + p - 1
+        S5 = Sm[:3 * 16 * rows_b * W * 8].view(3, 16, rows_b, W, 8)
+        for i, (xl, y) in enumerate(anchors):
+            got_sum = sum(S5[c3(k, P2), :, xl + 2 * k, y, :] for k in range(P2)).reshape(128)
+            want_sum = want_f[i].sum(dim=(1, 2))
+            tol = (2 * 2.0 ** -8 * want_f[i].abs() + 1e-3).sum(dim=(1, 2))
+            assert bool(((got_sum - want_sum).abs() <= tol).all()), 'fuse + row sums: max err %g' % float((got_sum - want_sum).abs().max())
     h.close()
 
 
