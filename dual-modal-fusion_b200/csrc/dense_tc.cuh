@@ -480,45 +480,60 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
                 P.out + ((((int64_t)cls_s[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
             mbar_wait(tfull_bar(buf), use & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = c_lo; c0 < ((P.dbg & 2) ? 0 : c_lo + C_SPAN); c0 += 32) {
-                // The packed weights carry sign(BN scale) and P.scale holds |scale|, so max_s relu(scale * z_s + shift) =
-                // relu(|scale| * max_s z'_s + shift): one FMNMX per accumulator value, the affine + ReLU + bf16 rounding once.
-                uint32_t m0[32], m1[32];
-                tmem_ld32_nowait(t_row + (uint32_t)(0 * C_OUT + c0), m0);
-                tmem_ld32_nowait(t_row + (uint32_t)(1 * C_OUT + c0), m1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // The packed weights carry sign(BN scale) and P.scale holds |scale|, so max_s relu(scale * z_s + shift) =
+            // relu(|scale| * max_s z'_s + shift): one FMNMX per accumulator value, the affine + ReLU + bf16 rounding once.
+            // Phase 1 reduces the 4 accumulators into registers and hands TMEM back to the MMA warp; phase 2 (affine, ReLU, bf16,
+            // stores) then runs under the next tile's MMAs.
+            constexpr int NG = C_SPAN / 32;                      // 32-channel groups per thread
+            uint32_t mx[NG][32];
+            if (!(P.dbg & 2)) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) m0[k] = __float_as_uint(fmaxf(__uint_as_float(m0[k]), __uint_as_float(m1[k])));
-                tmem_ld32_nowait(t_row + (uint32_t)(2 * C_OUT + c0), m1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int g = 0; g < NG; ++g) {
+                    const int c0 = c_lo + 32 * g;
+                    uint32_t m1[32];
+                    tmem_ld32_nowait(t_row + (uint32_t)(0 * C_OUT + c0), mx[g]);
+                    tmem_ld32_nowait(t_row + (uint32_t)(1 * C_OUT + c0), m1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < 32; ++k) m0[k] = __float_as_uint(fmaxf(__uint_as_float(m0[k]), __uint_as_float(m1[k])));
-                tmem_ld32_nowait(t_row + (uint32_t)(3 * C_OUT + c0), m1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint32_t pk[16];
-                const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
-                const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+                    for (int k = 0; k < 32; ++k) mx[g][k] = __float_as_uint(fmaxf(__uint_as_float(mx[g][k]), __uint_as_float(m1[k])));
+                    tmem_ld32_nowait(t_row + (uint32_t)(2 * C_OUT + c0), m1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float4 sc = sc4[k], sh = sh4[k];
-                    const float a0 = fmaxf(fmaf(fmaxf(__uint_as_float(m0[4 * k]), __uint_as_float(m1[4 * k])), sc.x, sh.x), 0.f);
-                    const float a1 = fmaxf(fmaf(fmaxf(__uint_as_float(m0[4 * k + 1]), __uint_as_float(m1[4 * k + 1])), sc.y, sh.y), 0.f);
-                    const float a2 = fmaxf(fmaf(fmaxf(__uint_as_float(m0[4 * k + 2]), __uint_as_float(m1[4 * k + 2])), sc.z, sh.z), 0.f);
-                    const float a3 = fmaxf(fmaf(fmaxf(__uint_as_float(m0[4 * k + 3]), __uint_as_float(m1[4 * k + 3])), sc.w, sh.w), 0.f);
-                    pk[2 * k] = pack_bf16x2(a0, a1);
-                    pk[2 * k + 1] = pack_bf16x2(a2, a3);
-                }
-                if (valid) {
+                    for (int k = 0; k < 32; ++k) mx[g][k] = __float_as_uint(fmaxf(__uint_as_float(mx[g][k]), __uint_as_float(m1[k])));
+                    tmem_ld32_nowait(t_row + (uint32_t)(3 * C_OUT + c0), m1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4)
-                        *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + s4) * cstride) =
-                            make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                    for (int k = 0; k < 32; ++k) mx[g][k] = __float_as_uint(fmaxf(__uint_as_float(mx[g][k]), __uint_as_float(m1[k])));
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (!(P.dbg & 2)) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const int c0 = c_lo + 32 * g;
+                    uint32_t pk[16];
+                    const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
+                    const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 sc = sc4[k], sh = sh4[k];
+                        const float a0 = fmaxf(fmaf(__uint_as_float(mx[g][4 * k]), sc.x, sh.x), 0.f);
+                        const float a1 = fmaxf(fmaf(__uint_as_float(mx[g][4 * k + 1]), sc.y, sh.y), 0.f);
+                        const float a2 = fmaxf(fmaf(__uint_as_float(mx[g][4 * k + 2]), sc.z, sh.z), 0.f);
+                        const float a3 = fmaxf(fmaf(__uint_as_float(mx[g][4 * k + 3]), sc.w, sh.w), 0.f);
+                        pk[2 * k] = pack_bf16x2(a0, a1);
+                        pk[2 * k + 1] = pack_bf16x2(a2, a3);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; ++s4)
+                            *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + s4) * cstride) =
+                                make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
+                    }
+                }
+            }
         }
     }
 
