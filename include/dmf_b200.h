@@ -151,7 +151,7 @@ int dmf_infer_scene(dmf_net* n, const dmf_scene* s, int row0, int row1, uint8_t*
 /* Scene-dense evaluation of the same band (csrc/dense.cu): whole-scene inference visits patches at stride 1, so
  * every layer is computed once per scene position and border class instead of once per patch; same results up to
  * fp32 summation order.  logits_out_dev: [(row1-row0)*W][C] f32 or NULL.  dmf_infer_scene uses this path unless
- * dmf_net_set_dense(n, 0, 0) selects the per-patch kernels; band_rows = anchor rows per pass (workspace ~ 13 KB per
+ * dmf_net_set_dense(n, 0, 0) selects the per-patch kernels; band_rows = anchor rows per pass (workspace ~ 11 KB per
  * map position; 0 keeps the current value, default 512). */
 int dmf_infer_scene_dense(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logits_out_dev,
                           uint8_t* pred_map_dev, int64_t* cm_dev, void* stream);
