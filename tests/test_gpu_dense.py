@@ -242,3 +242,20 @@ def test_dense_degenerate_scene_shapes(dmf, p, H, W):
     assert float((lg_d - lg_p).abs().max()) <= LOGIT_ATOL + LOGIT_RTOL * float(lg_p.abs().max())
     assert float((pm_d == pm_p).float().mean()) >= 0.999
     h.close()
+
+
+@pytest.mark.parametrize('C', [2, 37, 64])
+def test_dense_class_counts(dmf, C):
+    """Class counts from the minimum to the maximum the C-ABI accepts (the head's class loop, logits layout, histogram size)."""
+    p, H, W = 8, 20, 150
+    ms, pan, label, sc, ref, h = scene_and_net(dmf, p, H, W, C, seed=31)
+    h.set_dense(True, band_rows=64)
+    pm_d, cm_d, lg_d = h.infer_scene(sc, want_logits=True)
+    h.set_dense(False)
+    pm_p, cm_p, lg_p = h.infer_scene(sc, want_logits=True)
+    torch.cuda.synchronize()
+    assert int(cm_d.sum()) == H * W and int(pm_d.max()) < C
+    assert float((lg_d - lg_p).abs().max()) <= LOGIT_ATOL + LOGIT_RTOL * float(lg_p.abs().max())
+    assert torch.equal(lg_d.max(1)[1].to(torch.uint8).view(H, W), pm_d)
+    assert np.array_equal(cm_d.cpu().numpy().astype(np.float64), orc.confusion(pm_d.cpu().numpy().reshape(-1), label.reshape(-1), C))
+    h.close()
