@@ -609,7 +609,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
         mark();          // (stage slot of the former separate pooling pass)
         // ---- PAN branch
         pan_stem_map_kernel<<<dim3(grid_for((int64_t)2 * rows * C2, 256, 8), C_PAN1 / 8), 256, 0, st>>>(
-            s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
+            n->use_mspan ? s->mspan : s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
         DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2, 8>(d->mapB1, true, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, rows, R1, C1, st)));
@@ -678,6 +678,7 @@ int dmf_infer_scene_dense(dmf_net* n, const dmf_scene* s, int row0, int row1, fl
     DMF_REQUIRE(s && row0 >= 0 && row1 >= row0 && row1 <= s->H, "infer_scene_dense: bad row band [%d,%d)", row0, row1);
     DMF_REQUIRE(s->p == n->p, "infer_scene_dense: scene patch size %d != net patch size %d", s->p, n->p);
     DMF_REQUIRE(!cm_dev || s->label, "infer_scene_dense: confusion matrix needs dmf_scene_set_labels");
+    DMF_REQUIRE(!n->use_mspan || s->mspan, "infer_scene_dense: the IHS product was selected as input but the scene has none (dmf_scene_set_mspan)");
     if (row1 == row0) return DMF_OK;
     return dense_infer(n, s, row0, row1, logits_out_dev, pred_map_dev, cm_dev, (cudaStream_t)stream);
 }

@@ -434,7 +434,7 @@ static int launch_stems(dmf_net* n, const PatchSrc& src, bool from_scene, int64_
     if (which & 2) {
         auto l2 = [](int v) { int e = 0; while ((1 << e) < v) ++e; return e; };
         tc::StemPanParams Q;
-        Q.scene_pan = src.scene.pan; Q.pan_pitch = src.scene.pan_pitch; Q.scene_W = src.scene.W;
+        Q.scene_pan = (from_scene && n->use_mspan) ? src.scene.mspan : src.scene.pan; Q.pan_pitch = src.scene.pan_pitch; Q.scene_W = src.scene.W;
         Q.idx = src.idx; Q.first = src.first; Q.patches = src.patches; Q.from_scene = from_scene ? 1 : 0;
         Q.p = n->p; Q.S_l2 = l2(2 * n->p); Q.tpp_l2 = l2(4 * n->p * n->p / 128); Q.N = N;
         Q.n_stage = stem_pan_stages(n->p); Q.raw_pitch = stem_pan_raw_pitch(n->p);
@@ -611,6 +611,12 @@ int dmf_net_finalize(dmf_net* n, void* stream) {
     return DMF_OK;
 }
 
+int dmf_net_set_pan_source(dmf_net* n, int use_mspan) {
+    DMF_REQUIRE(n, "net_set_pan_source: null");
+    n->use_mspan = use_mspan ? 1 : 0;
+    return DMF_OK;
+}
+
 int dmf_net_set_timing(dmf_net* n, int enabled) {
     DMF_REQUIRE(n, "net_set_timing: null");
     n->timing = enabled != 0;
@@ -665,6 +671,7 @@ int dmf_net_forward_scene(dmf_net* n, const dmf_scene* s, const int64_t* flat_id
     DMF_REQUIRE(s && N >= 0, "net_forward_scene: bad argument");
     DMF_REQUIRE(s->p == n->p, "net_forward_scene: scene patch size %d != net patch size %d", s->p, n->p);
     DMF_REQUIRE(!cm_dev || s->label, "net_forward_scene: confusion matrix needs dmf_scene_set_labels");
+    DMF_REQUIRE(!n->use_mspan || s->mspan, "net_forward_scene: the IHS product was selected as input but the scene has none (dmf_scene_set_mspan)");
     DMF_REQUIRE(flat_idx_dev || (first >= 0 && first + N <= (int64_t)s->H * s->W), "net_forward_scene: pixel range outside the scene");
     for (int64_t o = 0; o < N; o += n->NB) {
         const int64_t nb = std::min<int64_t>(n->NB, N - o);

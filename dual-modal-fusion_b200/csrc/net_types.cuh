@@ -43,6 +43,7 @@ struct dmf_net {
     dmf::DenseWs* dense = nullptr;
     int dense_band = 512;     // anchor rows per band of the dense path
     int dense_mode = 1;       // dmf_infer_scene: 1 = scene-dense maps, 0 = per-patch kernels
+    int use_mspan = 0;        // scene inference reads the IHS product (dataset_tri's third raster) as the PAN input
 };
 
 namespace dmf {

@@ -365,6 +365,10 @@ class NetHandle:
         check(lib.dmf_net_set_dense(self._h, 1 if enabled else 0, int(band_rows)))
         self.dense = bool(enabled)
 
+    def set_pan_source(self, use_mspan):
+        """Scene inference reads the scene's IHS product (Scene.set_mspan) instead of the PAN raster (IHS-input models)."""
+        check(lib.dmf_net_set_pan_source(self._h, 1 if use_mspan else 0))
+
     def get_dense_timing(self, reset=True):
         buf = (C.c_float * 12)()
         check(lib.dmf_net_get_dense_timing(self._h, buf, 1 if reset else 0))

@@ -44,6 +44,7 @@ SIGNATURES = {
     'dmf_net_set_dense': (i32, [vp, i32, i32]),
     'dmf_net_get_dense_timing': (i32, [vp, C.POINTER(C.c_float), i32]),
     'dmf_net_dense_buffer': (i32, [vp, cstr, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int32)]),
+    'dmf_net_set_pan_source': (i32, [vp, i32]),
     'dmf_net_set_timing': (i32, [vp, i32]),
     'dmf_net_get_timing': (i32, [vp, C.POINTER(C.c_float)]),
     'dmf_net_debug_layer': (i32, [vp, i32, i32, vp, vp, i64, vp]),

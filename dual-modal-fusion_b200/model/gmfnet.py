@@ -102,8 +102,12 @@ class Net(nn.Module):
             self._native_key = key
         return self._native
 
-    def infer_scene(self, scene, row0=0, row1=None, pred_map=None, cm=None):
-        return self.native().infer_scene(scene, row0, row1, pred_map, cm)
+    def infer_scene(self, scene, row0=0, row1=None, pred_map=None, cm=None, use_mspan=False):
+        """Whole-band inference; use_mspan feeds the scene's IHS product (Scene.set_mspan) as the PAN input, the evaluation
+        counterpart of train_step_scene(..., use_mspan=True)."""
+        h = self.native()
+        h.set_pan_source(use_mspan)
+        return h.infer_scene(scene, row0, row1, pred_map, cm)
 
     # ---------------------------------------------------------------- native training
     def trainer(self):

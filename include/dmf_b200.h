@@ -161,6 +161,9 @@ int dmf_net_set_dense(dmf_net* n, int enabled, int band_rows);
 int dmf_net_get_dense_timing(dmf_net* n, float out_ms[12], int reset);
 /* test hook: device pointer of a dense-path map ("A","CAT","B1","B2" bf16, "S" fp32); dims = rows, cols of the MS grid */
 int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* bytes_out, int32_t dims[2]);
+/* IHS-input models (trained with dmf_train_step_scene(..., use_mspan = 1)): scene inference (dmf_net_forward_scene,
+ * dmf_infer_scene, dmf_infer_scene_dense) reads the scene's IHS product (dmf_scene_set_mspan) in place of the PAN raster. */
+int dmf_net_set_pan_source(dmf_net* n, int use_mspan);
 /* device time of each stage of the last forward call, in ms (synchronises): out[0..7] = stem_ms,
  * conv_ms2, stem_pan, conv_pan2, conv_pan3, conv_fuse, head, total; needs dmf_net_set_timing(n,1). */
 int dmf_net_set_timing(dmf_net* n, int enabled);

@@ -259,3 +259,31 @@ def test_dense_class_counts(dmf, C):
     assert torch.equal(lg_d.max(1)[1].to(torch.uint8).view(H, W), pm_d)
     assert np.array_equal(cm_d.cpu().numpy().astype(np.float64), orc.confusion(pm_d.cpu().numpy().reshape(-1), label.reshape(-1), C))
     h.close()
+
+
+def test_ihs_product_as_pan_input(dmf):
+    """set_pan_source(True): scene inference reads the scene's IHS product (dataset_tri's third raster, train/dataset.py:259-279)
+    in place of PAN — same logits as a scene whose PAN raster IS that product, on the dense path and on the per-patch kernels."""
+    p, H, W, C = 16, 24, 40, 6
+    ms, pan, label, sc, ref, h = scene_and_net(dmf, p, H, W, C, seed=41)
+    g = np.random.default_rng(5)
+    mspan_pad = g.random((4 * H + 4 * p - 1, 4 * W + 4 * p - 1)).astype(np.float32)      # stands for data_padding(IHS_tran(...))
+    sc.set_mspan(mspan_pad)
+    ms_pad = sc.export(0).cpu().numpy()
+    twin = dmf.Scene.from_padded(ms_pad, mspan_pad, p, DEV)                              # PAN := the product
+    twin.set_labels(label)
+    for dense in (True, False):
+        h.set_dense(dense, band_rows=16)
+        h.set_pan_source(True)
+        pm_a, cm_a, lg_a = h.infer_scene(sc, want_logits=True)
+        h.set_pan_source(False)
+        pm_b, cm_b, lg_b = h.infer_scene(twin, want_logits=True)
+        pm_c, _, lg_c = h.infer_scene(sc, want_logits=True)                              # plain PAN input: must differ
+        torch.cuda.synchronize()
+        assert torch.equal(lg_a, lg_b) and torch.equal(pm_a, pm_b) and torch.equal(cm_a, cm_b)
+        assert not torch.equal(lg_a, lg_c)
+    bare = dmf.Scene.from_raw(ms, pan, p, DEV)
+    h.set_pan_source(True)
+    with pytest.raises(RuntimeError, match='IHS product'):
+        h.infer_scene(bare)
+    h.close()
