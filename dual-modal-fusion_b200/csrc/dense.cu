@@ -683,6 +683,25 @@ int dmf_infer_scene_dense(dmf_net* n, const dmf_scene* s, int row0, int row1, fl
     return dense_infer(n, s, row0, row1, logits_out_dev, pred_map_dev, cm_dev, (cudaStream_t)stream);
 }
 
+/* test hook (host only, no GPU): the class table conv_pool4_kernel gets for pooled border class (a, b).  aligned = 1: pan2 (phase
+ * planes, boxes of 17 x 9 cells, 4 chunks per step); 0: the stride-1 layers (19 x 11, 2 chunks).  win[16], box_plane[9], box_drow[9],
+ * box_dcol[9]; returns the box slot size in bytes through *slot_bytes and the box count through *n_boxes. */
+int dmf_dense_class_table(int a, int b, int aligned, int16_t* win, int16_t* box_plane, int8_t* box_drow, int8_t* box_dcol, int32_t* n_boxes,
+                          int32_t* slot_bytes) {
+    DMF_REQUIRE(a >= 0 && a < 3 && b >= 0 && b < 3 && win && box_plane && box_drow && box_dcol && n_boxes && slot_bytes, "dense_class_table: bad argument");
+    tc::Pool4Cls c;
+    using CfgA = tc::Pool4Cfg<C_PAN1, C_PAN2, 4, 2, 17, 9, 2>;
+    using CfgS = tc::Pool4Cfg<C_MS1, C_MS2, 2, 3, 19, 11, 1>;
+    DMF_TRY(aligned ? build_pool4_cls(c, a, b, true, 17, 9, CfgA::MAX_BOXES, CfgA::BOX_SLOT) : build_pool4_cls(c, a, b, false, 19, 11, CfgS::MAX_BOXES, CfgS::BOX_SLOT));
+    memcpy(win, c.win, sizeof(c.win));
+    memcpy(box_plane, c.box_plane, sizeof(c.box_plane));
+    memcpy(box_drow, c.box_drow, sizeof(c.box_drow));
+    memcpy(box_dcol, c.box_dcol, sizeof(c.box_dcol));
+    *n_boxes = c.n_boxes;
+    *slot_bytes = (int32_t)(aligned ? CfgA::BOX_SLOT : CfgS::BOX_SLOT);
+    return DMF_OK;
+}
+
 int dmf_net_get_dense_timing(dmf_net* n, float out_ms[12], int reset) {
     DMF_REQUIRE(n && out_ms, "net_get_dense_timing: null");
     if (!n->dense) { memset(out_ms, 0, 12 * sizeof(float)); return DMF_OK; }

@@ -43,6 +43,7 @@ SIGNATURES = {
     'dmf_infer_scene_dense': (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
     'dmf_net_set_dense': (i32, [vp, i32, i32]),
     'dmf_net_get_dense_timing': (i32, [vp, C.POINTER(C.c_float), i32]),
+    'dmf_dense_class_table': (i32, [i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'dmf_net_dense_buffer': (i32, [vp, cstr, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int32)]),
     'dmf_net_set_pan_source': (i32, [vp, i32]),
     'dmf_net_set_timing': (i32, [vp, i32]),

@@ -159,6 +159,9 @@ int dmf_net_set_dense(dmf_net* n, int enabled, int band_rows);
 /* accumulated device time per stage of the dense path (needs dmf_net_set_timing(n,1)): out[0..10] = ms stem maps,
  * ms2 conv+pool, (unused), pan stem maps, pan2 conv+pool, (unused), pan3 conv+pool, (unused), fuse conv + row sums, head, -; out[11] = total */
 int dmf_net_get_dense_timing(dmf_net* n, float out_ms[12], int reset);
+/* test hook (host only): the per-class window / box table of the fused conv + pool kernel (csrc/dense_tc.cuh), see dense.cu */
+int dmf_dense_class_table(int a, int b, int aligned, int16_t* win, int16_t* box_plane, int8_t* box_drow, int8_t* box_dcol,
+                          int32_t* n_boxes, int32_t* slot_bytes);
 /* test hook: device pointer of a dense-path map ("A","CAT","B1","B2" bf16, "S" fp32); dims = rows, cols of the MS grid */
 int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* bytes_out, int32_t dims[2]);
 /* IHS-input models (trained with dmf_train_step_scene(..., use_mspan = 1)): scene inference (dmf_net_forward_scene,

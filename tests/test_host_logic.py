@@ -171,3 +171,54 @@ def test_band_slice_reproduces_whole_scene_windows():
                 assert np.array_equal(band_pad[x - s0:x - s0 + p], whole[x:x + p]), (H, p, world, rank, x)
             covered[r0:r1] += 1
         assert (covered == 1).all()
+
+
+@pytest.mark.parametrize('aligned', [0, 1])
+def test_dense_class_tables_match_brute_force(aligned):
+    """The window / box table of conv_pool4_kernel (csrc/dense.cu::build_pool4_cls) against a brute-force walk over a patch:
+    for pooled border class (a, b), sub-position (s, t) and tap (dy, dx), the input the conv reads sits at a definite offset from
+    the pooled cell's origin, carries a definite border variant, and (aligned pooling) lives in a definite parity phase.  The
+    table must send that (offset) to a box holding exactly that plane, at exactly that cell shift."""
+    import dmf._lib as L
+    box_rows, box_cols, kq = (17, 9, 4) if aligned else (19, 11, 2)
+    plane_bytes = box_rows * box_cols * 16
+    for a in range(3):
+        for b in range(3):
+            win = (ctypes.c_int16 * 16)()
+            bp = (ctypes.c_int16 * 9)()
+            dr, dc = (ctypes.c_int8 * 9)(), (ctypes.c_int8 * 9)()
+            nb, slot = ctypes.c_int32(), ctypes.c_int32()
+            L.check(L.lib.dmf_dense_class_table(a, b, aligned, win, bp, dr, dc, ctypes.byref(nb), ctypes.byref(slot)))
+            assert slot.value % 128 == 0 and slot.value >= kq * plane_bytes
+            for P2 in (4, 8, 16):                                 # pooled cells per axis of the layer's OUTPUT (p/2 or p)
+                S = 2 * P2                                        # conv positions per axis
+                cell = {0: 0, 1: 1, 2: P2 - 1}                    # a representative cell index of each border class
+                for s in range(2):
+                    for t in range(2):
+                        for dy in (-1, 0, 1):
+                            for dx in (-1, 0, 1):
+                                if aligned:
+                                    i, j = 2 * cell[a] + s + dy, 2 * cell[b] + t + dx      # patch-relative input position
+                                else:
+                                    # stride-1 pooling: the layer's input and conv grids coincide; cell k covers conv rows k', k'+1 of
+                                    # a patch whose pooled cell k sits at conv row 2k: same arithmetic with the conv row 2k + s
+                                    i, j = 2 * cell[a] + s + dy, 2 * cell[b] + t + dx
+                                orow, ocol = s + dy, t + dx
+                                w = win[(orow + 1) * 4 + ocol + 1]
+                                if not (0 <= i < S and 0 <= j < S):
+                                    assert w == -1, (a, b, s, t, dy, dx)
+                                    continue
+                                assert w >= 0
+                                vr = 0 if i == 0 else (2 if i == S - 1 else 1)
+                                vc = 0 if j == 0 else (2 if j == S - 1 else 1)
+                                k, rem = divmod(w * 16, slot.value)
+                                assert k < nb.value and rem % 16 == 0
+                                r_in, c_in = divmod(rem // 16, box_cols)
+                                assert r_in + 16 <= box_rows and c_in + 8 <= box_cols
+                                if aligned:
+                                    want_plane = (vr * 3 + vc) * 4 + (orow & 1) * 2 + (ocol & 1)
+                                    want_shift = (orow // 2, ocol // 2)                    # floor division: -1 -> -1
+                                else:
+                                    want_plane, want_shift = vr * 3 + vc, (orow, ocol)
+                                assert bp[k] == want_plane, (a, b, s, t, dy, dx, bp[k], want_plane)
+                                assert (dr[k] + r_in, dc[k] + c_in) == want_shift
