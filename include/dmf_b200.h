@@ -78,7 +78,8 @@ int dmf_scene_create_raw(dmf_scene** out, const void* ms, int ms_dtype, const vo
  * loop, e.g. tiles of a mosaic). */
 int dmf_scene_update_raw(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype,
                          int on_device, void* stream);
-/* Row-band scenes (one band of a larger scene per GPU): min / max of a raw raster on the device (lohi_out_dev = 2 doubles),
+/* Row-band scenes (one band of a larger scene per GPU).  to_tensor (function/function.py:120-124) normalises with the min / max of
+ * the WHOLE raster: dmf_raster_minmax gives a band's min / max on the device (lohi_out_dev = 2 doubles) for the ranks to all-reduce,
  * and a re-fill that normalises with GIVEN ranges (device {min, max} pairs, e.g. the all-reduced ranges of all bands) instead of
  * the band's own.  A band made of scene rows [s0, s1) with s1 = min(H, r1 + p - 1) reproduces the whole scene's windows for the
  * anchors of rows [r0, r1): interior bands carry the next band's first p-1 rows, the last band's reflect padding is its own. */
@@ -148,7 +149,8 @@ int dmf_net_forward_scene(dmf_net* n, const dmf_scene* s, const int64_t* flat_id
  * (solver/mainsolver.py:167-185, train/test.py:58-60) in one call. */
 int dmf_infer_scene(dmf_net* n, const dmf_scene* s, int row0, int row1, uint8_t* pred_map_dev,
                     int64_t* cm_dev, void* stream);
-/* Scene-dense evaluation of the same band (csrc/dense.cu): whole-scene inference visits patches at stride 1, so
+/* Scene-dense evaluation of the same band (csrc/dense.cu) — replaces the two whole-scene loader passes of Solver.color()
+ * (solver/mainsolver.py:167-185) and the full-loader Solver.test() (:104-141): whole-scene inference visits patches at stride 1, so
  * every layer is computed once per scene position and border class instead of once per patch; same results up to
  * fp32 summation order.  logits_out_dev: [(row1-row0)*W][C] f32 or NULL.  dmf_infer_scene uses this path unless
  * dmf_net_set_dense(n, 0, 0) selects the per-patch kernels; band_rows = anchor rows per pass (workspace ~ 11 KB per
@@ -164,7 +166,8 @@ int dmf_dense_class_table(int a, int b, int aligned, int16_t* win, int16_t* box_
                           int32_t* n_boxes, int32_t* slot_bytes);
 /* test hook: device pointer of a dense-path map ("A","CAT","B1","B2" bf16, "S" fp32); dims = rows, cols of the MS grid */
 int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* bytes_out, int32_t dims[2]);
-/* IHS-input models (trained with dmf_train_step_scene(..., use_mspan = 1)): scene inference (dmf_net_forward_scene,
+/* IHS-input models (dataset_tri's third raster, train/dataset.py:259-279; trained with dmf_train_step_scene(..., use_mspan = 1)):
+ * scene inference (dmf_net_forward_scene,
  * dmf_infer_scene, dmf_infer_scene_dense) reads the scene's IHS product (dmf_scene_set_mspan) in place of the PAN raster. */
 int dmf_net_set_pan_source(dmf_net* n, int use_mspan);
 /* device time of each stage of the last forward call, in ms (synchronises): out[0..7] = stem_ms,
@@ -228,7 +231,8 @@ int dmf_train_debug_op(dmf_train* t, int op, int layer, int64_t N, void* stream)
 int dmf_argmax_confusion(const float* logits_dev, const void* target_dev, int target_dtype, int64_t N,
                          int C, int64_t* pred_out_dev, int64_t* cm_dev, void* stream);
 
-/* The same matrix from whole-scene maps: cm[pred_map[k]][label_map[k]] += 1 for k in flat_idx (NULL = the first N pixels).
+/* The same matrix (solver/mainsolver.py:139-141) from whole-scene maps: cm[pred_map[k]][label_map[k]] += 1 for k in flat_idx (NULL =
+ * the first N pixels).
  * Lets Solver.test() take its loader's sample set out of one scene-dense pass instead of running the network per sample. */
 int dmf_confusion_at(const uint8_t* pred_map_dev, const uint8_t* label_map_dev, const int64_t* flat_idx_dev, int64_t N,
                      int C, int64_t* cm_dev, void* stream);
