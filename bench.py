@@ -377,19 +377,28 @@ def main():
         handle.set_timing(False)
         band = max(1, min(args.band, r1 - r0))
         bands = [min(band, r1 - b) for b in range(r0, r1, band)]
-        pos = sum((nb + P - 1) * (W + P - 1) for nb in bands)                 # MS-resolution map positions computed
-        kernels = {   # kernel -> (stage keys, FLOPs per MS-resolution position, launches per band)
-            'conv_pool4_kernel<64,128,KQ=2,3 stages> (ms2 + pan3: conv + stride-1 2x2 max, 9 pooled classes)':
-                (['conv_ms2', 'conv_pan3'], 2 * 256 * 2 * 64 * 128, 2),
-            'conv_pool4_kernel<32,64,KQ=4,2 stages> (pan2: conv + aligned 2x2 max)': (['conv_pan2'], 256 * 2 * 32 * 64, 1),
+        pos = sum((nb + P - 1) * (W + P - 1) for nb in bands)                 # MS-resolution map positions of the bands
+        tr = (5, 6, 5)                                                        # live tap rows (columns) of the 2 sub-positions per border class
+
+        def taps(nb, cells, step):
+            """tap evaluations of one conv + pool layer over a band: per border class only the rows / columns some anchor uses"""
+            ext = (0, step * (cells - 3), 0)
+            return sum(t * (nb + e) for t, e in zip(tr, ext)) * sum(t * (W + e) for t, e in zip(tr, ext))
+
+        fl_s1 = sum(taps(nb, P // 2, 2) for nb in bands) * 2 * 64 * 128       # ms2, pan3: p/2 pooled cells at x + 2k
+        fl_al = sum(taps(nb, P, 1) for nb in bands) * 2 * 32 * 64             # pan2: p pooled cells at x + k
+        fl_fu = sum(3 * nb + P - 6 for nb in bands) * 3 * (W + P - 1) * 2 * 256 * 128
+        kernels = {   # kernel -> (stage keys, FLOPs executed over all bands, launches per band)
+            'conv_pool4_kernel<64,128,KQ=2,3 stages> (ms2 + pan3: conv + stride-1 2x2 max, 9 pooled classes)': (['conv_ms2', 'conv_pan3'], 2 * fl_s1, 2),
+            'conv_pool4_kernel<32,64,KQ=4,2 stages> (pan2: conv + aligned 2x2 max)': (['conv_pan2'], fl_al, 1),
             'fuse_rowsum_kernel (1x1 fusion conv on 9 planes + row sums of the average pool; no credit for the 128/114 tile overlap)':
-                (['conv_fuse'], 9 * 2 * 256 * 128, 1),
+                (['conv_fuse'], fl_fu, 1),
         }
         ncu_key = {k: v for k, v in zip(kernels, ('tc::conv_pool4_kernel<64,128,2,3,19,11,1,8>', 'tc::conv_pool4_kernel<32,64,4,2,17,9,2,8>',
                                                   'tc::fuse_rowsum_kernel<8>'))}
-        name, (keys, fl_pos, per_band) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
+        name, (keys, fl_k, per_band) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
         k_ms = sum(stage[k] for k in keys)
-        achieved = fl_pos * pos / (k_ms / 1e3) / 1e12
+        achieved = fl_k / (k_ms / 1e3) / 1e12
         conv_fl = sum(v[1] for v in kernels.values())
         conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
         roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
@@ -397,16 +406,16 @@ def main():
                 'traffic': ncu_traffic('r01_dense_ncu_summary.json', ncu_key[name]) if args.band == 512 else None,
                 'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
                 'avg_launch_ms': k_ms / (len(bands) * per_band), 'launches': len(bands) * per_band,
-                'flops_per_launch': fl_pos * pos / (len(bands) * per_band),
+                'flops_per_launch': fl_k / (len(bands) * per_band),
                 'stage_ms': {k: round(v, 3) for k, v in stage.items()},
-                'map_positions': pos, 'flops_executed_per_pixel': conv_fl * pos / n_local,
+                'map_positions': pos, 'flops_executed_per_pixel': conv_fl / n_local,
                 'per_patch_equivalent_tflops': handle.flops_per_patch * n_local / (stage['total'] / 1e3) / 1e12,
                 'note': 'achieved = tensor-core FLOPs this kernel executes / its time; per_patch_equivalent_tflops = the per-patch '
                         'network FLOPs (flops_per_pixel) the same result would cost / whole-step time: it exceeds the peak because '
                         'the dense algorithm shares work between overlapping patches'}
-        util = {'achieved_TFLOPs': conv_fl * pos / (conv_ms / 1e3) / 1e12,
-                'frac_of_sustained_peak': conv_fl * pos / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
-                'frac_of_burst_peak': conv_fl * pos / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
+        util = {'achieved_TFLOPs': conv_fl / (conv_ms / 1e3) / 1e12,
+                'frac_of_sustained_peak': conv_fl / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
+                'frac_of_burst_peak': conv_fl / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
                 'ncu_tensor_pipe_active_pct': 'profiles/r01_dense_ncu_summary.json'}
         return roof, util
 

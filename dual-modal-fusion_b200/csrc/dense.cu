@@ -458,11 +458,24 @@ static int build_pool4_cls(tc::Pool4Cls& c, int a, int b, bool aligned, int box_
 // conv + pool of one layer over the band: in = 9 (x 4 phases) planes, out = 9 pooled planes
 template <int CI, int CO, int KQ, int STAGES, int BR, int BC, int NBUF, int EW>
 static int launch_pool4(const CUtensorMap& map, bool aligned, const __nv_bfloat16* w, const float* scale, const float* shift, __nv_bfloat16* out,
-                        int out_chunks, int out_chunk0, int rows, int R1, int C1, cudaStream_t st) {
+                        int out_chunks, int out_chunk0, int nb, int W, int p, int R1, int C1, cudaStream_t st) {
     using Cfg = tc::Pool4Cfg<CI, CO, KQ, STAGES, BR, BC, NBUF>;
     static_assert(Cfg::SMEM <= (size_t)kSmemLimit, "conv_pool4_kernel does not fit in shared memory");
     tc::Pool4Params P{};
-    P.rows = R1; P.cols = C1; P.tiles_x = cdiv(C1, 8); P.tiles_y = cdiv(rows, 16); P.n_tiles = P.tiles_x * P.tiles_y * 9;
+    P.rows = R1; P.cols = C1;
+    // Output cells per patch axis: aligned pooling (pan2) p cells at X = x + k; stride-1 pooling p/2 cells at X = x + 2k.  A border
+    // class (first / interior / last cell) is only ever read at the rows the band's anchors x in [0, nb) put it on.
+    const int cells = aligned ? p : p / 2, step = aligned ? 1 : 2;
+    const int k_lo[3] = {0, 1, cells - 1}, k_hi[3] = {0, cells - 2, cells - 1};
+    int max_r = 0, max_c = 0;
+    for (int a = 0; a < 3; ++a) {
+        P.row_lo[a] = P.col_lo[a] = step * k_lo[a];
+        P.row_n[a] = nb + step * (k_hi[a] - k_lo[a]);
+        P.col_n[a] = W + step * (k_hi[a] - k_lo[a]);
+        max_r = std::max(max_r, P.row_n[a]);
+        max_c = std::max(max_c, P.col_n[a]);
+    }
+    P.tiles_x = cdiv(max_c, 8); P.tiles_y = cdiv(max_r, 16); P.n_tiles = P.tiles_x * P.tiles_y * 9;
     P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0;
     P.w = w; P.scale = scale; P.shift = shift; P.out = out;
     static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
@@ -604,7 +617,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, b0, rows, R1, C1, d->w_ms1, n->L[4].scale, n->L[4].shift, d->A);
         DMF_LAUNCHED();
         mark();
-        DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1, 8>(d->mapA, false, d->w_cp[0], d->sc_cp[0], d->sh_cp[0], d->CAT, C_CAT / 8, 0, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1, 8>(d->mapA, false, d->w_cp[0], d->sc_cp[0], d->sh_cp[0], d->CAT, C_CAT / 8, 0, nb, W, p, R1, C1, st)));
         mark();
         mark();          // (stage slot of the former separate pooling pass)
         // ---- PAN branch
@@ -612,10 +625,10 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             n->use_mspan ? s->mspan : s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
-        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2, 8>(d->mapB1, true, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2, 8>(d->mapB1, true, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, nb, W, p, R1, C1, st)));
         mark();
         mark();
-        DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1, 8>(d->mapB2s, false, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, rows, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1, 8>(d->mapB2s, false, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, nb, W, p, R1, C1, st)));
         mark();
         mark();
         // ---- fusion conv (1x1) on the 9 pooled planes + row sums of the global average pool
@@ -627,6 +640,10 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             P.dbg = dbg;
             P.w = n->L[3].w; P.scale = n->L[3].scale; P.shift = n->L[3].shift; P.S = reinterpret_cast<float4*>(d->S);
             P.cat = d->CAT; P.R1 = R1; P.C1 = C1;
+            {   // pooled cells k of a patch sit at X = x + 2k: first k = 0, interior 1 .. p/2 - 2, last p/2 - 1
+                const int P2 = p / 2, k_lo[3] = {0, 1, P2 - 1}, k_hi[3] = {0, P2 - 2, P2 - 1};
+                for (int a = 0; a < 3; ++a) { P.row_lo[a] = 2 * k_lo[a]; P.row_n[a] = nb + 2 * (k_hi[a] - k_lo[a]); }
+            }
             auto fk = p == 8 ? tc::fuse_rowsum_kernel<4> : p == 16 ? tc::fuse_rowsum_kernel<8> : tc::fuse_rowsum_kernel<16>;
             fk<<<std::min(P.n_tiles, num_sms()), 320, tc::kFrSmem, st>>>(P);
             DMF_LAUNCHED();

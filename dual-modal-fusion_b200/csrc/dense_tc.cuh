@@ -32,6 +32,7 @@ struct FuseRowsParams {
     int rows, W;                          // map rows of this band, anchor columns
     int tiles_x, n_tiles;
     int s_rows;                           // row dimension of S ([3][16][s_rows][W][8] fp32)
+    int row_lo[3], row_n[3];              // map rows [lo, lo + n) of each row class that some anchor of the band uses
     int R1, C1;                           // CAT plane geometry: [9][32 chunks][R1][C1][8] bf16 (+ 2 KB of slack behind the tensor)
     const __nv_bfloat16* cat;
     int dbg;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
             if (++a == 3) { a = 0; ++X; }
         }
     };
+    auto live = [&]() { return X >= P.row_lo[a] && X < P.row_lo[a] + P.row_n[a]; };    // rows no anchor uses are skipped by every role alike
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
         int st = 0;
         uint32_t ph = 1;
         for (int i = 0; i < n_local; ++i, next_tile()) {
+            if (!live()) continue;
             for (int step = 0; step < 3 * NSTEP; ++step) {
                 mbar_wait(empty_bar(st), ph);
                 if (leader) {
@@ -138,8 +141,11 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
         int st = 0;
         uint32_t ph = 0;
-        for (int i = 0; i < n_local; ++i) {
-            mbar_wait(tempty_bar, (i & 1) ^ 1);
+        int it = 0;                                    // tiles actually processed
+        for (int i = 0; i < n_local; ++i, next_tile()) {
+            if (!live()) continue;
+            mbar_wait(tempty_bar, (it & 1) ^ 1);
+            ++it;
             for (int step = 0; step < 3 * NSTEP; ++step) {
                 const int b = step / NSTEP, kq = step % NSTEP;
                 mbar_wait(full_bar(st), ph);
@@ -164,8 +170,11 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
         const int q = warp & 3, hc = (warp - 2) >> 2;
         const int m = q * 32 + lane;                      // phase 1: column of the tile; phase 2: anchor column
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        int it = 0;                                    // tiles actually processed
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            mbar_wait(tfull_bar, i & 1);
+            if (!live()) continue;
+            mbar_wait(tfull_bar, it & 1);
+            ++it;
             tc_fence_after();
             if (!(P.dbg & 2)) {
 #pragma unroll 1
@@ -281,6 +290,8 @@ struct Pool4Params {
     int tiles_x, tiles_y, n_tiles;
     int out_chunks, out_chunk0;
     int dbg;
+    // rows / columns of each border class (first, interior, last) that some anchor of the band actually uses: [lo, lo + n)
+    int row_lo[3], row_n[3], col_lo[3], col_n[3];
     const __nv_bfloat16* w;               // packed [tap][C_in/8][C_out][8], output channel co multiplied by sign(BN scale[co])
     const float* scale;                   // |BN scale| (its sign is folded into w)
     const float* shift;
@@ -358,6 +369,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
             if (++c == 9) { c = 0; ++ty; }
         }
     };
+    // tiles outside the rows / columns that any anchor of the band uses for this border class are skipped by every role alike
+    auto live = [&]() { return ty * 16 < P.row_n[c / 3] && tx * 8 < P.col_n[c % 3]; };
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer: all boxes of a step land on one barrier
@@ -373,7 +386,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         int st = 0;
         uint32_t ph = 1;
         for (int i = 0; i < n_local; ++i, next_tile()) {
+            if (!live()) continue;
             const int nbx = cls_s[c].n_boxes;
+            const int row0 = P.row_lo[c / 3] + ty * 16, col0 = P.col_lo[c % 3] + tx * 8;
             for (int kq = 0; kq < NSTEP; ++kq) {
                 mbar_wait(empty_bar(st), ph);
                 if (leader) {
@@ -383,8 +398,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
                         mbar_expect_tx(full_bar(st), (uint32_t)nbx * Cfg::BOX_BYTES);
                         const uint32_t dst = smem_u32(a_s) + (uint32_t)st * Cfg::STAGE;
                         for (int b = 0; b < nbx; ++b)
-                            tma_load_4d(dst + (uint32_t)b * Cfg::BOX_SLOT, &in_map, full_bar(st), (tx * 8 + cls_s[c].box_dcol[b]) * 8,
-                                        cls_s[c].box_plane[b], ty * 16 + cls_s[c].box_drow[b], kq * KQ);
+                            tma_load_4d(dst + (uint32_t)b * Cfg::BOX_SLOT, &in_map, full_bar(st), (col0 + cls_s[c].box_dcol[b]) * 8,
+                                        cls_s[c].box_plane[b], row0 + cls_s[c].box_drow[b], kq * KQ);
                     }
                 }
                 __syncwarp();
@@ -399,9 +414,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
         int st = 0;
         uint32_t ph = 0;
+        int it = 0;                                    // tiles actually processed
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            const int buf = NBUF == 2 ? (i & 1) : 0;
-            const int use = NBUF == 2 ? (i >> 1) : i;
+            if (!live()) continue;
+            const int buf = NBUF == 2 ? (it & 1) : 0;
+            const int use = NBUF == 2 ? (it >> 1) : it;
+            ++it;
             mbar_wait(tempty_bar(buf), (use & 1) ^ 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 4 * C_OUT);
             const int16_t* win = cls_s[c].win;
@@ -470,11 +488,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         const int c_lo = NBUF == 2 ? 0 : eg * C_SPAN;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(NBUF == 2 ? eg * 4 * C_OUT : 0);
         const int64_t cstride = (int64_t)P.rows * P.cols * 8;
+        int it = -1;                                   // tiles actually processed
         for (int i = 0; i < n_local; ++i, next_tile()) {
-            if (NBUF == 2 && (i & 1) != eg) continue;
+            if (!live()) continue;
+            ++it;
+            if (NBUF == 2 && (it & 1) != eg) continue;
             const int buf = NBUF == 2 ? eg : 0;
-            const int use = NBUF == 2 ? (i >> 1) : i;
-            const int row = ty * 16 + (m >> 3), col = tx * 8 + (m & 7);
+            const int use = NBUF == 2 ? (it >> 1) : it;
+            const int row = P.row_lo[c / 3] + ty * 16 + (m >> 3), col = P.col_lo[c % 3] + tx * 8 + (m & 7);
             const bool valid = row < P.rows && col < P.cols;
             __nv_bfloat16* const obase =
                 P.out + ((((int64_t)cls_s[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
