@@ -105,86 +105,85 @@ __global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restri
     }
 }
 
-// PAN stem (conv3x3 1->32 + BN + ReLU + maxpool2) on the pooled grid: band-local pooled row Ul <-> pooled row u0 + Ul
-// = PAN rows 2(u0+Ul), 2(u0+Ul)+1.  The pooling grid is aligned to every patch origin (4x is even).  A pooled cell on
-// the first pooled row of a patch = max(first-row variant of its upper conv row, interior variant of its lower one).
-// w: fp32 [32][1][3][3].  grid.y = channel chunk.  out: B1[9][phase 4][4][R1][C1][8], PHASE-SEPARATED: pooled cell (U, V) is
-// stored at (U >> 1, V >> 1) of phase plane (U & 1) * 2 + (V & 1) (see conv_pool4_kernel).  rows / C2 count pooled cells.
-__global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restrict__ pan, int H4p, int W4p, int pitch, int u0, int rows,
+// PAN stem (conv3x3 1->32 + BN + ReLU + maxpool2) on the pooled-once grid (2 cells per pixel and axis; the pooling grid is aligned to
+// every patch origin because 4x is even).  One thread = the 2 x 2 pooled cells of one pixel (I, J) = all four (row, column) parity
+// phases, one 6 x 6 window of PAN, 8 channels.  A cell on an even pooled row can only be the FIRST pooled row of a patch (u = 0) or an
+// interior one, a cell on an odd row only the LAST (u = 2p-1) or interior; columns likewise: 2 x 2 of the 9 border variants exist per
+// phase, the others are never read (conv_pool4_kernel's class table) and are neither computed nor stored.  "First" masks the dy = -1
+// taps of the cell's upper conv row, "last" the dy = +1 taps of its lower one; everything is static per phase.  BN after the max: the
+// weights carry sign(scale), sc_s holds |scale| (max commutes with a non-negative scale).
+// w: fp32 [32][1][3][3].  grid.y = channel chunk.  out: B1[9][phase 4][4][R1][C1][8], PHASE-SEPARATED: pooled cell (U, V) is stored at
+// (U >> 1, V >> 1) of phase plane (U & 1) * 2 + (V & 1).  i0 = first pixel row of the band, rows = pixel rows to produce.
+__global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restrict__ pan, int H4p, int W4p, int pitch, int i0, int rows,
                                                            int R1, int C1, const float* __restrict__ w, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ B1) {
-    const int C2 = 2 * C1;
     __shared__ float w_s[8][9], sc_s[8], sh_s[8];
     const int ch = blockIdx.y;
     for (int i = threadIdx.x; i < 72; i += blockDim.x) w_s[i / 9][i % 9] = scale[ch * 8 + i / 9] < 0.f ? -w[ch * 72 + i] : w[ch * 72 + i];
     if (threadIdx.x < 8) { sc_s[threadIdx.x] = fabsf(scale[ch * 8 + threadIdx.x]); sh_s[threadIdx.x] = shift[ch * 8 + threadIdx.x]; }
     __syncthreads();
-    const int64_t total = (int64_t)rows * C2;
+    const int64_t total = (int64_t)rows * C1;
     const int64_t plane = (int64_t)R1 * C1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int Ul = (int)(i / C2), PY = (int)(i % C2);
-        const int PX = u0 + Ul;
-        float xw[4][4];                  // PAN rows 2PX-1 .. 2PX+2, cols 2PY-1 .. 2PY+2
+        const int Il = (int)(i / C1), J = (int)(i % C1);
+        const int I = i0 + Il;
+        float xw[6][6];                  // PAN rows 4I-1 .. 4I+4, cols 4J-1 .. 4J+4
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int xx = 2 * PX - 1 + a, yy = 2 * PY - 1 + b;
+            for (int b = 0; b < 6; ++b) {
+                const int xx = 4 * I - 1 + a, yy = 4 * J - 1 + b;
                 xw[a][b] = (xx >= 0 && xx < H4p && yy >= 0 && yy < W4p) ? __ldg(pan + (int64_t)xx * pitch + yy) : 0.f;
             }
-        const int pr = Ul & 1, pc = PY & 1;                       // u0 is even: band-local and absolute row parity agree
-        uint32_t out[4][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            // sv[a][b][re][ce]: conv position (a, b) of the pooled cell with its row (column) taps masked as on the patch edge
-            // that position can touch (a = 0: first row, a = 1: last row) when re (ce) = 0, unmasked when 1.  A pooled variant
-            // only ever combines these 4 of the 9 border classes of a position.
-            float sv[2][2][2][2];
+        for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
+            for (int pc = 0; pc < 2; ++pc) {
+                uint32_t out[4][4];      // [edge/interior row variant][edge/interior column variant] -> 8 packed channels
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    float u[3][2];                   // u[dy][ce]
+                for (int j = 0; j < 8; ++j) {
+                    // sv[a][b][re][ce]: conv position (a, b) of this pooled cell with its row (column) taps masked as on the patch edge
+                    // that position can touch (a = 0: first row, a = 1: last row) when re (ce) = 0, unmasked when 1
+                    float sv[2][2][2][2];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const float t0 = xw[a + d][b] * w_s[j][3 * d], t1 = xw[a + d][b + 1] * w_s[j][3 * d + 1], t2 = xw[a + d][b + 2] * w_s[j][3 * d + 2];
-                        u[d][0] = b == 0 ? t1 + t2 : t0 + t1;          // edge column class: no dx = -1 (left) / no dx = +1 (right)
-                        u[d][1] = b == 0 ? u[d][0] + t0 : u[d][0] + t2;
-                    }
+                    for (int a = 0; a < 2; ++a)
 #pragma unroll
-                    for (int ce = 0; ce < 2; ++ce) {
-                        sv[a][b][0][ce] = a == 0 ? u[1][ce] + u[2][ce] : u[0][ce] + u[1][ce];   // edge row class: no dy = -1 (top) / no dy = +1 (bottom)
-                        sv[a][b][1][ce] = a == 0 ? sv[a][b][0][ce] + u[0][ce] : sv[a][b][0][ce] + u[2][ce];
-                    }
+                        for (int b = 0; b < 2; ++b) {
+                            float u[3][2];                   // u[dy][ce]
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                const float t0 = xw[2 * pr + a + d][2 * pc + b] * w_s[j][3 * d], t1 = xw[2 * pr + a + d][2 * pc + b + 1] * w_s[j][3 * d + 1],
+                                            t2 = xw[2 * pr + a + d][2 * pc + b + 2] * w_s[j][3 * d + 2];
+                                u[d][0] = b == 0 ? t1 + t2 : t0 + t1;          // edge column class: no dx = -1 (left) / no dx = +1 (right)
+                                u[d][1] = b == 0 ? u[d][0] + t0 : u[d][0] + t2;
+                            }
+#pragma unroll
+                            for (int ce = 0; ce < 2; ++ce) {
+                                sv[a][b][0][ce] = a == 0 ? u[1][ce] + u[2][ce] : u[0][ce] + u[1][ce];   // edge row class: no dy = -1 / no dy = +1
+                                sv[a][b][1][ce] = a == 0 ? sv[a][b][0][ce] + u[0][ce] : sv[a][b][0][ce] + u[2][ce];
+                            }
+                        }
+#pragma unroll
+                    for (int er = 0; er < 2; ++er)
+#pragma unroll
+                        for (int ec = 0; ec < 2; ++ec) {
+                            // er = 0: this phase's edge row variant (first if pr == 0: the upper conv row is masked; last if pr == 1: the lower)
+                            const int r0e = (er == 0 && pr == 0) ? 0 : 1, r1e = (er == 0 && pr == 1) ? 0 : 1;
+                            const int c0e = (ec == 0 && pc == 0) ? 0 : 1, c1e = (ec == 0 && pc == 1) ? 0 : 1;
+                            const float m = fmaxf(fmaxf(sv[0][0][r0e][c0e], sv[0][1][r0e][c1e]), fmaxf(sv[1][0][r1e][c0e], sv[1][1][r1e][c1e]));
+                            const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(fmaf(m, sc_s[j], sh_s[j]), 0.f)));
+                            if (j & 1) out[er * 2 + ec][j >> 1] |= bits << 16;
+                            else out[er * 2 + ec][j >> 1] = bits;
+                        }
                 }
-            // A cell on an even pooled row can only be the FIRST pooled row of a patch (u = 0) or an interior one, a cell on an odd
-            // row only the LAST (u = 2p-1) or interior; columns likewise: 2 x 2 of the 9 variants exist per phase, the others are
-            // never read (conv_pool4_kernel's class table) and are neither computed nor stored.
+                uint4* o = reinterpret_cast<uint4*>(B1) + (((int64_t)(pr * 2 + pc) * 4 + ch) * R1 + Il) * C1 + J;
 #pragma unroll
-            for (int er = 0; er < 2; ++er)
+                for (int er = 0; er < 2; ++er)
 #pragma unroll
-                for (int ec = 0; ec < 2; ++ec) {
-                    // er = 0: this cell's edge row variant (first if pr == 0, last if pr == 1); er = 1: interior.  The upper conv row
-                    // is masked for "first", the lower one for "last".
-                    const int r0e = (er == 0 && pr == 0) ? 0 : 1, r1e = (er == 0 && pr == 1) ? 0 : 1;
-                    const int c0e = (ec == 0 && pc == 0) ? 0 : 1, c1e = (ec == 0 && pc == 1) ? 0 : 1;
-                    const float m = fmaxf(fmaxf(r0e ? (c0e ? sv[0][0][1][1] : sv[0][0][1][0]) : (c0e ? sv[0][0][0][1] : sv[0][0][0][0]),
-                                                r0e ? (c1e ? sv[0][1][1][1] : sv[0][1][1][0]) : (c1e ? sv[0][1][0][1] : sv[0][1][0][0])),
-                                          fmaxf(r1e ? (c0e ? sv[1][0][1][1] : sv[1][0][1][0]) : (c0e ? sv[1][0][0][1] : sv[1][0][0][0]),
-                                                r1e ? (c1e ? sv[1][1][1][1] : sv[1][1][1][0]) : (c1e ? sv[1][1][0][1] : sv[1][1][0][0])));
-                    // BN after the max: the weights carry sign(scale), sc_s holds |scale| (max commutes with a non-negative scale)
-                    const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(fmaf(m, sc_s[j], sh_s[j]), 0.f)));
-                    if (j & 1) out[er * 2 + ec][j >> 1] |= bits << 16;
-                    else out[er * 2 + ec][j >> 1] = bits;
-                }
-        }
-        uint4* o = reinterpret_cast<uint4*>(B1) + (((int64_t)(pr * 2 + pc) * 4 + ch) * R1 + (Ul >> 1)) * C1 + (PY >> 1);
-#pragma unroll
-        for (int er = 0; er < 2; ++er)
-#pragma unroll
-            for (int ec = 0; ec < 2; ++ec) {
-                const int v = (er ? 1 : (pr ? 2 : 0)) * 3 + (ec ? 1 : (pc ? 2 : 0));
-                o[(int64_t)v * 16 * plane] = make_uint4(out[er * 2 + ec][0], out[er * 2 + ec][1], out[er * 2 + ec][2], out[er * 2 + ec][3]);
+                    for (int ec = 0; ec < 2; ++ec) {
+                        const int v = (er ? 1 : (pr ? 2 : 0)) * 3 + (ec ? 1 : (pc ? 2 : 0));
+                        o[(int64_t)v * 16 * plane] = make_uint4(out[er * 2 + ec][0], out[er * 2 + ec][1], out[er * 2 + ec][2], out[er * 2 + ec][3]);
+                    }
             }
     }
 }
@@ -602,7 +601,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
     const int p = n->p, W = s->W;
     const int band = std::max(1, std::min(n->dense_band, row1 - row0));
     DMF_TRY(dense_prepare(n, W, band));
-    const int R1 = d->R1, C1 = d->C1, C2 = 2 * C1;
+    const int R1 = d->R1, C1 = d->C1;
     const bool tm = n->timing;
     int evi = 0;
     auto mark = [&]() { if (tm && evi < 12) cudaEventRecord(d->ev[evi++], st); };
@@ -621,8 +620,8 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
         mark();
         mark();          // (stage slot of the former separate pooling pass)
         // ---- PAN branch
-        pan_stem_map_kernel<<<dim3(grid_for((int64_t)2 * rows * C2, 256, 8), C_PAN1 / 8), 256, 0, st>>>(
-            n->use_mspan ? s->mspan : s->pan, s->H4p, s->W4p, s->pan_pitch, 2 * b0, 2 * rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
+        pan_stem_map_kernel<<<dim3(grid_for((int64_t)rows * C1, 256, 8), C_PAN1 / 8), 256, 0, st>>>(
+            n->use_mspan ? s->mspan : s->pan, s->H4p, s->W4p, s->pan_pitch, b0, rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
         DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2, 8>(d->mapB1, true, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, nb, W, p, R1, C1, st)));
