@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restri
 // weights carry sign(scale), sc_s holds |scale| (max commutes with a non-negative scale).
 // w: fp32 [32][1][3][3].  grid.y = channel chunk.  out: B1[9][phase 4][4][R1][C1][8], PHASE-SEPARATED: pooled cell (U, V) is stored at
 // (U >> 1, V >> 1) of phase plane (U & 1) * 2 + (V & 1).  i0 = first pixel row of the band, rows = pixel rows to produce.
-__global__ void __launch_bounds__(256) pan_stem_map_kernel(const float* __restrict__ pan, int H4p, int W4p, int pitch, int i0, int rows,
+__global__ void __launch_bounds__(256, 2) pan_stem_map_kernel(const float* __restrict__ pan, int H4p, int W4p, int pitch, int i0, int rows,
                                                            int R1, int C1, const float* __restrict__ w, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ B1) {
     __shared__ float w_s[8][9], sc_s[8], sh_s[8];
