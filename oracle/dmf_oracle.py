@@ -261,3 +261,33 @@ def synthetic_scene(H, W, n_classes, seed=0, label_seed=1, blocky=False):
     lrng = np.random.default_rng(label_seed)
     label = lrng.integers(0, n_classes + 1, (H, W), dtype=np.uint8)
     return ms, pan, label
+
+
+def synthetic_scene_structured(H, W, n_classes, seed=0, label_seed=1, cell=20):
+    """A scene whose labels DEPEND on the rasters, so that a classifier can have Kappa > 0 on it (the uniform-noise scene
+    above cannot: its labels are independent of the image).  A coarse grid of `cell` x `cell` regions carries a class each;
+    every class has a 4-band spectral signature and a PAN texture (oriented stripes of class-specific period and amplitude
+    on top of the band mean); sensor noise on both rasters.  uint16 in [0, 2047] like the 11-bit sensors.  label = class + 1,
+    with ~15 % of the pixels unlabelled (0) in 8 x 8 blocks.  Returns (ms [H,W,4], pan [4H,4W], label [H,W])."""
+    rng = np.random.default_rng(seed)
+    gh, gw = H // cell + 2, W // cell + 2
+    grid = rng.integers(0, n_classes, (gh, gw))
+    oy, ox = int(rng.integers(0, cell)), int(rng.integers(0, cell))
+    cmap = np.kron(grid, np.ones((cell, cell), dtype=np.int64))[oy:oy + H, ox:ox + W]
+    sig = rng.uniform(350.0, 1650.0, (n_classes, 4))
+    period = rng.integers(3, 9, n_classes).astype(np.float64)
+    amp = rng.uniform(40.0, 220.0, n_classes)
+    angle = rng.uniform(0.0, np.pi, n_classes)
+    ms = sig[cmap] + rng.normal(0.0, 45.0, (H, W, 4))
+    c4 = np.repeat(np.repeat(cmap, 4, axis=0), 4, axis=1)
+    rr, cc = np.meshgrid(np.arange(4 * H, dtype=np.float32), np.arange(4 * W, dtype=np.float32), indexing='ij')
+    phase = (rr * np.cos(angle)[c4].astype(np.float32) + cc * np.sin(angle)[c4].astype(np.float32)) / period[c4].astype(np.float32)
+    pan = sig.mean(1)[c4] + amp[c4] * np.sin(2.0 * np.pi * phase) + rng.normal(0.0, 60.0, (4 * H, 4 * W)).astype(np.float32)
+    ms = np.clip(np.rint(ms), 0, 2047).astype(np.uint16)
+    pan = np.clip(np.rint(pan), 0, 2047).astype(np.uint16)
+    lrng = np.random.default_rng(label_seed)
+    holes = np.kron(lrng.random((H // 8 + 1, W // 8 + 1)) < 0.15, np.ones((8, 8), dtype=bool))[:H, :W]
+    label = (cmap + 1).astype(np.uint8)
+    label[holes] = 0
+    return ms, pan, label
+

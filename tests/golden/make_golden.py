@@ -198,11 +198,82 @@ def golden_solver_c1():
     np.savez_compressed(os.path.join(HERE, 'solver_c1.npz'), **out)
 
 
+def golden_solver_c1_fitted():
+    """The C1 whole-scene path once more, on a network whose predictions VARY: the structured synthetic scene (labels depend
+    on the rasters) and the fitted net of oracle/fitted_net.py (seed-3407 convolutions, calibrated BatchNorm, fitted head),
+    again through the reference's own BaseSolver / DataLoader / dataset_dual objects and the clean confusion loop
+    (train/test.py:58-60).  The default-initialised net of golden_solver_c1 predicts a single class everywhere."""
+    import tempfile
+    from oracle import fitted_net
+    H = W = 128
+    p, ncls = 16, 7
+    ms, pan, label = orc.synthetic_scene_structured(H, W, ncls, seed=0, label_seed=1)
+    tmp = tempfile.mkdtemp() + '/'
+    np.save(tmp + 'label.npy', label)
+    cfg = small_cfg(H, W, p, ncls, city='c1')
+    cfg.update({'task': 'classification', 'time': 1, 'index': 0, 'epoch': 1, 'device': 'cpu', 'gpu_mode': False,
+                'data_new': 0, 'data_address': tmp, 'use_h5': False, 'nohup': 0, 'model_name': 'gmfnet',
+                'batchsize': 256, 'test_batchsize': 300, 'color_batchsize': 300, 'train_rate': 0.02,
+                'verify_rate': 0.02, 'Categories_Number': ncls + 1,
+                'schedule': {'loss': 'Criterion', 'optimizer': 'ADAM', 'if_scheduler': 0, 'scheduler': 'ExponentialLR',
+                             'activate': 'Relu', 'lr': 1e-3, 'base_lr': 5e-4},
+                'train': {'index': 0, 'pretrained': 0, 'save_best': True}, 'test': {'index': 1, 'save_matrix': 1},
+                'color': {'index': 1, 'supervised': 1, 'unsupervised': 1}})
+    rbs.read_tif = lambda c, mode: ms if mode == 'ms' else pan
+
+    class FittedNet(gmfnet_ref.Net):
+        def __init__(self, args):
+            super().__init__(args)
+            self.load_state_dict(fitted_net.fitted_state('c1'))
+
+    mod = types.ModuleType('model.gmfnet')
+    mod.Net = FittedNet
+    sys.modules['model'] = types.ModuleType('model')
+    sys.modules['model.gmfnet'] = mod
+    torch.manual_seed(3407)
+    s = quiet(rms.Solver, cfg)
+    quiet(s.dataloader)
+    quiet(s.init_model)
+    net = s.model.eval()
+    C = ncls + 1
+    M = np.zeros([C, C])
+    M_test = np.zeros([C, C])
+    label_map = np.zeros([H, W])
+    logits_all = np.zeros((H * W, C), dtype=np.float32)
+    with torch.no_grad():
+        for loader in (s.color_loader1, s.color_loader2):
+            for d1, d2, tgt, x, y in loader:
+                o = net(d1, d2)
+                pred = o.data.max(1, keepdim=True)[1]
+                for i in range(len(tgt)):
+                    M[int(pred[i].item())][int(tgt[i].item())] += 1
+                    label_map[int(x[i])][int(y[i])] = int(pred[i])
+                logits_all[(x * W + y).numpy()] = o.numpy()
+        # Solver.test()'s loop over the WHOLE test loader (train/test.py:58-60 semantics, no first-batch break)
+        for d1, d2, tgt, x, y in s.test_loader:
+            pred = net(d1, d2).data.max(1, keepdim=True)[1]
+            for i in range(len(tgt)):
+                M_test[int(pred[i].item())][int(tgt[i].item())] += 1
+    aa, oa, k, _ = quiet(rk.aa_oa, M)
+    aat, oat, kt, _ = quiet(rk.aa_oa, M_test)
+    srt = np.sort(logits_all, axis=1)
+    out = {'M': M, 'label_map': label_map.astype(np.uint8), 'aa_oa_k': np.array([aa, oa, k]),
+           'M_test': M_test, 'test_aa_oa_k': np.array([aat, oat, kt]),
+           'test_idx': np.asarray([s.test_loader.dataset.dataset.indices[i] for i in s.test_loader.dataset.indices]),
+           'logits': logits_all.astype(np.float16),      # coarse copy of all 16 384 rows, for the tolerance check only
+           'logits_first512': logits_all[:512], 'margin_top2': (srt[:, -1] - srt[:, -2]).astype(np.float32),
+           'logits_checksum': np.float64(logits_all.astype(np.float64).sum())}
+    print('c1 fitted: predicted classes %d, OA %.4f AA %.4f Kappa %.4f; min top-2 margin %.3g' %
+          (len(np.unique(label_map)), oa, aa, k, out['margin_top2'].min()))
+    np.savez_compressed(os.path.join(HERE, 'solver_c1_fitted.npz'), **out)
+
+
 if __name__ == '__main__':
     golden_prep()
     golden_ihs()
     golden_metrics()
     golden_solver_c1()
+    golden_solver_c1_fitted()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))
