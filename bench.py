@@ -3,14 +3,18 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3]
 
-One "step" = one whole-scene classification pass (every pixel: co-registered MS/PAN window ->
-GMFNet -> argmax -> confusion matrix + label map) over the synthetic scene of the workload:
-  N = 1 : C2  Xi'an-scale   MS 4x1000x1000 / PAN 4000x4000, 12 classes (+background = 13)
-  N > 1 : C3  Hohhot-scale  MS 4x2001x2101 / PAN 8004x8404, 11 classes, row-band sharded,
-          one int64 C*C all-reduce per step (strong scaling: the scene is fixed).
-`value` is timed with CUDA events with the scene resident in HBM; `e2e` goes through the public API
-from pinned HOST rasters (H2D + normalise/pad + inference + D2H of label map and matrix + OA/AA/Kappa).
-`--impl reference` times the reference's CPU path (oracle/ref_pipeline.py port) on the host cores.
+One "step" = one whole-scene classification pass (every pixel: co-registered MS/PAN window -> GMFNet -> argmax -> confusion
+matrix + label map) over the synthetic scene of the workload.  The SAME workload at every N, so the 1/2/4/8 numbers are one
+strong-scaling curve:
+  C3  Hohhot-scale  MS 4x2001x2101 / PAN 8004x8404, 11 classes (+background = 12): the configuration BASELINE.json quotes the
+      scaling metric on; at N > 1 row-band sharded with one int64 C*C all-reduce per step.  It fits one GPU.
+  C2  Xi'an-scale   MS 4x1000x1000 / PAN 4000x4000, 12 classes: `--workload c2`, and a `secondary` entry of the default N = 1 run.
+Scene = oracle.synthetic_scene_structured (labels depend on the rasters); network = the fitted GMFNet of oracle/fitted_net.py
+(seed-3407 convolutions, calibrated BatchNorm, fitted head), so predictions vary and OA / AA / Kappa are not degenerate.
+`value`: CUDA events around each step with the scene resident in HBM.  `e2e`: the public API (dmf.ScenePipeline) from pinned
+HOST rasters — H2D + range + normalise/pad + inference + all-reduce + D2H of label band and matrix + OA/AA/Kappa every step,
+software-pipelined (scene i+1 uploads while scene i is classified).  `--impl reference` times the reference's own CPU
+objects (oracle/_ref through oracle/ref_runner.py; the oracle port if that copy is absent) on all host cores.
 """
 import argparse
 import json
@@ -33,6 +37,16 @@ WORKLOADS = {
 }
 P = 16
 METRIC, UNIT = 'scene pixels classified/sec', 'px/s'
+
+
+def make_config(wl_key):
+    """The `config` object: identical in both arms (--impl b200 / reference) and at every N."""
+    wl = WORKLOADS[wl_key]
+    return {'workload': wl['name'], 'patch_size': P, 'classes_with_background': wl['classes'] + 1, 'pixels': wl['H'] * wl['W'],
+            'scene': 'structured synthetic rasters, uint16 11-bit, labels depend on the rasters (oracle.synthetic_scene_structured, seeds 0 / 1)',
+            'net': 'GMFNet, seed-3407 convolutions + calibrated BatchNorm + fitted head (oracle/fitted_net.py): predictions vary, Kappa > 0',
+            'sharding': 'row bands over the ranks, scene replicated per rank, one int64 CxC all-reduce per step',
+            'l2': 'explicit 256 MiB L2 flush between timed steps; the per-step intermediates (GBs) exceed L2 too'}
 
 
 def peaks():
@@ -82,33 +96,71 @@ class ClockSampler:
                 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
-def cpu_reference_run(wl, budget_s, steps=1, warmup=0):
-    """The reference's CPU path on the host cores; returns (px/s, cores, description, per-step ms)."""
+def workload_scene(wl_key):
     from oracle import dmf_oracle as orc
-    from oracle.ref_pipeline import RefPipeline
-    ms, pan, label = orc.synthetic_scene(wl['H'], wl['W'], wl['classes'], seed=0, label_seed=1)
-    pipe = RefPipeline(ms, pan, label, P, wl['classes'] + 1)
-    order = np.arange(wl['H'] * wl['W'])
-    per_step_px = 0
-    times = []
-    cursor = 0
+    wl = WORKLOADS[wl_key]
+    return orc.synthetic_scene_structured(wl['H'], wl['W'], wl['classes'], seed=0, label_seed=1)
+
+
+def cpu_reference_run(wl_key, budget_s, steps=1, warmup=0, scene=None):
+    """The reference's CPU path on ALL host cores; returns (px/s, cores, kind, description, per-step ms).
+    kind "reference": the reference's own Solver / DataLoader / dataset_dual / aa_oa objects (oracle/_ref, vendored by
+    __graft_entry__.build()); kind "port": oracle/ref_pipeline.py when that copy is absent."""
+    from oracle import fitted_net, ref_runner
+    wl = WORKLOADS[wl_key]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)                          # torchrun exports OMP_NUM_THREADS=1: undo it explicitly
+    ms, pan, label = scene if scene is not None else workload_scene(wl_key)
+    state = fitted_net.fitted_state(wl_key)
+
+    def factory(args):
+        net = fitted_net.base_net(wl_key)
+        net.load_state_dict(state)
+        return net
+
+    if ref_runner.available():
+        kind = 'reference'
+        run = ref_runner.RefRun(ms, pan, label, P, wl['classes'], factory)
+        classify = run.classify
+        prep_s = run.prep_s
+    else:
+        kind = 'port'
+        from oracle.ref_pipeline import RefPipeline
+        pipe = RefPipeline(ms, pan, label, P, wl['classes'] + 1, net=factory(None))
+        order, state_ = np.arange(wl['H'] * wl['W']), {'c': 0}
+
+        def classify(b):
+            M, lm, done, secs = pipe.classify(order[state_['c']:state_['c'] + 200000], batch_size=300, budget_s=b)
+            state_['c'] = (state_['c'] + done) % max(1, order.size - 200000)
+            return M, lm, done, secs
+        prep_s = pipe.prep_s
+    px, secs_total, M_total = 0, 0.0, None
     for s in range(warmup + steps):
-        idx = order[cursor:cursor + 200000]
-        _, _, done, secs = pipe.classify(idx, batch_size=300, budget_s=budget_s if s >= warmup else min(budget_s, 3.0))
-        cursor = (cursor + done) % (order.size - 200000 if order.size > 200000 else 1)
+        M, _, done, secs = classify(budget_s if s >= warmup else min(budget_s, 3.0))
         if s >= warmup:
-            per_step_px += done
-            times.append(secs)
-    total = float(sum(times))
-    desc = ('%d px (row-major prefix, DataLoader bs=300 num_workers=0, per-item __getitem__, fp32 Net on CPU, per-sample '
-            'confusion loop) in %.1f s; scene prep %.1f s not counted' % (per_step_px, total, pipe.prep_s))
-    return per_step_px / total, torch.get_num_threads(), desc, 1e3 * total / max(1, steps)
+            px += done
+            secs_total += secs
+            M_total = M if M_total is None else M_total + M
+    desc = ('%d px of the scene in %.1f s (%s: Solver.__init__ + dataloader(), DataLoader bs=300 num_workers=0 over '
+            'dataset_dual.__getitem__, fp32 Net on the CPU with %d torch threads, per-sample confusion + label-map loops); '
+            'scene prep (to_tensor, data_padding, split_data_old) %.1f s not counted'
+            % (px, secs_total, 'the reference\'s own objects from oracle/_ref' if kind == 'reference' else 'oracle port', torch.get_num_threads(), prep_s))
+    return px / secs_total, torch.get_num_threads(), kind, desc, 1e3 * secs_total / max(1, steps)
+
+
+def fitted_product_net(wl_key, dev, **b200):
+    from model.gmfnet import Net
+    from oracle import fitted_net
+    net = Net(dict(fitted_net.cfg_for(wl_key), b200=b200))
+    net.load_state_dict(fitted_net.fitted_state(wl_key))
+    return net.to(dev).eval()
 
 
 def train_step_metric(dev, world, batch=512, steps=30, warmup=5):
-    """BASELINE.json configs[3]: IHS-input training step, `batch` patches per GPU (data-parallel, weak scaling): K2 IHS
-    product -> K1 tri-gather from the resident scene -> native forward (train-mode BatchNorm) -> CrossEntropyLoss ->
-    native backward -> one flat-gradient all-reduce -> FusedAdam.  CUDA events, max over ranks."""
+    """BASELINE.json configs[3]: IHS-input training step, `batch` patches per GPU (data-parallel, weak scaling): the IHS product
+    computed on the device straight into the scene (dmf_scene_set_mspan_ihs) -> K1 tri-gather from the resident scene -> native
+    forward (train-mode BatchNorm) -> CrossEntropyLoss -> native backward -> one flat-gradient all-reduce -> FusedAdam.  CUDA events,
+    max over ranks."""
     import random
     import torch.distributed as dist
     import dmf
@@ -116,28 +168,35 @@ def train_step_metric(dev, world, batch=512, steps=30, warmup=5):
     from image_convert.IHS import draw_offsets
     from model.gmfnet import Net
     C, Hs, Ws = 12, 400, 400
-    ms, pan, label = orc.synthetic_scene(Hs, Ws, C - 1, seed=0, label_seed=1)
-    msn = (ms - ms.min()) / (ms.max() - ms.min())
-    pann = (pan - pan.min()) / (pan.max() - pan.min())
+    ms, pan, label = orc.synthetic_scene_structured(Hs, Ws, C - 1, seed=0, label_seed=1)
     random.seed(7)
     offs = draw_offsets(Hs, Ws, 4, 4)
-    mspan = dmf.ihs_tran(torch.from_numpy(msn).to(dev), torch.from_numpy(pann).to(dev), torch.from_numpy(offs).to(dev), device=dev)
     sc = dmf.Scene.from_raw(ms, pan, P, dev)
     sc.set_labels(label)
-    sc.set_mspan(np.pad(mspan.cpu().numpy(), ((0, 4 * P - 1), (0, 4 * P - 1)), mode='reflect'))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_d = torch.from_numpy(ms.view(np.int16)).to(dev)
+    pan_d = torch.from_numpy(pan.view(np.int16)).to(dev)
+    offs_d = torch.from_numpy(offs).to(dev)
+    sc.set_mspan_ihs(ms_d, pan_d, offs_d)
+    e0.record()
+    sc.set_mspan_ihs(ms_d, pan_d, offs_d)
+    e1.record()
+    torch.cuda.synchronize()
+    ihs_ms = e0.elapsed_time(e1)
     torch.manual_seed(0)
     net = Net({'Categories_Number': C, 'patch_size': P, 'schedule': {'activate': 'Relu'}, 'b200': {'max_train_batch': batch}}).to(dev).train()
     opt = dmf.FusedAdam(net.parameters(), lr=1e-3)
     labelled = torch.from_numpy(np.flatnonzero(label.reshape(-1) != 0)).to(dev)
     g = torch.Generator(device=dev).manual_seed(1 + (dist.get_rank() if world > 1 else 0))
     batches = [labelled[torch.randint(0, labelled.numel(), (batch,), device=dev, generator=g)] for _ in range(8)]
+    first = None
     for i in range(warmup):
-        net.train_step_scene(sc, batches[i % 8], opt, use_mspan=True)
+        loss = net.train_step_scene(sc, batches[i % 8], opt, use_mspan=True)
+        first = float(loss) if first is None else first
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     l0 = dmf.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         loss = net.train_step_scene(sc, batches[i % 8], opt, use_mspan=True)
@@ -150,7 +209,8 @@ def train_step_metric(dev, world, batch=512, steps=30, warmup=5):
     flops = 3 * net.native().flops_per_patch * batch * world
     return {'workload': 'C4 IHS-input training step, batch %d per GPU, p=16, 12 classes, data-parallel x%d' % (batch, world),
             'ms_per_step': ms_step, 'patches_per_s': batch * world / ms_step * 1e3, 'algorithmic_TFLOPs': flops / ms_step / 1e9,
-            'kernels_per_step': (dmf.launch_count() - l0) / steps, 'loss_after': float(loss), 'steps': steps,
+            'kernels_per_step': (dmf.launch_count() - l0) / steps, 'loss_first_step': first, 'loss_after': float(loss), 'steps': steps,
+            'ihs_product_on_device_ms': ihs_ms, 'ihs_scene': '%dx%d raw uint16 -> padded fp32 MSPAN in the scene, no host round trip' % (Hs, Ws),
             'collective': 'one NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step' % (net.trainer().flat_grad.numel() * 4 / 1e6) if world > 1 else None}
 
 
@@ -169,7 +229,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default=None, choices=list(WORKLOADS))
+    ap.add_argument('--workload', default='c3', choices=list(WORKLOADS))
     ap.add_argument('--max-batch', type=int, default=16384)
     ap.add_argument('--mode', default='dense', choices=['dense', 'patch'],
                     help='whole-scene algorithm: scene-dense maps (default) or the per-patch kernels')
@@ -177,30 +237,29 @@ def main():
     ap.add_argument('--cpu-budget-s', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the secondary C4 training-step measurement')
+    ap.add_argument('--no-secondary', action='store_true', help='skip every secondary measurement (C2, per-patch path, C5 sweep, C4 step)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    wl_key = args.workload or ('c2' if max(world, args.gpus) == 1 else 'c3')
+    wl_key = args.workload
     wl = WORKLOADS[wl_key]
-    config = {'workload': wl['name'], 'patch_size': P, 'sharding': 'row bands, scene replicated per rank',
-              'l2': 'explicit 256 MiB L2 flush between timed steps; the per-step intermediates (GBs) exceed L2 too'}
+    config = make_config(wl_key)
 
     if args.impl == 'reference':
         if rank != 0:
             return
         per_step = max(2.0, min(args.cpu_budget_s, 120.0 / max(1, args.steps + args.warmup)))
-        v, cores, desc, ms_step = cpu_reference_run(wl, per_step, steps=args.steps, warmup=min(args.warmup, 1))
+        v, cores, kind, desc, ms_step = cpu_reference_run(wl_key, per_step, steps=args.steps, warmup=min(args.warmup, 1))
         emit(({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-                          'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
-                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                          'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
-                          'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+               'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
+               'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+               'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': desc},
+               'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 
     import torch.distributed as dist
     import dmf
-    from oracle import dmf_oracle as orc          # synthetic scene generator + cpu_baseline only
     from model.gmfnet import Net
     from indicators.kappa import aa_oa
     from solver.mainsolver import row_band
@@ -213,14 +272,12 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device(dev))
     C = wl['classes'] + 1
     H, W = wl['H'], wl['W']
-    ms, pan, label = orc.synthetic_scene(H, W, wl['classes'], seed=0, label_seed=1)
-    torch.manual_seed(3407)
-    net = Net({'Categories_Number': C, 'patch_size': P, 'schedule': {'activate': 'Relu'}, 'b200': {'max_batch': args.max_batch}})
-    net = net.to(dev).eval()
+    ms, pan, label = workload_scene(wl_key)
+    net = fitted_product_net(wl_key, dev, max_batch=args.max_batch)
     handle = net.native()
     handle.set_dense(args.mode == 'dense', args.band)
-    config['algorithm'] = ('scene-dense: every layer evaluated once per scene position and border class (csrc/dense.cu), bands of %d rows' % args.band
-                           if args.mode == 'dense' else 'per-patch kernels, chunks of %d pixels' % args.max_batch)
+    details = {'algorithm': ('scene-dense: every layer evaluated once per scene position and border class (csrc/dense.cu), bands of %d rows' % args.band
+                             if args.mode == 'dense' else 'per-patch kernels, chunks of %d pixels' % args.max_batch)}
     r0, r1 = row_band(H, rank, world)
     npix_total = H * W
 
@@ -263,215 +320,280 @@ def main():
     cm_host = cm.cpu().numpy().astype(np.float64)
     assert cm_host.sum() == npix_total, 'confusion matrix does not cover the scene'
 
-    # ---- e2e: public API from pinned host rasters, copies inside the timed region.  Every rank uploads only the scene rows its
-    # band needs (band + p-1 halo rows); the normalisation range of the whole scene is a 4-value min/max all-reduce.
-    s0, s1 = dmf.band_slice(H, P, r0, r1)
+    # ---- e2e: the public API from pinned host rasters, every copy inside the timed region; 2-deep software pipeline
     ms_pin = torch.from_numpy(ms.view(np.int16)).pin_memory()
     pan_pin = torch.from_numpy(pan.view(np.int16)).pin_memory()
     lab_pin = torch.from_numpy(label).pin_memory()
-    Hb = s1 - s0
-    pm_host = torch.empty((r1 - r0, W), dtype=torch.uint8).pin_memory()
-    cm_pin = torch.empty((C, C), dtype=torch.int64).pin_memory()
-    ms_dev = torch.empty((Hb, W, 4), dtype=torch.int16, device=dev)
-    pan_dev = torch.empty((4 * Hb, 4 * W), dtype=torch.int16, device=dev)
-    lab_dev = torch.empty((Hb, W), dtype=torch.uint8, device=dev)
-    e2e_scene = dmf.Scene.from_raw(ms_dev, pan_dev, P, dev)         # buffers reused by every step (same-size scenes)
-    e2e_pm = torch.zeros((Hb, W), dtype=torch.uint8, device=dev)
-    e2e_cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+    pipe = dmf.ScenePipeline(handle, H, W, P, r0, r1)
 
-    def e2e_step():
-        """host rasters -> H2D (this rank's rows) -> scene-wide min/max -> normalise/pad -> fused inference -> D2H label band +
-        matrix -> OA/AA/Kappa"""
-        ms_dev.copy_(ms_pin[s0:s1], non_blocking=True)
-        pan_dev.copy_(pan_pin[4 * s0:4 * s1], non_blocking=True)
-        lab_dev.copy_(lab_pin[s0:s1], non_blocking=True)
-        if world > 1:
-            a = dmf.raster_minmax(ms_dev[r0 - s0:r1 - s0])
-            b = dmf.raster_minmax(pan_dev[4 * (r0 - s0):4 * (r1 - s0)])
-            rng = torch.stack([a[0], -a[1], b[0], -b[1]])
-            dist.all_reduce(rng, op=dist.ReduceOp.MIN)
-            e2e_scene.update_raw(ms_dev, pan_dev, torch.stack([rng[0], -rng[1]]), torch.stack([rng[2], -rng[3]]))
-        else:
-            e2e_scene.update_raw(ms_dev, pan_dev)
-        e2e_scene.set_labels(lab_dev)
-        e2e_cm.zero_()
-        handle.infer_scene(e2e_scene, r0 - s0, r1 - s0, pred_map=e2e_pm, cm=e2e_cm)
-        if world > 1:
-            dist.all_reduce(e2e_cm)
-        pm_host.copy_(e2e_pm[r0 - s0:r1 - s0], non_blocking=True)
-        cm_pin.copy_(e2e_cm, non_blocking=True)
-        torch.cuda.synchronize()
+    def metrics_of(ticket):
+        _, cm_h = pipe.result(ticket)
         with open(os.devnull, 'w') as null, _redirect(null):
-            return aa_oa(cm_pin.numpy().astype(np.float64))
+            return aa_oa(cm_h.numpy().astype(np.float64)), cm_h
 
-    e2e_step()
+    def e2e_run(n, pipelined):
+        prev, out = None, None
+        for _ in range(n):
+            t = pipe.submit(ms_pin, pan_pin, lab_pin)
+            if not pipelined:
+                out = metrics_of(t)
+            else:
+                if prev is not None:
+                    out = metrics_of(prev)
+                prev = t
+        if prev is not None:
+            out = metrics_of(prev)
+        return out
+
+    e2e_run(2, True)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        result = e2e_step()
+    result, cm_e2e = e2e_run(args.steps, True)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = npix_total * args.steps / float(e2e_s)
-    assert np.array_equal(cm_pin.numpy(), cm.cpu().numpy()), 'e2e arm (band upload) and resident-scene arm disagree'
-    h2d = (ms.nbytes + pan.nbytes + label.nbytes) // H * Hb
-    d2h = (r1 - r0) * W + C * C * 8
+    assert np.array_equal(cm_e2e.numpy(), cm.cpu().numpy()), 'e2e arm (band upload) and resident-scene arm disagree'
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(3, False)
+    barrier()
+    lat_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lat_s, op=dist.ReduceOp.MAX)
+    e2e_latency_ms = float(lat_s) / 3 * 1e3
+    io_bytes = torch.tensor([pipe.h2d_bytes, pipe.d2h_bytes], dtype=torch.int64, device=dev)      # summed over the ranks
+    if world > 1:
+        dist.all_reduce(io_bytes)
+    h2d_total, d2h_total = (int(v) for v in io_bytes.tolist())
 
     # ---- roofline of the dominant kernel: per-stage device events inside the library (one extra pass)
     pk, pk_src = peaks()
     n_local = (r1 - r0) * W
     conv = lambda cin, cout, k, h: 2 * cin * cout * k * k * h * h
 
-    def ncu_traffic(tag, key):
+    def ncu_traffic(tag, key, want_wl):
         try:
             prof = json.load(open(os.path.join(REPO, 'profiles', tag)))
-            if wl_key == prof.get('workload'):
+            if want_wl == prof.get('workload'):
                 return prof['kernels'].get(key, {}).get('dram_bytes_per_launch')
         except Exception:
             pass
         return None
 
-    def patch_roofline():
-        handle.set_timing(True)
-        handle.infer_scene(scene, r0, r1)
-        stage = handle.get_timing()
-        handle.set_timing(False)
-        n_chunks = -(-n_local // args.max_batch)
+    def fracs(achieved):
+        return {'frac': achieved / pk['bf16_tflops'], 'frac_of_burst': achieved / pk['bf16_tflops'],
+                'frac_of_sustained': achieved / pk['bf16_tflops_sustained'], 'peak': pk['bf16_tflops'],
+                'peak_sustained': pk['bf16_tflops_sustained'],
+                'peak_source': pk_src + ': burst cuBLAS bf16 figure (the kernel is timed in one isolated pass); the sustained figure beside it'}
+
+    def patch_roofline(h, sc, rows0, rows1, Wd):
+        h.set_timing(True)
+        h.infer_scene(sc, rows0, rows1)
+        stage = h.get_timing()
+        h.set_timing(False)
+        n_loc = (rows1 - rows0) * Wd
+        n_chunks = -(-n_loc // args.max_batch)
         kernels = {   # kernel instance -> (stage keys, algorithmic FLOPs per pixel, launches per chunk)
             'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': (['conv_ms2', 'conv_pan3'], 2 * conv(64, 128, 3, P), 2),
             'conv_rowpair_kernel<32,G=3> (pan2, 32->64)': (['conv_pan2'], conv(32, 64, 3, 2 * P), 1),
             'conv_tc_kernel<256,128,1,G=2,gap> (fuse + pooling)': (['conv_fuse'], conv(256, 128, 1, P // 2), 1),
         }
-        ncu_key = {'conv_tc_kernel<64,128,9,pool,G=3> (ms2 + pan3)': 'tc::conv_tc_kernel<64,128,9,1,3,1,0>',
-                   'conv_rowpair_kernel<32,G=3> (pan2, 32->64)': 'tc::conv_rowpair_kernel<32,3>',
-                   'conv_tc_kernel<256,128,1,G=2,gap> (fuse + pooling)': 'tc::conv_tc_kernel<256,128,1,0,2,1,1>'}
         name, (keys, fl_px, per_chunk) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
         k_ms = sum(stage[k] for k in keys)
-        achieved = fl_px * n_local / (k_ms / 1e3) / 1e12
+        achieved = fl_px * n_loc / (k_ms / 1e3) / 1e12
         conv_fl = 2 * conv(64, 128, 3, P) + conv(32, 64, 3, 2 * P) + conv(256, 128, 1, P // 2)
         conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
-        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['bf16_tflops_sustained'],
-                'traffic': ncu_traffic('r01_ncu_summary.json', ncu_key[name]) if args.max_batch == 16384 else None,
-                'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
+        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'unit': 'TFLOP/s', **fracs(achieved), 'traffic': None,
                 'avg_launch_ms': k_ms / (n_chunks * per_chunk), 'launches': n_chunks * per_chunk,
-                'flops_per_launch': fl_px * n_local / (n_chunks * per_chunk),
+                'flops_per_launch': fl_px * n_loc / (n_chunks * per_chunk),
                 'stage_ms': {k: round(v, 3) for k, v in stage.items()},
-                'whole_net_tflops': handle.flops_per_patch * n_local / (stage['total'] / 1e3) / 1e12}
-        util = {'achieved_TFLOPs': conv_fl * n_local / (conv_ms / 1e3) / 1e12,
-                'frac_of_sustained_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
-                'frac_of_burst_peak': conv_fl * n_local / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
-                'ncu_tensor_pipe_active_pct': 'profiles/r01_ncu_summary.json'}
+                'whole_net_tflops': h.flops_per_patch * n_loc / (stage['total'] / 1e3) / 1e12}
+        a = conv_fl * n_loc / (conv_ms / 1e3) / 1e12
+        util = {'achieved_TFLOPs': a, 'frac_of_sustained_peak': a / pk['bf16_tflops_sustained'], 'frac_of_burst_peak': a / pk['bf16_tflops']}
         return roof, util
 
-    def dense_roofline():
+    def dense_roofline(h, sc, rows0, rows1, Wd, tag_wl):
         """FLOPs the dense kernels execute.  A fused conv + pool layer evaluates, per map position and pooled border class
         (first / interior / last per axis), the 4 conv outputs of the pooling window with 2,3 / 3,3 / 3,2 live tap rows
         (columns): (5 + 6 + 5)^2 = 256 tap evaluations of 2*Cin*Cout FLOPs per position (no credit for tile padding, skipped
         taps or don't-care rows)."""
-        handle.set_timing(True)
-        handle.get_dense_timing(reset=True)
-        handle.infer_scene(scene, r0, r1)
-        stage = handle.get_dense_timing()
-        handle.set_timing(False)
-        band = max(1, min(args.band, r1 - r0))
-        bands = [min(band, r1 - b) for b in range(r0, r1, band)]
-        pos = sum((nb + P - 1) * (W + P - 1) for nb in bands)                 # MS-resolution map positions of the bands
+        h.set_timing(True)
+        h.get_dense_timing(reset=True)
+        h.infer_scene(sc, rows0, rows1)
+        stage = h.get_dense_timing()
+        h.set_timing(False)
+        band = max(1, min(args.band, rows1 - rows0))
+        bands = [min(band, rows1 - b) for b in range(rows0, rows1, band)]
+        pos = sum((nb + P - 1) * (Wd + P - 1) for nb in bands)                 # MS-resolution map positions of the bands
         tr = (5, 6, 5)                                                        # live tap rows (columns) of the 2 sub-positions per border class
 
-        def taps(nb, cells, step):
+        def taps(nb, cells, step_):
             """tap evaluations of one conv + pool layer over a band: per border class only the rows / columns some anchor uses"""
-            ext = (0, step * (cells - 3), 0)
-            return sum(t * (nb + e) for t, e in zip(tr, ext)) * sum(t * (W + e) for t, e in zip(tr, ext))
+            ext = (0, step_ * (cells - 3), 0)
+            return sum(t * (nb + e) for t, e in zip(tr, ext)) * sum(t * (Wd + e) for t, e in zip(tr, ext))
 
         fl_s1 = sum(taps(nb, P // 2, 2) for nb in bands) * 2 * 64 * 128       # ms2, pan3: p/2 pooled cells at x + 2k
         fl_al = sum(taps(nb, P, 1) for nb in bands) * 2 * 32 * 64             # pan2: p pooled cells at x + k
-        fl_fu = sum(3 * nb + P - 6 for nb in bands) * 3 * (W + P - 1) * 2 * 256 * 128
+        fl_fu = sum(3 * nb + P - 6 for nb in bands) * 3 * (Wd + P - 1) * 2 * 256 * 128
         kernels = {   # kernel -> (stage keys, FLOPs executed over all bands, launches per band)
-            'conv_pool4_kernel<64,128,KQ=2,3 stages> (ms2 + pan3: conv + stride-1 2x2 max, 9 pooled classes)': (['conv_ms2', 'conv_pan3'], 2 * fl_s1, 2),
-            'conv_pool4_kernel<32,64,KQ=4,2 stages> (pan2: conv + aligned 2x2 max)': (['conv_pan2'], fl_al, 1),
+            'conv_pool4_kernel<64,128> (ms2 + pan3: conv + stride-1 2x2 max, 9 pooled classes)': (['conv_ms2', 'conv_pan3'], 2 * fl_s1, 2),
+            'conv_pool4_kernel<32,64> (pan2: conv + aligned 2x2 max)': (['conv_pan2'], fl_al, 1),
             'fuse_rowsum_kernel (1x1 fusion conv on 9 planes + row sums of the average pool; no credit for the 128/114 tile overlap)':
                 (['conv_fuse'], fl_fu, 1),
         }
-        ncu_key = {k: v for k, v in zip(kernels, ('tc::conv_pool4_kernel<64,128,2,3,19,11,1,8>', 'tc::conv_pool4_kernel<32,64,4,2,17,9,2,8>',
-                                                  'tc::fuse_rowsum_kernel<8>'))}
+        ncu_key = {k: v for k, v in zip(kernels, ('conv_pool4_64_128', 'conv_pool4_32_64', 'fuse_rowsum'))}
         name, (keys, fl_k, per_band) = max(kernels.items(), key=lambda kv: sum(stage[k] for k in kv[1][0]))
         k_ms = sum(stage[k] for k in keys)
         achieved = fl_k / (k_ms / 1e3) / 1e12
         conv_fl = sum(v[1] for v in kernels.values())
         conv_ms = sum(stage[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
-        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['bf16_tflops_sustained'],
-                'traffic': ncu_traffic('r01_dense_ncu_summary.json', ncu_key[name]) if args.band == 512 else None,
-                'peak_source': pk_src + ', sustained figure (kernel timed inside a long step)',
+        n_loc = (rows1 - rows0) * Wd
+        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'unit': 'TFLOP/s', **fracs(achieved),
+                'traffic': ncu_traffic('r02_dense_ncu_summary.json', ncu_key[name], tag_wl) if args.band == 512 else None,
                 'avg_launch_ms': k_ms / (len(bands) * per_band), 'launches': len(bands) * per_band,
                 'flops_per_launch': fl_k / (len(bands) * per_band),
                 'stage_ms': {k: round(v, 3) for k, v in stage.items()},
-                'map_positions': pos, 'flops_executed_per_pixel': conv_fl / n_local,
-                'per_patch_equivalent_tflops': handle.flops_per_patch * n_local / (stage['total'] / 1e3) / 1e12,
-                'note': 'achieved = tensor-core FLOPs this kernel executes / its time; per_patch_equivalent_tflops = the per-patch '
-                        'network FLOPs (flops_per_pixel) the same result would cost / whole-step time: it exceeds the peak because '
-                        'the dense algorithm shares work between overlapping patches'}
-        util = {'achieved_TFLOPs': conv_fl / (conv_ms / 1e3) / 1e12,
-                'frac_of_sustained_peak': conv_fl / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops_sustained'],
-                'frac_of_burst_peak': conv_fl / (conv_ms / 1e3) / 1e12 / pk['bf16_tflops'],
-                'ncu_tensor_pipe_active_pct': 'profiles/r01_dense_ncu_summary.json'}
+                'map_positions': pos, 'flops_executed_per_pixel': conv_fl / n_loc,
+                'whole_step_executed_TFLOPs': conv_fl / (stage['total'] / 1e3) / 1e12,
+                'per_patch_equivalent_tflops': h.flops_per_patch * n_loc / (stage['total'] / 1e3) / 1e12,
+                'note': 'achieved = tensor-core FLOPs this kernel executes / its time (one isolated pass with per-stage events); '
+                        'per_patch_equivalent_tflops = the per-patch network FLOPs the same result would cost / whole-step time: it '
+                        'exceeds the peak because the dense algorithm shares work between overlapping patches'}
+        a = conv_fl / (conv_ms / 1e3) / 1e12
+        util = {'achieved_TFLOPs': a, 'frac_of_sustained_peak': a / pk['bf16_tflops_sustained'], 'frac_of_burst_peak': a / pk['bf16_tflops'],
+                'ncu_tensor_pipe_active_pct': 'profiles/r02_dense_ncu_summary.json'}
         return roof, util
 
-    roofline, conv_util = dense_roofline() if args.mode == 'dense' else patch_roofline()
+    roofline, conv_util = (dense_roofline(handle, scene, r0, r1, W, wl_key) if args.mode == 'dense'
+                           else patch_roofline(handle, scene, r0, r1, W))
 
-    # ---- secondary metrics named by BASELINE.json: K1 patch-gather GB/s and conv tensor-pipe utilisation
-    gidx = torch.randint(0, H * W, (8192,), device=dev)
-    for _ in range(3):
-        scene.gather(gidx, want_target=False)
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g_ms = 1e9
-    for _ in range(5):
-        flush.fill_(1)
-        g0.record()
-        scene.gather(gidx, want_target=False)
-        g1.record()
-        torch.cuda.synchronize()
-        g_ms = min(g_ms, g0.elapsed_time(g1))
-    gather_gbs = 8192 * (4 * P * P + 16 * P * P) * 4 / g_ms / 1e6
-    secondary = {'patch_gather': {'GBs_written': gather_gbs, 'frac_of_hbm_copy_peak': gather_gbs / pk['hbm_gbs'], 'batch': 8192,
-                                  'bytes_per_patch': (4 * P * P + 16 * P * P) * 4,
-                                  'note': 'write-only kernel; measured pure-write ceiling on this pool is 3934 GB/s (memset), copy peak counts read+write'},
-                 'conv_tensor_util': conv_util}
-    if args.mode == 'dense':
-        # the per-patch kernels on the same band, for comparison (one warm-up pass + one timed pass)
-        handle.set_dense(False)
-        handle.infer_scene(scene, r0, r1, pred_map=pred_map)
-        pp0, pp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.fill_(1)
-        pp0.record()
-        handle.infer_scene(scene, r0, r1, pred_map=pred_map)
-        pp1.record()
-        torch.cuda.synchronize()
-        pp_roof, pp_util = patch_roofline()
-        secondary['per_patch_path'] = {'px_per_s_this_rank': n_local / pp0.elapsed_time(pp1) * 1e3, 'chunk_pixels': args.max_batch,
-                                       'dominant_kernel': pp_roof['kernel'], 'achieved_TFLOPs': pp_roof['achieved'], 'frac': pp_roof['frac'],
-                                       'whole_net_tflops': pp_roof['whole_net_tflops'], 'conv_tensor_util': pp_util,
-                                       'stage_ms': pp_roof['stage_ms']}
-        handle.set_dense(True, args.band)
+    secondary = {'conv_tensor_util': conv_util, 'e2e_single_scene_latency_ms': e2e_latency_ms}
+    if not args.no_secondary:
+        # ---- K1 patch gather GB/s (BASELINE.json metric, second item) at the C5 sizes: p = 8 / 16 / 32, batch 8192
+        wt = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    if not args.no_train:
-        secondary['train_step'] = train_step_metric(dev, world)
+        def best_ms(fn, reps=5):
+            for _ in range(3):
+                fn()
+            best = 1e9
+            for _ in range(reps):
+                flush.fill_(1)
+                g0.record()
+                fn()
+                g1.record()
+                torch.cuda.synchronize()
+                best = min(best, g0.elapsed_time(g1))
+            return best
+        write_ceiling = (1 << 30) / best_ms(lambda: wt.zero_()) / 1e6
+        del wt
+        sweep = []
+        for p_ in (8, 16, 32):
+            sc_p = scene if p_ == P else dmf.Scene.from_raw(ms[:1000, :1000], pan[:4000, :4000], p_, dev)
+            gidx = torch.randint(0, sc_p.H * sc_p.W, (8192,), device=dev)
+            o_ms = torch.empty((8192, 4, p_, p_), device=dev)
+            o_pan = torch.empty((8192, 1, 4 * p_, 4 * p_), device=dev)
+            import ctypes as Cc
+            call = lambda: dmf.check(dmf.lib.dmf_gather(sc_p._h, Cc.c_void_p(gidx.data_ptr()), 8192, Cc.c_void_p(o_ms.data_ptr()),
+                                                        Cc.c_void_p(o_pan.data_ptr()), None, None,
+                                                        Cc.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            g_ms = best_ms(call)
+            gbs = 8192 * 20 * p_ * p_ * 4 / g_ms / 1e6
+            entry = {'patch_size': p_, 'batch': 8192, 'bytes_per_patch': 20 * p_ * p_ * 4, 'gather_GBs_written': gbs,
+                     'frac_of_write_ceiling': gbs / write_ceiling, 'frac_of_hbm_copy_peak': gbs / pk['hbm_gbs']}
+            # conv tensor-pipe utilisation of the per-patch kernels at this patch size, batch 8192 (default-initialised weights)
+            torch.manual_seed(0)
+            net_p = Net({'Categories_Number': C, 'patch_size': p_, 'schedule': {'activate': 'Relu'}, 'b200': {'max_batch': 8192}}).to(dev).eval()
+            hp = net_p.native()
+            hp.set_dense(False)
+            hp.forward_scene(sc_p, flat_idx=gidx, want_logits=False, want_pred=True)
+            hp.set_timing(True)
+            hp.forward_scene(sc_p, flat_idx=gidx, want_logits=False, want_pred=True)
+            stp = hp.get_timing()
+            hp.set_timing(False)
+            cfl = 2 * conv(64, 128, 3, p_) + conv(32, 64, 3, 2 * p_) + conv(256, 128, 1, p_ // 2)
+            cms = sum(stp[k] for k in ('conv_ms2', 'conv_pan2', 'conv_pan3', 'conv_fuse'))
+            entry.update({'conv_TFLOPs': cfl * 8192 / (cms / 1e3) / 1e12, 'conv_frac_of_burst': cfl * 8192 / (cms / 1e3) / 1e12 / pk['bf16_tflops'],
+                          'whole_net_TFLOPs': hp.flops_per_patch * 8192 / (stp['total'] / 1e3) / 1e12,
+                          'patches_per_s': 8192 / (stp['total'] / 1e3), 'stage_ms': {k: round(v, 4) for k, v in stp.items()}})
+            sweep.append(entry)
+            hp.close()
+            del net_p, o_ms, o_pan
+            if sc_p is not scene:
+                sc_p.close()
+        p16 = sweep[1]
+        secondary['patch_gather'] = {'GBs_written': p16['gather_GBs_written'], 'frac_of_write_ceiling': p16['frac_of_write_ceiling'],
+                                     'frac_of_hbm_copy_peak': p16['frac_of_hbm_copy_peak'], 'batch': 8192, 'bytes_per_patch': p16['bytes_per_patch'],
+                                     'write_ceiling_GBs': write_ceiling,
+                                     'note': 'write-only kernel (TMA load -> bulk store): ceiling = a 1 GiB memset measured in this run; the copy peak counts read + write'}
+        secondary['c5_patch_size_sweep'] = {'workload': 'BASELINE.json configs[4]: p = 8 / 16 / 32 at batch 8192: K1 gather GB/s and conv tensor throughput of the per-patch kernels',
+                                            'entries': sweep}
+        if args.mode == 'dense':
+            # the per-patch kernels on the same band, for comparison (one warm-up pass + one timed pass)
+            handle.set_dense(False)
+            handle.infer_scene(scene, r0, r1, pred_map=pred_map)
+            pp0, pp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.fill_(1)
+            pp0.record()
+            handle.infer_scene(scene, r0, r1, pred_map=pred_map)
+            pp1.record()
+            torch.cuda.synchronize()
+            pp_roof, pp_util = patch_roofline(handle, scene, r0, r1, W)
+            secondary['per_patch_path'] = {'px_per_s_this_rank': n_local / pp0.elapsed_time(pp1) * 1e3, 'chunk_pixels': args.max_batch,
+                                           'dominant_kernel': pp_roof['kernel'], 'achieved_TFLOPs': pp_roof['achieved'], 'frac_of_burst': pp_roof['frac_of_burst'],
+                                           'frac_of_sustained': pp_roof['frac_of_sustained'], 'whole_net_tflops': pp_roof['whole_net_tflops'],
+                                           'conv_tensor_util': pp_util, 'stage_ms': pp_roof['stage_ms']}
+            handle.set_dense(True, args.band)
+        if wl_key == 'c3' and world == 1:
+            # BASELINE.json configs[1]: the C2 scene on one GPU
+            ms2, pan2, lab2 = workload_scene('c2')
+            net2 = fitted_product_net('c2', dev, max_batch=args.max_batch)
+            h2 = net2.native()
+            h2.set_dense(args.mode == 'dense', args.band)
+            sc2 = dmf.Scene.from_raw(ms2, pan2, P, dev)
+            sc2.set_labels(lab2)
+            cm2 = torch.zeros((13, 13), dtype=torch.int64, device=dev)
+            pm2 = torch.zeros((1000, 1000), dtype=torch.uint8, device=dev)
+            for _ in range(3):
+                h2.infer_scene(sc2, 0, 1000, pred_map=pm2, cm=cm2)
+            ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            for a, b in ev2:
+                flush.fill_(1)
+                cm2.zero_()
+                a.record()
+                h2.infer_scene(sc2, 0, 1000, pred_map=pm2, cm=cm2)
+                b.record()
+            torch.cuda.synchronize()
+            ms2_step = sum(a.elapsed_time(b) for a, b in ev2) / len(ev2)
+            with open(os.devnull, 'w') as null, _redirect(null):
+                r2 = aa_oa(cm2.cpu().numpy().astype(np.float64))
+            roof2, _ = dense_roofline(h2, sc2, 0, 1000, 1000, 'c2') if args.mode == 'dense' else patch_roofline(h2, sc2, 0, 1000, 1000)
+            secondary['c2_single_gpu'] = {'workload': WORKLOADS['c2']['name'], 'px_per_s': 1e6 / (ms2_step / 1e3), 'ms_per_step': ms2_step, 'steps': 10,
+                                          'OA_AA_Kappa': [float(r2[1]), float(r2[0]), float(r2[2])], 'stage_ms': roof2['stage_ms'],
+                                          'dominant_kernel_TFLOPs': roof2['achieved'], 'frac_of_burst': roof2['frac_of_burst']}
+            sc2.close()
+            del net2, ms2, pan2
+        if not args.no_train:
+            secondary['train_step'] = train_step_metric(dev, world)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, desc, _ = cpu_reference_run(wl, args.cpu_budget_s)
-        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc}
+        v, cores, kind, desc, _ = cpu_reference_run(wl_key, args.cpu_budget_s, scene=(ms, pan, label))
+        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': desc}
 
     if rank == 0:
-        config.update({'global_pixels': npix_total, 'row_band_rank0': [r0, r1],
-                       'flops_per_pixel': handle.flops_per_patch, 'OA_AA_Kappa': [float(result[1]), float(result[0]), float(result[2])]})
+        details.update({'global_pixels': npix_total, 'row_band_rank0': [r0, r1], 'flops_per_pixel': handle.flops_per_patch,
+                        'OA_AA_Kappa': [float(result[1]), float(result[0]), float(result[2])],
+                        'classes_predicted': int((cm_host.sum(axis=1) > 0).sum()),
+                        'e2e': 'dmf.ScenePipeline: 2-deep software pipeline over a stream of scenes (upload of scene i+1 on a copy stream while scene i is '
+                               'classified); secondary.e2e_single_scene_latency_ms is the un-pipelined submit -> result time'})
         emit(({'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-                          'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                          'dtype': 'bf16', 'data': 'synthetic', 'config': config, 'clocks': clk.summary(),
-                          'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
-                          'gpu_launches': int(launches), 'roofline': roofline, 'secondary': secondary, 'cpu_baseline': cpu_baseline}))
+               'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+               'dtype': 'bf16', 'data': 'synthetic', 'config': config, 'clocks': clk.summary(),
+               'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_total, 'd2h_bytes_per_step': d2h_total},
+               'gpu_launches': int(launches), 'roofline': roofline, 'secondary': secondary, 'cpu_baseline': cpu_baseline, 'details': details}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -65,6 +65,17 @@ __host__ __device__ __forceinline__ int reflect101(int i, int n) {
 
 int num_sms();
 
+#ifdef __CUDACC__
+__device__ __forceinline__ double run_mean4(double a0, double a1, double a2, double a3) {
+    // I = a0; I = (I*i + a_i) / (i+1) for i = 1..3   (image_convert/IHS.py:42-46, 49-53)
+    double I = a0;
+    I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 1.0), a1), 2.0);
+    I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 2.0), a2), 3.0);
+    I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 3.0), a3), 4.0);
+    return I;
+}
+#endif
+
 }  // namespace dmf
 
 // Device scene: normalised, reflect-padded fp32 rasters.
@@ -77,4 +88,5 @@ struct dmf_scene {
     float* pan = nullptr;      // [H4p][pan_pitch]
     float* mspan = nullptr;    // [H4p][pan_pitch] or null
     uint8_t* label = nullptr;  // [H][W] or null
+    struct dmf_scene_k1* k1 = nullptr;   // host-side extras of the K1 gather (planar MS copy + TMA tensor maps), scene.cu
 };

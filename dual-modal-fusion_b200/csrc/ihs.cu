@@ -11,15 +11,6 @@
 
 namespace dmf {
 
-__device__ __forceinline__ double run_mean4(double a0, double a1, double a2, double a3) {
-    // I = a0; I = (I*i + a_i) / (i+1) for i = 1..3   (image_convert/IHS.py:42-46, 49-53)
-    double I = a0;
-    I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 1.0), a1), 2.0);
-    I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 2.0), a2), 3.0);
-    I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 3.0), a3), 4.0);
-    return I;
-}
-
 __global__ void __launch_bounds__(256) ihs_tran_kernel(const double* __restrict__ ms, const double* __restrict__ pan,
                                                        const int8_t* __restrict__ offs, double* __restrict__ out,
                                                        int H, int W) {

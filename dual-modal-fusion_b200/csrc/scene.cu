@@ -10,6 +10,17 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "net_geom.cuh"
+
+// K1 extras of a scene: the MS raster once more in PLANAR layout [4][Hp][pitch] (a patch's CHW tensor is then one 3-D TMA box)
+// and the tensor maps of the three rasters.
+struct dmf_scene_k1 {
+    float* ms_pl = nullptr;
+    int pitch = 0;                                   // floats per planar MS row (multiple of 4)
+    alignas(64) CUtensorMap tm_ms, tm_pan, tm_mspan;
+    int p_maps = 0, rc = 0;                          // patch size / PAN rows per chunk the maps were encoded for (0 = none: p % 4 != 0)
+    bool has_mspan_map = false;
+};
 
 namespace dmf {
 
@@ -170,6 +181,58 @@ static int normalize_pad_any(const void* raw, int dt, int H, int W, int bands, i
     return DMF_ERR_ARG;
 }
 
+// ---------------------------------------------------------------- IHS product straight into the scene
+// dataset_tri's third raster (train/dataset.py:249-268) is the product of IHS_tran (image_convert/IHS.py:40-54) on the normalised
+// rasters, reflect-padded like PAN.  One pass: per padded output element, source element (r, c) = reflect-101 of the padded
+// coordinate; the four bands of MS pixel (r / 4, c / 4) and the PAN element are normalised in float64 (to_tensor,
+// function/function.py:120-124, numpy promotion rules via Norm<T>), the zero-stuffed bands `up` follow from the (m, n) offsets
+// (unpooling, :22-29), then I = running band mean, delta = PAN - I, result = up + delta, MSPAN = running band mean, all float64
+// in the reference's operation order, and the float32 cast of the dataset (train/dataset.py:265-268) on the way out.
+template <typename TM, typename TP>
+__global__ void __launch_bounds__(256) ihs_scene_kernel(const TM* __restrict__ ms, const TP* __restrict__ pan, const int8_t* __restrict__ offs,
+                                                        const double* __restrict__ ms_lohi, const double* __restrict__ pan_lohi, int H, int W,
+                                                        int H4p, int W4p, int pitch, float* __restrict__ out) {
+    const double mlo = ms_lohi[0], mhi = ms_lohi[1], plo = pan_lohi[0], phi = pan_lohi[1];
+    const int64_t HW = (int64_t)H * W;
+    for (int R = blockIdx.y; R < H4p; R += gridDim.y) {
+        const int r = reflect101(R, 4 * H), j = r >> 2, rr = r & 3;
+        for (int Cc = blockIdx.x * blockDim.x + threadIdx.x; Cc < W4p; Cc += gridDim.x * blockDim.x) {
+            const int c = reflect101(Cc, 4 * W), k = c >> 2, cc = c & 3;
+            const int64_t px = (int64_t)j * W + k;
+            double up[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const char2 o = __ldg(reinterpret_cast<const char2*>(offs) + i * HW + px);
+                up[i] = (o.x == rr && o.y == cc) ? Norm<TM>::q(ms[px * 4 + i], mlo, mhi) : 0.0;
+            }
+            const double pv = Norm<TP>::q(pan[(int64_t)r * (4 * W) + c], plo, phi);
+            const double I = run_mean4(up[0], up[1], up[2], up[3]);
+            const double delta = __dsub_rn(pv, I);
+            out[(int64_t)R * pitch + Cc] =
+                (float)run_mean4(__dadd_rn(up[0], delta), __dadd_rn(up[1], delta), __dadd_rn(up[2], delta), __dadd_rn(up[3], delta));
+        }
+    }
+}
+
+template <typename TM, typename TP>
+static void launch_ihs_scene(const void* ms, const void* pan, const int8_t* offs, const double* mlohi, const double* plohi, dmf_scene* s, cudaStream_t st) {
+    const dim3 grid((unsigned)std::min((s->W4p + 255) / 256, 64), (unsigned)std::min(s->H4p, 65535));
+    ihs_scene_kernel<TM, TP><<<grid, 256, 0, st>>>((const TM*)ms, (const TP*)pan, offs, mlohi, plohi, s->H, s->W, s->H4p, s->W4p, s->pan_pitch, s->mspan);
+}
+
+template <typename TM>
+static int ihs_scene_pan(const void* ms, const void* pan, int pan_dtype, const int8_t* offs, const double* mlohi, const double* plohi, dmf_scene* s,
+                         cudaStream_t st) {
+    switch (pan_dtype) {
+        case DMF_U8: launch_ihs_scene<TM, uint8_t>(ms, pan, offs, mlohi, plohi, s, st); return DMF_OK;
+        case DMF_U16: launch_ihs_scene<TM, uint16_t>(ms, pan, offs, mlohi, plohi, s, st); return DMF_OK;
+        case DMF_F32: launch_ihs_scene<TM, float>(ms, pan, offs, mlohi, plohi, s, st); return DMF_OK;
+        case DMF_F64: launch_ihs_scene<TM, double>(ms, pan, offs, mlohi, plohi, s, st); return DMF_OK;
+    }
+    set_error("scene_set_mspan_ihs: unknown PAN dtype %d", pan_dtype);
+    return DMF_ERR_ARG;
+}
+
 // padded f32/f64 [rows][cols*bands] -> f32 [rows][pitch]
 template <typename T>
 __global__ void repitch_cast_kernel(const T* __restrict__ in, int rows, int64_t row_elems, int64_t out_pitch,
@@ -216,74 +279,187 @@ static int scene_alloc(dmf_scene* s, int H, int W, int p) {
 }
 
 // ---------------------------------------------------------------- K1 gather
-// One CTA per patch.  PAN window: 4p rows of p float4.  MS window: p x p pixels, each a float4 of
-// 4 bands (HWC) that has to land in 4 CHW planes -> a thread takes 4 neighbouring pixels and
-// writes one float4 per plane.
-template <bool VEC>
-__global__ void __launch_bounds__(256) gather_kernel(dmf_scene s, const int64_t* __restrict__ idx, int64_t N,
-                                                     float* __restrict__ ms_out, float* __restrict__ pan_out,
-                                                     float* __restrict__ mspan_out, float* __restrict__ target_out) {
+// dataset_dual / dataset_tri + default_collate + .to(device) (train/dataset.py:168-185, 259-279; solver/mainsolver.py:50) is pure
+// data movement: per pixel a p x p x 4 MS window (HWC -> CHW) and one or two 4p x 4p windows of the PAN grid, 20 KB (28 KB tri) of
+// fp32 at p = 16, bounded by the HBM WRITE of the batch (the windows overlap and are served by L2).  No register ever touches
+// the data: a window is one TMA tensor load (cp.async.bulk.tensor: 2-D box of the pitched PAN / MSPAN raster, 3-D box
+// {p, p, 4 bands} of the planar MS copy) into shared memory, and because the box lands densely packed it IS the output tensor's
+// layout, so it leaves again as one bulk copy shared -> global (cp.async.bulk, L2 evict-first so that the batch does not push the
+// scene out of L2).  Unit of work = (patch, part): part 0 = the MS window, then the PAN window in chunks of <= 16 KB, then the
+// MSPAN chunks.  One warp = one shared-memory stage driven by its elected lane: wait until the stage's previous store has read
+// it, arm the mbarrier, load, wait, store.  CTAs are persistent (2 per SM, ~96 KB of stages each).
+constexpr int kK1StageMax = 16384;
+
+struct GatherParams {
+    const int64_t* idx;
+    int64_t N, HW;
+    int W, p, rc, n_chunks, upp;          // PAN rows per chunk, chunks per window, units per patch
+    uint32_t stage_bytes;
+    float *ms_out, *pan_out, *mspan_out, *target_out;
+    const uint8_t* label;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_evict_first(void* dst, uint32_t src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"((uint64_t)dst), "r"(src), "r"(bytes),
+                 "l"(policy)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(768) gather_tma_kernel(const __grid_constant__ CUtensorMap tm_ms, const __grid_constant__ CUtensorMap tm_pan,
+                                                         const __grid_constant__ CUtensorMap tm_mspan, const GatherParams P) {
+    extern __shared__ __align__(1024) uint8_t k1_smem[];
+    __shared__ uint64_t bars[32];
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (!tc::elect_one()) return;                                            // one driving lane per warp / stage
+    const uint32_t bar = tc::smem_u32(&bars[warp]);
+    const uint32_t stage = tc::smem_u32(k1_smem) + (uint32_t)warp * P.stage_bytes;
+    tc::mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (warp == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_ms) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_pan) : "memory");
+    }
+    const int64_t total = P.N * P.upp, stride = (int64_t)gridDim.x * nwarps;
+    const int p = P.p, P4 = 4 * p;
+    const uint32_t ms_bytes = 16u * p * p, chunk_bytes = (uint32_t)P.rc * P4 * 4u;
+    uint32_t phase = 0;
+    int64_t g = (int64_t)blockIdx.x * nwarps + warp;
+    int64_t k_next = g < total ? __ldg(P.idx + g / P.upp) : 0;
+    for (; g < total; g += stride) {
+        const int64_t n = g / P.upp;
+        const int u = (int)(g - n * P.upp);
+        int64_t k = k_next;
+        if (g + stride < total) k_next = __ldg(P.idx + (g + stride) / P.upp);      // in flight while this unit moves
+        k = k < 0 ? 0 : (k >= P.HW ? P.HW - 1 : k);                                // never address outside the scene
+        const int x = (int)((uint32_t)k / (uint32_t)P.W), y = (int)((uint32_t)k - (uint32_t)x * (uint32_t)P.W);
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");             // the stage's previous store has read it
+        void* dst;
+        uint32_t bytes;
+        if (u == 0) {
+            bytes = ms_bytes;
+            tc::mbar_expect_tx(bar, bytes);
+            tma_load_3d(stage, &tm_ms, bar, y, x, 0);
+            dst = P.ms_out + n * (int64_t)(4 * p * p);
+            if (P.target_out) P.target_out[n] = (float)__ldg(P.label + k);
+        } else {
+            const int c = u - 1;
+            const bool third = c >= P.n_chunks;
+            const int ck = third ? c - P.n_chunks : c;
+            bytes = chunk_bytes;
+            tc::mbar_expect_tx(bar, bytes);
+            tma_load_2d(stage, third ? &tm_mspan : &tm_pan, bar, 4 * y, 4 * x + ck * P.rc);
+            dst = (third ? P.mspan_out : P.pan_out) + n * (int64_t)(P4 * P4) + (int64_t)ck * P.rc * P4;
+        }
+        tc::mbar_wait(bar, phase);
+        phase ^= 1;
+        bulk_store_evict_first(dst, stage, bytes, policy);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// generic path for patch sizes that are not a multiple of 4 (TMA boxes need 16-byte rows): one CTA per patch, scalar copies
+__global__ void __launch_bounds__(256) gather_scalar_kernel(dmf_scene s, const int64_t* __restrict__ idx, int64_t N,
+                                                            float* __restrict__ ms_out, float* __restrict__ pan_out,
+                                                            float* __restrict__ mspan_out, float* __restrict__ target_out) {
     const int64_t n = blockIdx.x;
-    const int64_t k = idx[n];
+    const int64_t HW = (int64_t)s.H * s.W;
+    int64_t k = idx[n];
+    k = k < 0 ? 0 : (k >= HW ? HW - 1 : k);
     const int x = (int)(k / s.W), y = (int)(k % s.W);
     const int p = s.p, P = 4 * p;
-    if (VEC) {
-        const int nq = P * p;   // float4 per PAN window
-        const float* base = s.pan + (int64_t)(4 * x) * s.pan_pitch + 4 * y;
-        float4* dst = reinterpret_cast<float4*>(pan_out + n * (int64_t)P * P);
-        // 4 independent 16-byte loads in flight per thread before the first store (latency-bound otherwise)
-        for (int i0 = threadIdx.x; i0 < nq; i0 += 4 * blockDim.x) {
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * blockDim.x;
-                if (i < nq) {
-                    const int r = i / p, c4 = i - r * p;
-                    v[u] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * s.pan_pitch) + c4);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * blockDim.x;
-                if (i < nq) __stcs(dst + i, v[u]);
-            }
-        }
-        if (mspan_out) {
-            const float* b2 = s.mspan + (int64_t)(4 * x) * s.pan_pitch + 4 * y;
-            float4* d2 = reinterpret_cast<float4*>(mspan_out + n * (int64_t)P * P);
-            for (int i = threadIdx.x; i < nq; i += blockDim.x) {
-                int r = i / p, c4 = i - r * p;
-                float4 v = __ldg(reinterpret_cast<const float4*>(b2 + (int64_t)r * s.pan_pitch) + c4);
-                __stcs(d2 + i, v);
-            }
-        }
-        const int pq = p / 4;
-        const float4* ms4 = reinterpret_cast<const float4*>(s.ms);
-        float* mo = ms_out + n * (int64_t)4 * p * p;
-        for (int i = threadIdx.x; i < p * pq; i += blockDim.x) {
-            int r = i / pq, c = (i - r * pq) * 4;
-            const float4* src = ms4 + (int64_t)(x + r) * s.Wp + y + c;
-            float4 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2), a3 = __ldg(src + 3);
-            int o = r * p + c;
-            __stcs(reinterpret_cast<float4*>(mo + o), make_float4(a0.x, a1.x, a2.x, a3.x));
-            __stcs(reinterpret_cast<float4*>(mo + p * p + o), make_float4(a0.y, a1.y, a2.y, a3.y));
-            __stcs(reinterpret_cast<float4*>(mo + 2 * p * p + o), make_float4(a0.z, a1.z, a2.z, a3.z));
-            __stcs(reinterpret_cast<float4*>(mo + 3 * p * p + o), make_float4(a0.w, a1.w, a2.w, a3.w));
-        }
-    } else {
-        const float* base = s.pan + (int64_t)(4 * x) * s.pan_pitch + 4 * y;
-        for (int i = threadIdx.x; i < P * P; i += blockDim.x) {
-            int r = i / P, c = i - r * P;
-            pan_out[n * (int64_t)P * P + i] = base[(int64_t)r * s.pan_pitch + c];
-            if (mspan_out)
-                mspan_out[n * (int64_t)P * P + i] = s.mspan[(int64_t)(4 * x + r) * s.pan_pitch + 4 * y + c];
-        }
-        for (int i = threadIdx.x; i < 4 * p * p; i += blockDim.x) {
-            int b = i / (p * p), rem = i - b * p * p, r = rem / p, c = rem - r * p;
-            ms_out[n * (int64_t)4 * p * p + i] = s.ms[((int64_t)(x + r) * s.Wp + y + c) * 4 + b];
-        }
+    const float* base = s.pan + (int64_t)(4 * x) * s.pan_pitch + 4 * y;
+    for (int i = threadIdx.x; i < P * P; i += blockDim.x) {
+        int r = i / P, c = i - r * P;
+        pan_out[n * (int64_t)P * P + i] = base[(int64_t)r * s.pan_pitch + c];
+        if (mspan_out)
+            mspan_out[n * (int64_t)P * P + i] = s.mspan[(int64_t)(4 * x + r) * s.pan_pitch + 4 * y + c];
+    }
+    for (int i = threadIdx.x; i < 4 * p * p; i += blockDim.x) {
+        int b = i / (p * p), rem = i - b * p * p, r = rem / p, c = rem - r * p;
+        ms_out[n * (int64_t)4 * p * p + i] = s.ms[((int64_t)(x + r) * s.Wp + y + c) * 4 + b];
     }
     if (threadIdx.x == 0 && target_out) target_out[n] = (float)s.label[k];
+}
+
+// MS [Hp][Wp] float4 (HWC) -> planar [4][Hp][pitch]
+__global__ void __launch_bounds__(256) ms_planar_kernel(const float4* __restrict__ ms, int Hp, int Wp, int pitch, float* __restrict__ out) {
+    const int64_t total = (int64_t)Hp * Wp, plane = (int64_t)Hp * pitch;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / Wp, c = i - r * Wp;
+        const float4 v = __ldg(ms + i);
+        float* o = out + r * pitch + c;
+        o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
+    }
+}
+
+static int encode_f32_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DMF_ERR_CUDA; }
+    const cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (scene raster, rank %d) failed: CUresult %d", rank, (int)r); return DMF_ERR_CUDA; }
+    return DMF_OK;
+}
+
+// (re)build the planar MS copy and the tensor maps after the rasters changed
+static int scene_k1_refresh(dmf_scene* s, cudaStream_t st, bool ms_changed) {
+    if (!s->k1) s->k1 = new dmf_scene_k1();
+    dmf_scene_k1* k = s->k1;
+    const int p = s->p;
+    if (p % 4 != 0 || p > 64) { k->p_maps = 0; return DMF_OK; }   // TMA boxes need 16-byte rows of <= 256 elements: gather_scalar_kernel
+    if (!k->ms_pl) {
+        k->pitch = (s->Wp + 3) & ~3;
+        DMF_CUDA(cudaMalloc(&k->ms_pl, sizeof(float) * 4 * (size_t)s->Hp * k->pitch));
+        ms_changed = true;
+    }
+    if (ms_changed) {
+        const int64_t total = (int64_t)s->Hp * s->Wp;
+        ms_planar_kernel<<<(int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, k->pitch, k->ms_pl);
+        DMF_LAUNCHED();
+    }
+    if (k->p_maps != p) {
+        const int P4 = 4 * p;
+        k->rc = std::min(P4, kK1StageMax / (P4 * 4));
+        while (P4 % k->rc) --k->rc;                                  // chunks tile the window
+        {
+            const cuuint64_t dims[3] = {(cuuint64_t)s->Wp, (cuuint64_t)s->Hp, 4};
+            const cuuint64_t strides[2] = {(cuuint64_t)k->pitch * 4, (cuuint64_t)k->pitch * 4 * s->Hp};
+            const cuuint32_t box[3] = {(cuuint32_t)p, (cuuint32_t)p, 4};
+            DMF_TRY(encode_f32_map(&k->tm_ms, k->ms_pl, 3, dims, strides, box));
+        }
+        const cuuint64_t dims[2] = {(cuuint64_t)s->W4p, (cuuint64_t)s->H4p};
+        const cuuint64_t strides[1] = {(cuuint64_t)s->pan_pitch * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)P4, (cuuint32_t)k->rc};
+        DMF_TRY(encode_f32_map(&k->tm_pan, s->pan, 2, dims, strides, box));
+        k->tm_mspan = k->tm_pan;
+        k->has_mspan_map = false;
+        k->p_maps = p;
+    }
+    if (s->mspan && !k->has_mspan_map) {
+        const int P4 = 4 * p;
+        const cuuint64_t dims[2] = {(cuuint64_t)s->W4p, (cuuint64_t)s->H4p};
+        const cuuint64_t strides[1] = {(cuuint64_t)s->pan_pitch * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)P4, (cuuint32_t)k->rc};
+        DMF_TRY(encode_f32_map(&k->tm_mspan, s->mspan, 2, dims, strides, box));
+        k->has_mspan_map = true;
+    }
+    return DMF_OK;
 }
 
 __global__ void unpitch_kernel(const float* __restrict__ in, int rows, int cols, int pitch, float* __restrict__ out) {
@@ -319,6 +495,7 @@ static int scene_fill_raw(dmf_scene* s, const void* ms, int ms_dtype, const void
     if (rc == DMF_OK) rc = upload(pan, dtype_size(pan_dtype) * 16 * (size_t)H * W, on_device, st, &t2, &dpan);
     if (rc == DMF_OK) rc = normalize_pad_any(dms, ms_dtype, H, W, 4, p, s->ms, DMF_F32, (int64_t)s->Wp * 4, st, ms_lohi);
     if (rc == DMF_OK) rc = normalize_pad_any(dpan, pan_dtype, 4 * H, 4 * W, 1, 4 * p, s->pan, DMF_F32, s->pan_pitch, st, pan_lohi);
+    if (rc == DMF_OK) rc = scene_k1_refresh(s, st, true);
     if (t1) cudaFreeAsync(t1, st);
     if (t2) cudaFreeAsync(t2, st);
     return rc;
@@ -385,6 +562,7 @@ int dmf_scene_create_padded(dmf_scene** out, const void* ms_pad, const void* pan
     int rc = scene_alloc(s, H, W, p);
     if (rc == DMF_OK) rc = copy_padded(ms_pad, dtype, s->Hp, (int64_t)s->Wp * 4, (int64_t)s->Wp * 4, s->ms, on_device, st);
     if (rc == DMF_OK) rc = copy_padded(pan_pad, dtype, s->H4p, s->W4p, s->pan_pitch, s->pan, on_device, st);
+    if (rc == DMF_OK) rc = scene_k1_refresh(s, st, true);
     if (rc != DMF_OK) { dmf_scene_destroy(s); return rc; }
     *out = s;
     return DMF_OK;
@@ -393,7 +571,48 @@ int dmf_scene_create_padded(dmf_scene** out, const void* ms_pad, const void* pan
 int dmf_scene_set_mspan(dmf_scene* s, const void* mspan_pad, int dtype, int on_device, void* stream) {
     DMF_REQUIRE(s && mspan_pad, "scene_set_mspan: null");
     if (!s->mspan) DMF_CUDA(cudaMalloc(&s->mspan, sizeof(float) * (size_t)s->H4p * s->pan_pitch));
-    return copy_padded(mspan_pad, dtype, s->H4p, s->W4p, s->pan_pitch, s->mspan, on_device, (cudaStream_t)stream);
+    DMF_TRY(copy_padded(mspan_pad, dtype, s->H4p, s->W4p, s->pan_pitch, s->mspan, on_device, (cudaStream_t)stream));
+    return scene_k1_refresh(s, (cudaStream_t)stream, false);
+}
+
+int dmf_scene_set_mspan_ihs(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int on_device,
+                            const int8_t* offsets_dev, const double* ms_lohi_dev, const double* pan_lohi_dev, void* stream) {
+    DMF_REQUIRE(s && ms && pan && offsets_dev, "scene_set_mspan_ihs: null");
+    DMF_REQUIRE((ms_lohi_dev == nullptr) == (pan_lohi_dev == nullptr), "scene_set_mspan_ihs: give both ranges or neither");
+    DMF_REQUIRE(((uintptr_t)offsets_dev & 1) == 0, "scene_set_mspan_ihs: offsets must be 2-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int H = s->H, W = s->W;
+    if (!s->mspan) DMF_CUDA(cudaMalloc(&s->mspan, sizeof(float) * (size_t)s->H4p * s->pan_pitch));
+    void *t1 = nullptr, *t2 = nullptr;
+    double* lohi = nullptr;
+    const void *dms = nullptr, *dpan = nullptr;
+    int rc = upload(ms, dtype_size(ms_dtype) * 4 * (size_t)H * W, on_device, st, &t1, &dms);
+    if (rc == DMF_OK) rc = upload(pan, dtype_size(pan_dtype) * 16 * (size_t)H * W, on_device, st, &t2, &dpan);
+    if (rc == DMF_OK && !ms_lohi_dev) {
+        if (cudaMallocAsync(&lohi, sizeof(double) * 4, st) != cudaSuccess) { set_error("scene_set_mspan_ihs: out of memory"); rc = DMF_ERR_CUDA; }
+        if (rc == DMF_OK) rc = dmf_raster_minmax(dms, ms_dtype, (int64_t)H * W * 4, lohi, st);
+        if (rc == DMF_OK) rc = dmf_raster_minmax(dpan, pan_dtype, (int64_t)H * W * 16, lohi + 2, st);
+        ms_lohi_dev = lohi; pan_lohi_dev = lohi + 2;
+    }
+    if (rc == DMF_OK) {
+        switch (ms_dtype) {
+            case DMF_U8: rc = ihs_scene_pan<uint8_t>(dms, dpan, pan_dtype, offsets_dev, ms_lohi_dev, pan_lohi_dev, s, st); break;
+            case DMF_U16: rc = ihs_scene_pan<uint16_t>(dms, dpan, pan_dtype, offsets_dev, ms_lohi_dev, pan_lohi_dev, s, st); break;
+            case DMF_F32: rc = ihs_scene_pan<float>(dms, dpan, pan_dtype, offsets_dev, ms_lohi_dev, pan_lohi_dev, s, st); break;
+            case DMF_F64: rc = ihs_scene_pan<double>(dms, dpan, pan_dtype, offsets_dev, ms_lohi_dev, pan_lohi_dev, s, st); break;
+            default: set_error("scene_set_mspan_ihs: unknown MS dtype %d", ms_dtype); rc = DMF_ERR_ARG;
+        }
+        if (rc == DMF_OK) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { set_error("scene_set_mspan_ihs: kernel launch -> %s", cudaGetErrorString(e)); rc = DMF_ERR_CUDA; }
+        }
+    }
+    if (lohi) cudaFreeAsync(lohi, st);
+    if (t1) cudaFreeAsync(t1, st);
+    if (t2) cudaFreeAsync(t2, st);
+    if (rc == DMF_OK) rc = scene_k1_refresh(s, st, false);
+    return rc;
 }
 
 int dmf_scene_set_labels(dmf_scene* s, const uint8_t* label, int on_device, void* stream) {
@@ -410,6 +629,7 @@ int dmf_scene_destroy(dmf_scene* s) {
     cudaFree(s->pan);
     cudaFree(s->mspan);
     cudaFree(s->label);
+    if (s->k1) { cudaFree(s->k1->ms_pl); delete s->k1; }
     delete s;
     return DMF_OK;
 }
@@ -446,10 +666,30 @@ int dmf_gather(const dmf_scene* s, const int64_t* flat_idx_dev, int64_t N, float
     if (N == 0) return DMF_OK;
     DMF_REQUIRE(N < (int64_t)1 << 31, "gather: N too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
-    if (s->p % 4 == 0)
-        gather_kernel<true><<<(unsigned)N, 256, 0, st>>>(*s, flat_idx_dev, N, ms_out_dev, pan_out_dev, mspan_out_dev, target_out_dev);
-    else
-        gather_kernel<false><<<(unsigned)N, 256, 0, st>>>(*s, flat_idx_dev, N, ms_out_dev, pan_out_dev, mspan_out_dev, target_out_dev);
+    const dmf_scene_k1* k = s->k1;
+    if (k && k->p_maps == s->p) {
+        const int p = s->p, P4 = 4 * p;
+        DMF_REQUIRE((int64_t)s->H * s->W < ((int64_t)1 << 31), "gather: scene too large for 32-bit pixel indices");
+        DMF_REQUIRE(!mspan_out_dev || k->has_mspan_map, "gather: tri mode needs dmf_scene_set_mspan");
+        GatherParams P{};
+        P.idx = flat_idx_dev; P.N = N; P.HW = (int64_t)s->H * s->W; P.W = s->W; P.p = p; P.rc = k->rc; P.n_chunks = P4 / k->rc;
+        P.upp = 1 + P.n_chunks * (mspan_out_dev ? 2 : 1);
+        P.stage_bytes = (uint32_t)std::max(16 * p * p, k->rc * P4 * 4);
+        P.stage_bytes = (P.stage_bytes + 1023u) & ~1023u;
+        P.ms_out = ms_out_dev; P.pan_out = pan_out_dev; P.mspan_out = mspan_out_dev; P.target_out = target_out_dev; P.label = s->label;
+        const int warps = (int)std::max<uint32_t>(1, std::min<uint32_t>(24, (96u * 1024u) / P.stage_bytes));
+        const size_t smem = (size_t)warps * P.stage_bytes;
+        static bool attr_set = false;
+        if (!attr_set) {
+            DMF_CUDA(cudaFuncSetAttribute(gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_set = true;
+        }
+        const int64_t units = N * P.upp;
+        const int grid = (int)std::min<int64_t>((units + warps - 1) / warps, (int64_t)2 * num_sms());
+        gather_tma_kernel<<<grid, warps * 32, smem, st>>>(k->tm_ms, k->tm_pan, k->tm_mspan, P);
+    } else {
+        gather_scalar_kernel<<<(unsigned)N, 256, 0, st>>>(*s, flat_idx_dev, N, ms_out_dev, pan_out_dev, mspan_out_dev, target_out_dev);
+    }
     DMF_LAUNCHED();
     return DMF_OK;
 }

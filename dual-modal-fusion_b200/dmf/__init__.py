@@ -152,6 +152,31 @@ class Scene:
             torch.cuda.current_stream().synchronize()
         self.has_mspan = True
 
+    def set_mspan_ihs(self, ms, pan, offsets, ms_range=None, pan_range=None):
+        """The IHS product of the scene's own rasters, computed and reflect-padded on the device (no host round trip):
+        float32(IHS_tran(to_tensor(ms), to_tensor(pan))) of image_convert/IHS.py:40-54 as dataset_tri's third raster.
+        ms [H,W,4] / pan [4H,4W]: the RAW rasters (ndarrays, pinned CPU or CUDA tensors) the scene was built from; offsets: int8
+        [4,H,W,2] unpooling draws (image_convert.IHS.draw_offsets), ndarray or CUDA tensor; ms_range / pan_range as in update_raw."""
+        code = {torch.uint8: U8, torch.int16: U16, torch.uint16: U16, torch.float32: F32, torch.float64: F64}
+        assert (ms_range is None) == (pan_range is None), 'give both ranges or neither'
+        with torch.cuda.device(self.device):
+            off = _as_dev(np.asarray(offsets, dtype=np.int8) if isinstance(offsets, np.ndarray) else offsets, self.device)
+            assert off.dtype == torch.int8 and tuple(off.shape) == (4, self.H, self.W, 2), 'offsets must be int8 [4,H,W,2]'
+            if isinstance(ms, np.ndarray):
+                a, b = np.ascontiguousarray(ms), np.ascontiguousarray(pan)
+                assert a.shape == (self.H, self.W, 4) and b.shape == (4 * self.H, 4 * self.W)
+                check(lib.dmf_scene_set_mspan_ihs(self._h, a.ctypes.data_as(C.c_void_p), np_dtype_code(a), b.ctypes.data_as(C.c_void_p),
+                                                  np_dtype_code(b), 0, _ptr(off), _ptr(ms_range), _ptr(pan_range), _stream()))
+                torch.cuda.current_stream().synchronize()
+            else:
+                a, b = ms.contiguous(), pan.contiguous()
+                assert tuple(a.shape) == (self.H, self.W, 4) and tuple(b.shape) == (4 * self.H, 4 * self.W)
+                check(lib.dmf_scene_set_mspan_ihs(self._h, _ptr(a), code[a.dtype], _ptr(b), code[b.dtype], 1 if a.is_cuda else 0,
+                                                  _ptr(off), _ptr(ms_range), _ptr(pan_range), _stream()))
+                if not a.is_cuda:
+                    torch.cuda.current_stream().synchronize()
+        self.has_mspan = True
+
     def export(self, which):
         """0 -> MS [Hp,Wp,4], 1 -> PAN [H4p,W4p], 2 -> MSPAN; float32 CUDA tensors."""
         shape = (self.Hp, self.Wp, 4) if which == 0 else (self.H4p, self.W4p)
@@ -162,7 +187,12 @@ class Scene:
 
     def gather(self, flat_idx, tri=False, want_target=None):
         """K1: flat_idx int64 (tensor / ndarray / list) -> (ms [N,4,p,p], pan [N,1,4p,4p][, mspan], target [N])."""
-        idx = torch.as_tensor(flat_idx, dtype=torch.int64).to(self.device)
+        idx = torch.as_tensor(flat_idx, dtype=torch.int64)
+        if not idx.is_cuda and idx.numel():          # host index lists (the loaders') are range-checked; the kernels clamp
+            lo, hi = int(idx.min()), int(idx.max())
+            if lo < 0 or hi >= self.H * self.W:
+                raise IndexError('gather: flat pixel index %d outside the %d x %d scene' % (lo if lo < 0 else hi, self.H, self.W))
+        idx = idx.to(self.device)
         N, p = idx.numel(), self.p
         want_target = self.has_labels if want_target is None else want_target
         ms = torch.empty((N, 4, p, p), dtype=torch.float32, device=self.device)
@@ -452,7 +482,9 @@ class TrainHandle:
         total = sum(q.numel() for _, q in named)
         dev = named[0][1].device
         self.flat = torch.empty(total, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_store = torch.zeros(total + 1, dtype=torch.float32, device=dev)     # + 1: the sample count of a data-parallel all-reduce
+        self.flat_grad = self.grad_store[:total]
+        self.forward_id = 0
         off = 0
         self._views = []
         with torch.cuda.device(dev):
@@ -549,6 +581,89 @@ class TrainHandle:
             self.close()
         except Exception:
             pass
+
+
+class ScenePipeline:
+    """End-to-end whole-scene classification of a STREAM of same-sized scenes from pinned host rasters, software-pipelined:
+    while the kernels classify scene i on the caller's stream, scene i+1 is already being uploaded on a copy stream (H2D of
+    this rank's rows, its min / max, and under torch.distributed the 4-value range all-reduce), so the copy engine and the
+    SMs work at the same time.  Per scene: H2D (band + p-1 halo rows of MS, PAN, labels) -> to_tensor range of the WHOLE scene
+    (function/function.py:120-124) -> normalise + reflect-pad -> dmf_infer_scene on the rank's row band -> int64 C x C
+    all-reduce -> D2H of the label band and the matrix (solver/mainsolver.py:104-141, 167-185 for every pixel of the scene).
+
+        pipe = ScenePipeline(net_handle, H, W, p, r0, r1)          # rows [r0, r1) of the scene are this rank's anchors
+        t = pipe.submit(ms_pin, pan_pin, label_pin)                # whole-scene pinned tensors (int16 views of uint16 are fine)
+        pred_band, cm = pipe.result(t)                             # pinned host tensors, valid until `depth` more submits
+    """
+
+    class _Slot:
+        pass
+
+    def __init__(self, net, H, W, p, r0, r1, ms_dtype=torch.int16, pan_dtype=torch.int16, depth=2, device=None, group=None):
+        import torch.distributed as dist
+        self.net, self.H, self.W, self.p, self.r0, self.r1 = net, H, W, p, r0, r1
+        self.device = device or net.device
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.group, self.dist = group, dist
+        self.s0, self.s1 = band_slice(H, p, r0, r1)
+        Hb, C_ = self.s1 - self.s0, net.C
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots, self.n = [], 0
+        with torch.cuda.device(self.device):
+            for _ in range(depth):
+                s = ScenePipeline._Slot()
+                s.ms = torch.empty((Hb, W, 4), dtype=ms_dtype, device=self.device)
+                s.pan = torch.empty((4 * Hb, 4 * W), dtype=pan_dtype, device=self.device)
+                s.lab = torch.empty((Hb, W), dtype=torch.uint8, device=self.device)
+                s.scene = Scene.from_raw(s.ms, s.pan, p, self.device)          # allocates the padded rasters once (contents replaced per scene)
+                s.pm = torch.zeros((Hb, W), dtype=torch.uint8, device=self.device)
+                s.cm = torch.zeros((C_, C_), dtype=torch.int64, device=self.device)
+                s.pm_host = torch.empty((r1 - r0, W), dtype=torch.uint8).pin_memory()
+                s.cm_host = torch.empty((C_, C_), dtype=torch.int64).pin_memory()
+                s.uploaded, s.consumed, s.done = (torch.cuda.Event() for _ in range(3))
+                s.rng = None
+                s.consumed.record()
+                self.slots.append(s)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.slots[0].ms, self.slots[0].pan, self.slots[0].lab))
+        self.d2h_bytes = (r1 - r0) * W + C_ * C_ * 8
+
+    def submit(self, ms_pin, pan_pin, lab_pin):
+        s = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        s0, s1, r0, r1 = self.s0, self.s1, self.r0, self.r1
+        with torch.cuda.device(self.device):
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(s.consumed)               # the slot's raw buffers were read by its previous scene
+                s.ms.copy_(ms_pin[s0:s1], non_blocking=True)
+                s.pan.copy_(pan_pin[4 * s0:4 * s1], non_blocking=True)
+                s.lab.copy_(lab_pin[s0:s1], non_blocking=True)
+                if self.world > 1:
+                    a = raster_minmax(s.ms[r0 - s0:r1 - s0])
+                    b = raster_minmax(s.pan[4 * (r0 - s0):4 * (r1 - s0)])
+                    s.rng = torch.stack([a[0], -a[1], b[0], -b[1]])
+                    self.dist.all_reduce(s.rng, op=self.dist.ReduceOp.MIN, group=self.group)
+                    s.ranges = (torch.stack([s.rng[0], -s.rng[1]]), torch.stack([s.rng[2], -s.rng[3]]))
+                s.uploaded.record()
+            cur = torch.cuda.current_stream()
+            cur.wait_event(s.uploaded)
+            if self.world > 1:
+                s.scene.update_raw(s.ms, s.pan, *s.ranges)
+            else:
+                s.scene.update_raw(s.ms, s.pan)
+            s.scene.set_labels(s.lab)
+            s.consumed.record()
+            s.cm.zero_()
+            self.net.infer_scene(s.scene, r0 - s0, r1 - s0, pred_map=s.pm, cm=s.cm)
+            if self.world > 1:
+                self.dist.all_reduce(s.cm, group=self.group)
+            s.pm_host.copy_(s.pm[r0 - s0:r1 - s0], non_blocking=True)
+            s.cm_host.copy_(s.cm, non_blocking=True)
+            s.done.record()
+        return s
+
+    def result(self, ticket):
+        ticket.done.synchronize()
+        return ticket.pm_host, ticket.cm_host
 
 
 def _from_ptr(ptr, nbytes, device):

@@ -25,6 +25,7 @@ SIGNATURES = {
     'dmf_scene_update_raw_range': (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp]),
     'dmf_scene_create_padded': (i32, [C.POINTER(vp), vp, vp, i32, i32, i32, i32, i32, vp]),
     'dmf_scene_set_mspan': (i32, [vp, vp, i32, i32, vp]),
+    'dmf_scene_set_mspan_ihs': (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
     'dmf_scene_set_labels': (i32, [vp, vp, i32, vp]),
     'dmf_scene_destroy': (i32, [vp]),
     'dmf_scene_dims': (i32, [vp, C.POINTER(C.c_int32)]),

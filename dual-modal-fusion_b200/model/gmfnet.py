@@ -43,15 +43,28 @@ class _NativeTrainFn(torch.autograd.Function):
     def forward(ctx, net, ms, pan, *params):
         h = net.trainer()
         ctx.h, ctx.n_params = h, len(params)
-        return h.forward(ms, pan)
+        out = h.forward(ms, pan)
+        h.forward_id += 1                             # the handle keeps ONE set of activations: those of the latest forward
+        ctx.forward_id = h.forward_id
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
         h = ctx.h
+        if ctx.forward_id != h.forward_id:
+            raise RuntimeError("gmfnet: backward through a forward whose activations were overwritten by a later forward of the "
+                               "same model (the native training handle keeps one activation workspace); call backward before "
+                               "the next forward, or use Net.train_step per micro-batch")
+        # flat_grad is the storage of every p.grad (autograd ACCUMULATES what this function returns into it): run the native
+        # backward on a zeroed buffer, hand out a copy, put the accumulated gradients back untouched
+        keep = h.flat_grad.clone()
         h.flat_grad.zero_()
         h.backward(dlogits)
-        g = h.flat_grad.clone()                       # the buffer is reused by the next backward
-        h.flat_grad.zero_()
+        g = h.flat_grad.clone()
+        h.flat_grad.copy_(keep)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(g)                        # data-parallel: the ranks' gradients are averaged here too
+            g.div_(dist.get_world_size())
         grads = tuple(g[off:off + k].view(q.shape) for q, off, k in h._views)
         return (None, None, None) + grads
 
@@ -128,7 +141,7 @@ class Net(nn.Module):
         h = self.trainer()
         h.reseat_grads()
         loss = h.step_patches(ms, pan, target)
-        self._sync_grads(h)
+        self._sync_grads(h, ms.shape[0])
         optimizer.step()
         return loss
 
@@ -137,15 +150,21 @@ class Net(nn.Module):
         h = self.trainer()
         h.reseat_grads()
         loss = h.step_scene(scene, flat_idx, use_mspan)
-        self._sync_grads(h)
+        self._sync_grads(h, int(flat_idx.numel() if hasattr(flat_idx, 'numel') else len(flat_idx)))
         optimizer.step()
         return loss
 
     @staticmethod
-    def _sync_grads(h):
+    def _sync_grads(h, n_local):
+        """Data-parallel gradient of the GLOBAL batch: each rank's gradient is the mean over its n_local samples, so the global
+        mean is sum_r n_r g_r / sum_r n_r.  One collective: the sample count rides in the spare last element of the flat
+        gradient buffer (the ranks' sub-batches may differ by one sample)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(h.flat_grad)                          # one bucket: the whole model
-            h.flat_grad.div_(dist.get_world_size())
+            store = h.grad_store                                  # flat_grad + 1 trailing element
+            h.flat_grad.mul_(float(n_local))
+            store[-1] = float(n_local)
+            dist.all_reduce(store)                                # one bucket: the whole model
+            h.flat_grad.div_(store[-1])
 
     def forward(self, ms, pan):
         if not ms.is_cuda:

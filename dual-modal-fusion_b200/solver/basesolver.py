@@ -16,6 +16,8 @@ import time
 import numpy as np
 import torch
 
+import torch.distributed as dist
+
 import dmf
 from function.function import data_padding, data_show, label_mat2np, read_tif, split_data, split_data_old
 from indicators.kappa import aa_oa, expo_result
@@ -53,6 +55,12 @@ class BaseSolver:
             label_np = np.load(cfg['data_address'] + 'label.npy', encoding='bytes', allow_pickle=True)
         data_show(label_np)
         self.label_np = label_np
+        size = cfg['DATA_DICT'][cfg['data_city']]['size']
+        if tuple(label_np.shape[:2]) != (self.scene.H, self.scene.W) or (int(size[0]), int(size[1])) != (self.scene.H, self.scene.W):
+            # the index lists (split_data_old over cfg size), the label map and the rasters must describe the same grid: flat
+            # pixel indices row*W + col are shared by all three
+            raise ValueError('scene is %d x %d but label.npy is %s and DATA_DICT[%s].size is %s' %
+                             (self.scene.H, self.scene.W, tuple(label_np.shape), cfg['data_city'], size))
         self.scene.set_labels(label_np.astype(np.uint8))
         if cfg['data_new'] == 1:
             xyl_matrix, self.traintest_index = split_data(self.train_label, self.test_label, label_np, cfg)
@@ -78,8 +86,16 @@ class BaseSolver:
             self._PAN = data_padding(self.pan, self.cfg, 'pan')
         return self._PAN
 
-    def _loader(self, indices, batch_size, shuffle=False):
-        return PatchLoader(self.dataset, indices, batch_size, shuffle)
+    @staticmethod
+    def dist_info():
+        """(rank, world) of the default process group, (0, 1) without torch.distributed."""
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def _loader(self, indices, batch_size, shuffle=False, shard=False):
+        rank, world = self.dist_info() if shard else (0, 1)
+        return PatchLoader(self.dataset, indices, batch_size, shuffle, rank, world)
 
     def dataloader(self):
         """Same subsets, same split arithmetic and same consumption of the global torch RNG as
@@ -100,7 +116,8 @@ class BaseSolver:
                                                   [train_size, len(labelled) - train_size - valid_size, valid_size])
             train_idx, test_idx, valid_idx = (labelled[p.indices] for p in parts)
             color1 = labelled
-        self.train_loader = self._loader(train_idx, cfg['batchsize'], shuffle=True)
+        # data-parallel training: every rank takes its slice of each (identically drawn) batch; gradients are averaged
+        self.train_loader = self._loader(train_idx, cfg['batchsize'], shuffle=True, shard=True)
         self.test_loader = self._loader(test_idx, cfg['test_batchsize'])
         self.valid_loader = self._loader(valid_idx, cfg['color_batchsize'])
         self.color_loader1 = self._loader(color1, cfg['test_batchsize'])
@@ -116,11 +133,12 @@ class BaseSolver:
         self.ckp = {'epoch': self.epoch, 'records': self.records}
 
     def indicator(self):
-        if self.cfg['test']['save_matrix']:
+        writer = self.dist_info()[0] == 0                 # files are written by rank 0 only (every rank holds the same matrix)
+        if self.cfg['test']['save_matrix'] and writer:
             os.makedirs(self.cfg['RESULT_output'], exist_ok=True)
             np.save(self.cfg['RESULT_output'] + str(self.time) + "_matrix.npy", self.test_matrix)
         self.result = aa_oa(self.test_matrix)
-        if self.cfg.get('RESULT_excel'):
+        if self.cfg.get('RESULT_excel') and writer:
             expo_result(self.result, self.cfg, [self.train_time, self.test_time], self.time)
         return self.result
 

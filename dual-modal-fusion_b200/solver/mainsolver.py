@@ -39,6 +39,14 @@ def row_band(H, rank, world):
     return r0, r0 + base + (1 if rank < extra else 0)
 
 
+def indices_in_band(flat_idx, W, r0, r1):
+    """The flat pixel indices (row*W + col) whose row lies in [r0, r1): a rank's share of a sample set under row-band sharding.
+    The shares of all ranks partition the set, so the all-reduced confusion matrix counts every sample exactly once."""
+    flat_idx = np.asarray(flat_idx, dtype=np.int64)
+    rows = flat_idx // W
+    return flat_idx[(rows >= r0) & (rows < r1)]
+
+
 class Solver(BaseSolver):
     def __init__(self, cfg):
         super().__init__(cfg)
@@ -69,7 +77,14 @@ class Solver(BaseSolver):
         if not cfg['train']['pretrained']:
             self.init_model()
         self.cur_model = self.model.to(self.DEVICE)
-        os.makedirs(cfg['RESULT_output'], exist_ok=True)
+        rank, world = self.dist_info()
+        # Data-parallel training (torchrun): every rank holds the same initial weights (same seed, test.py:8), takes its slice of
+        # every batch (PatchLoader) and the flat gradient is averaged (Net.train_step), so the parameters stay identical on all
+        # ranks.  BatchNorm normalises with the rank's own sub-batch statistics; the running statistics are averaged over the
+        # ranks at the end of every epoch.  Files are written by rank 0.
+        if rank == 0:
+            os.makedirs(cfg['RESULT_output'], exist_ok=True)
+        self.val_losses = []
         while self.epoch < self.EPOCH:
             self.cur_model.train()
             bar = self._bar(self.train_loader)
@@ -93,6 +108,11 @@ class Solver(BaseSolver):
                     bar.set_postfix(ls=loss.item(), b_ep=best_epoch, ep=self.epoch, tm=self.time, m='train', d=cfg['device'])
             if cfg['schedule']['if_scheduler']:
                 self.scheduler.step()
+            if world > 1:
+                for b in self.cur_model.buffers():
+                    if torch.is_floating_point(b):
+                        dist.all_reduce(b)
+                        b.div_(world)
             if save_best:
                 self.cur_model.eval()
                 val_loss = torch.zeros((), device=self.DEVICE)
@@ -101,11 +121,17 @@ class Solver(BaseSolver):
                         out = self.cur_model(data1, data2)
                         val_loss += self.loss(out, target.long()) * data1.size(0)     # accumulated on the device
                 val_loss = float(val_loss)
+                self.val_losses.append(val_loss)
                 if val_loss < best_loss:
                     best_loss, best_epoch = val_loss, self.epoch
-                    torch.save(self.cur_model.state_dict(), self._weights('_weights.pth'))
-            save_checkpoint(self.cur_model, self.optimizer, self._weights('_curweights.pth'))
+                    if rank == 0:
+                        torch.save(self.cur_model.state_dict(), self._weights('_weights.pth'))
+            if rank == 0:
+                save_checkpoint(self.cur_model, self.optimizer, self._weights('_curweights.pth'))
             self.epoch += 1
+        self.best_epoch, self.best_loss = best_epoch, best_loss
+        if world > 1:
+            dist.barrier()                # the checkpoints rank 0 wrote are complete before any rank reads them
         self.train_time = time.time() - t0
         self.epoch = 0
 
@@ -115,10 +141,18 @@ class Solver(BaseSolver):
         if self.cur_model is None:
             self.cur_model = self.model.to(self.DEVICE)
         best, cur = self._weights('_weights.pth'), self._weights('_curweights.pth')
-        if self.cfg['train']['save_best'] and os.path.exists(best):
-            self.cur_model.load_state_dict(torch.load(best, map_location=self.DEVICE))
-        elif os.path.exists(cur):
-            self.cur_model.load_state_dict(torch.load(cur, map_location=self.DEVICE)['state_dict'])
+        # the reference's choice (solver/mainsolver.py:95-98): the best-validation weights when save_best, else the last epoch's
+        # (its `_curweights.pth` holds {state_dict, optimizer}, utils/utils.py:82-88).  A missing file raises, as torch.load does
+        # there: an untrained network must not produce plausible-looking metrics.  `test.allow_random_init` (tests, benchmarks
+        # of the inference path) evaluates the model as it stands instead.
+        if self.cfg['train']['save_best']:
+            path, pick = best, (lambda ck: ck)
+        else:
+            path, pick = cur, (lambda ck: ck['state_dict'])
+        if os.path.exists(path):
+            self.cur_model.load_state_dict(pick(torch.load(path, map_location=self.DEVICE)))
+        elif not self.cfg['test'].get('allow_random_init', False):
+            raise FileNotFoundError('no checkpoint %s (train first, or set test.allow_random_init)' % path)
         self.cur_model.eval()
 
     # ------------------------------------------------------------------ test
@@ -131,19 +165,27 @@ class Solver(BaseSolver):
         C = self.cfg['Categories_Number']
         cm = torch.zeros((C, C), dtype=torch.int64, device=self.DEVICE)
         first_only = bool(self.cfg['test'].get('first_batch_only', False))
-        sharded = dist.is_available() and dist.is_initialized() and self.cfg.get('shard_test')
+        rank, world = self.dist_info()
+        sharded = world > 1 and not first_only and self.cfg.get('shard_test', True)
         idx = getattr(self.test_loader, 'indices', None)
         H, W = self.scene.H, self.scene.W
+        flat = self.dataset.flat_index(idx) if idx is not None else None        # dataset indices -> flat pixel indices row*W + col
         # dense whole-scene pass ~ 10x cheaper per pixel than a per-patch evaluation
-        dense = (not first_only and not sharded and idx is not None and getattr(self.cur_model, 'dense', False)
-                 and 8 * len(idx) >= H * W)
+        dense = (not first_only and flat is not None and getattr(self.cur_model, 'dense', False) and 8 * len(flat) >= H * W)
         with torch.no_grad():
             if dense:
-                pred_map, _ = self.cur_model.infer_scene(self.scene, 0, H, cm=torch.zeros_like(cm))
-                label_dev = torch.from_numpy(np.asarray(self.label_np).astype(np.uint8)).to(self.DEVICE)
-                dmf.confusion_at(pred_map, label_dev, torch.from_numpy(np.asarray(idx, dtype=np.int64)), C, cm=cm)
+                # under torch.distributed every rank classifies its row band and counts the samples that fall into it
+                r0, r1 = row_band(H, rank, world) if sharded else (0, H)
+                mine = indices_in_band(flat, W, r0, r1)
+                if flat.size and (flat.min() < 0 or flat.max() >= H * W):
+                    raise IndexError('test sample outside the %d x %d scene' % (H, W))
+                pred_map, _ = self.cur_model.infer_scene(self.scene, r0, r1, cm=torch.zeros_like(cm))
+                dmf.confusion_at(pred_map, self.scene_labels(), torch.from_numpy(mine), C, cm=cm)
             else:
-                for data1, data2, target, _, _ in self._bar(self.test_loader):
+                loader = self.test_loader
+                if sharded:                       # each rank runs its slice of every batch
+                    loader = self._loader(idx, self.cfg['test_batchsize'], shard=True)
+                for data1, data2, target, _, _ in self._bar(loader):
                     out = self.cur_model(data1, data2)
                     dmf.argmax_confusion(out, target, C, cm=cm, want_pred=False)
                     if first_only:
@@ -153,6 +195,12 @@ class Solver(BaseSolver):
         self.test_time = time.time() - t0
         self.test_matrix = cm.cpu().numpy().astype(np.float64)
         self.indicator()
+
+    def scene_labels(self):
+        """the label map on the device, uint8 [H, W] (the scene's own grid)"""
+        if getattr(self, '_label_dev', None) is None:
+            self._label_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(self.label_np)[:self.scene.H, :self.scene.W]).astype(np.uint8)).to(self.DEVICE)
+        return self._label_dev
 
     # ------------------------------------------------------------------ whole-scene inference
     def classify_scene(self):
@@ -177,6 +225,8 @@ class Solver(BaseSolver):
         map1 = torch.where(labelled, pred_map, torch.zeros_like(pred_map)) if self.cfg['color']['supervised'] else torch.zeros_like(pred_map)
         map2 = pred_map if self.cfg['color']['unsupervised'] else map1
         self.label_np1, self.label_np2 = map1.cpu().numpy().astype(np.float64), map2.cpu().numpy().astype(np.float64)
+        if self.dist_info()[0] != 0:
+            return                                # every rank holds the whole label map after the all-reduce; rank 0 paints and writes
         os.makedirs(self.cfg['RESULT_output'], exist_ok=True)
         for tag, m in (('_pic_1.png', map1), ('_pic_2.png', map2)):
             rgb = dmf.paint_labels(m, colors).cpu().numpy()

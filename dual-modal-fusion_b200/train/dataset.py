@@ -91,15 +91,24 @@ class PatchLoader:
     SequentialSampler / BatchSampler behave (and consume the global RNG) exactly as in
     solver/basesolver.py:94-104."""
 
-    def __init__(self, dataset, indices, batch_size, shuffle=False):
+    def __init__(self, dataset, indices, batch_size, shuffle=False, rank=0, world=1):
+        """rank / world: data-parallel sharding of every batch (torch.distributed): all ranks draw the SAME batches from the
+        same sampler (same global seed, test.py:8) and rank r keeps elements r, r + world, ... of each, so the union of the
+        ranks' sub-batches is exactly the reference's batch and every sample is visited once per epoch."""
         self.dataset = dataset
         self.indices = np.asarray(indices, dtype=np.int64)
         self.batch_size = batch_size
+        self.rank, self.world = int(rank), int(world)
         self._index_loader = DataLoader(_IndexOnly(self.indices), batch_size=batch_size, shuffle=shuffle, num_workers=0)
 
     def __iter__(self):
         for idx in self._index_loader:
-            yield self.dataset.gather_batch(idx.numpy())
+            idx = idx.numpy()
+            if self.world > 1:
+                if idx.size < self.world:          # a tail batch that cannot feed every rank is dropped by ALL ranks alike
+                    continue
+                idx = idx[self.rank::self.world]
+            yield self.dataset.gather_batch(idx)
 
     def __len__(self):
         return len(self._index_loader)

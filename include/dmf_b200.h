@@ -93,6 +93,14 @@ int dmf_scene_create_padded(dmf_scene** out, const void* ms_pad, const void* pan
                             int H, int W, int p, int on_device, void* stream);
 /* Attach the third raster of dataset_tri (train/dataset.py:249-268), same shape as pan_pad. */
 int dmf_scene_set_mspan(dmf_scene* s, const void* mspan_pad, int dtype, int on_device, void* stream);
+/* The same raster computed ON THE DEVICE from the raw rasters of the scene — replaces IHS_tran(to_tensor(ms), to_tensor(pan))
+ * (image_convert/IHS.py:40-54 on function/function.py:120-124) + the reflect-101 padding of data_padding (function/function.py:104-110)
+ * + the dataset's float32 cast (train/dataset.py:265-268) in one pass: float64 arithmetic in the reference's operation order, so the
+ * result is float32(reference float64 value) bit for bit.  ms[H][W][4], pan[4H][4W] as for dmf_scene_create_raw; offsets_dev =
+ * int8[4][H][W][2], the (m, n) draws of unpooling() (image_convert/IHS.py:25-28) in band -> row -> col order; ms_lohi_dev /
+ * pan_lohi_dev: device {min, max} pairs to normalise with (row-band scenes), or both NULL = the rasters' own ranges. */
+int dmf_scene_set_mspan_ihs(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int on_device,
+                            const int8_t* offsets_dev, const double* ms_lohi_dev, const double* pan_lohi_dev, void* stream);
 /* Attach the label map uint8[H][W] (label.npy, solver/basesolver.py:35-37). */
 int dmf_scene_set_labels(dmf_scene* s, const uint8_t* label, int on_device, void* stream);
 int dmf_scene_destroy(dmf_scene* s);

@@ -44,3 +44,72 @@ def test_band_sharded_confusion_matrix_allreduce_gloo():
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert out.get(timeout=5) == (True, True)
+
+
+def _worker_shards(rank, world, port, out):
+    """Host logic of the data-parallel paths under a real process group (gloo, CPU): PatchLoader batch sharding, the row-band
+    share of a test sample set + all-reduced matrix (Solver.test), and the sample-weighted gradient average (Net._sync_grads)."""
+    for p in (REPO, os.path.join(REPO, 'dual-modal-fusion_b200')):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle import dmf_oracle as orc
+    from solver.mainsolver import indices_in_band, row_band
+    from train.dataset import PatchLoader
+    from model.gmfnet import Net
+
+    class FakeDataset:                                   # gather_batch would launch K1; the index flow is what is tested
+        def gather_batch(self, idx):
+            return np.asarray(idx)
+
+    H, W, C = 41, 23, 5
+    rng = np.random.default_rng(0)
+    pred = rng.integers(0, C, (H, W))
+    label = rng.integers(0, C, (H, W))
+    test_idx = np.sort(rng.choice(H * W, size=301, replace=False))
+    # (1) Solver.test under torch.distributed: every sample is counted exactly once
+    r0, r1 = row_band(H, rank, world)
+    mine = indices_in_band(test_idx, W, r0, r1)
+    cm = torch.from_numpy(orc.confusion(pred.reshape(-1)[mine], label.reshape(-1)[mine], C).astype(np.int64))
+    dist.all_reduce(cm)
+    ok_cm = int(cm.sum()) == len(test_idx) and np.array_equal(
+        cm.numpy().astype(np.float64), orc.confusion(pred.reshape(-1)[test_idx], label.reshape(-1)[test_idx], C))
+    # (2) PatchLoader sharding: same batches on every rank (same seed), rank r keeps elements r::world, short tails are dropped by all
+    train_idx = rng.permutation(H * W)[:101]
+    torch.manual_seed(3407)
+    got = [b for b in PatchLoader(FakeDataset(), train_idx, 8, shuffle=True, rank=rank, world=world)]
+    torch.manual_seed(3407)
+    full = [b for b in PatchLoader(FakeDataset(), train_idx, 8, shuffle=True)]
+    full = [b for b in full if len(b) >= world]
+    ok_loader = len(got) == len(full) and all(np.array_equal(g, f[rank::world]) for g, f in zip(got, full))
+    steps = torch.tensor([len(got)])
+    lo, hi = steps.clone(), steps.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok_loader = ok_loader and int(lo) == int(hi)          # every rank runs the same number of steps (no collective is left hanging)
+    # (3) gradient of the global batch = sum_r n_r g_r / sum_r n_r, one collective
+    class H_:
+        pass
+    h = H_()
+    h.grad_store = torch.zeros(7, dtype=torch.float32)
+    h.flat_grad = h.grad_store[:6]
+    n_local = 3 + rank                                     # unequal sub-batches
+    g_local = torch.arange(6, dtype=torch.float32) * (rank + 1)
+    h.flat_grad.copy_(g_local)
+    Net._sync_grads(h, n_local)
+    want = sum((3 + r) * torch.arange(6, dtype=torch.float32) * (r + 1) for r in range(world)) / sum(3 + r for r in range(world))
+    ok_grad = torch.allclose(h.flat_grad, want, rtol=1e-6)
+    if rank == 0:
+        out.put((bool(ok_cm), bool(ok_loader), bool(ok_grad)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_gloo():
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_shards, args=(r, 2, port, out)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(180) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert out.get(timeout=5) == (True, True, True)

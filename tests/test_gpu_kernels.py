@@ -193,3 +193,83 @@ def test_confusion_at_matches_oracle(dmf):
     assert np.array_equal(cm_all.cpu().numpy().astype(np.float64), orc.confusion(pm.reshape(-1), lab.reshape(-1), C))
     cm2 = dmf.confusion_at(pm_d, lab_d, torch.from_numpy(idx[:0]), C, cm=cm.clone())      # empty list: unchanged
     assert torch.equal(cm2, cm)
+
+
+# ------------------------------------------------------------------ r02: TMA gather sizes, device IHS -> scene
+@pytest.mark.parametrize('p', [4, 12, 20, 64])
+def test_gather_tma_chunking_other_patch_sizes(dmf, p):
+    """p = 4 (1 KB windows), 12 / 20 (PAN chunks that must divide the window: 48 rows, 40 + 40), 64 (16 chunks of 16 rows); dual and tri."""
+    H, W = 29, 31
+    ms, pan, label = orc.synthetic_scene(H, W, 5, seed=13, label_seed=14)
+    MS, PAN = orc.data_padding(ms, p), orc.data_padding(pan, p)
+    MSPAN = np.random.default_rng(p).random(PAN.shape)
+    sc = dmf.Scene.from_raw(ms, pan, p, DEV)
+    sc.set_labels(label)
+    sc.set_mspan(MSPAN)
+    rng = np.random.default_rng(100 + p)
+    idx = np.concatenate([rng.integers(0, H * W, 700 if p < 64 else 60), [0, W - 1, (H - 1) * W, H * W - 1]])
+    a, b, c, t = sc.gather(idx, tri=True)
+    ra, rb, rc = orc.gather_tri(MS, PAN, MSPAN, idx // W, idx % W, p)
+    eq(a.cpu().numpy(), ra)
+    eq(b.cpu().numpy(), rb)
+    eq(c.cpu().numpy(), rc)
+    eq(t.cpu().numpy(), label.reshape(-1)[idx].astype(np.float32))
+    a2, b2, _ = sc.gather(idx, want_target=False)
+    eq(a2.cpu().numpy(), ra)
+    eq(b2.cpu().numpy(), rb)
+
+
+def test_gather_rejects_out_of_range_host_indices(dmf):
+    ms, pan, _ = orc.synthetic_scene(20, 20, 3, seed=1)
+    sc = dmf.Scene.from_raw(ms, pan, 8, DEV)
+    with pytest.raises(IndexError):
+        sc.gather([0, 400], want_target=False)
+    with pytest.raises(IndexError):
+        sc.gather(np.array([-1]), want_target=False)
+
+
+def test_gather_after_update_raw_sees_the_new_rasters(dmf):
+    """the planar MS copy / tensor maps of K1 follow dmf_scene_update_raw"""
+    p, H, W = 16, 33, 38
+    ms1, pan1, _ = orc.synthetic_scene(H, W, 5, seed=1)
+    ms2, pan2, _ = orc.synthetic_scene(H, W, 5, seed=2, blocky=True)
+    sc = dmf.Scene.from_raw(ms1, pan1, p, DEV)
+    idx = np.arange(0, H * W, 7)
+    sc.gather(idx, want_target=False)
+    sc.update_raw(ms2, pan2)
+    a, b, _ = sc.gather(idx, want_target=False)
+    ra, rb = orc.gather_dual(orc.data_padding(ms2, p), orc.data_padding(pan2, p), idx // W, idx % W, p)
+    eq(a.cpu().numpy(), ra)
+    eq(b.cpu().numpy(), rb)
+
+
+@pytest.mark.parametrize('dt', ['u16', 'u8', 'f32', 'f64'])
+def test_scene_mspan_from_ihs_on_device_matches_oracle(dmf, dt):
+    """dmf_scene_set_mspan_ihs == float32(reflect-pad(IHS_tran(to_tensor(ms), to_tensor(pan)))) bit for bit
+    (image_convert/IHS.py:40-54 on function/function.py:99-124), then the tri gather reads it."""
+    rng = np.random.default_rng(17)
+    H, W, p = 23, 27, 8
+    if dt == 'u16':
+        ms, pan = rng.integers(0, 2048, (H, W, 4), dtype=np.uint16), rng.integers(0, 2048, (4 * H, 4 * W), dtype=np.uint16)
+    elif dt == 'u8':
+        ms, pan = rng.integers(2, 251, (H, W, 4), dtype=np.uint8), rng.integers(0, 256, (4 * H, 4 * W), dtype=np.uint8)
+    else:
+        t = np.float32 if dt == 'f32' else np.float64
+        ms, pan = rng.normal(100, 30, (H, W, 4)).astype(t), rng.normal(90, 25, (4 * H, 4 * W)).astype(t)
+    offs = rng.integers(0, 4, (4, H, W, 2)).astype(np.int8)
+    prod = orc.ihs_tran_from_offsets(orc.to_tensor(ms), orc.to_tensor(pan), offs)
+    rows = orc.reflect101_index(np.arange(4 * H + 4 * p - 1), 4 * H)
+    cols = orc.reflect101_index(np.arange(4 * W + 4 * p - 1), 4 * W)
+    want = prod[rows][:, cols].astype(np.float32)
+    sc = dmf.Scene.from_raw(ms, pan, p, DEV)
+    sc.set_mspan_ihs(ms, pan, offs)
+    eq(sc.export(2).cpu().numpy(), want)
+    # device-resident inputs give the same raster; so does the host-padded route it replaces
+    as_t = lambda a: torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).to(DEV)
+    sc2 = dmf.Scene.from_raw(ms, pan, p, DEV)
+    sc2.set_mspan_ihs(as_t(ms), as_t(pan), torch.from_numpy(offs).to(DEV))
+    eq(sc2.export(2).cpu().numpy(), want)
+    idx = np.array([0, W - 1, (H - 1) * W, H * W - 1, 5 * W + 3])
+    _, _, c, _ = sc.gather(idx, tri=True, want_target=False)
+    _, rc = orc.gather_dual(orc.data_padding(ms, p), prod[rows][:, cols], idx // W, idx % W, p)
+    eq(c.cpu().numpy(), rc)

@@ -21,7 +21,7 @@ def c1_cfg(tmp, ms, pan, label, train=0, color=1):
             'DATA_DICT': {'c1': {'size': [128, 128, 4], 'color': colors}},
             'schedule': {'loss': 'Criterion', 'optimizer': 'ADAM', 'if_scheduler': 0, 'scheduler': 'ExponentialLR',
                          'activate': 'Relu', 'lr': 1e-3, 'base_lr': 5e-4},
-            'train': {'index': train, 'pretrained': 0, 'save_best': True}, 'test': {'index': 1, 'save_matrix': 1},
+            'train': {'index': train, 'pretrained': 0, 'save_best': True}, 'test': {'index': 1, 'save_matrix': 1, 'allow_random_init': True},
             'color': {'index': color, 'supervised': 1, 'unsupervised': 1},
             'RESULT_output': str(tmp) + '/out/', 'RESULT_excel': str(tmp) + '/result.xlsx',
             'rasters': {'ms': ms, 'pan': pan, 'label': label}}
@@ -97,3 +97,81 @@ def test_train_epoch_then_eval_uses_updated_weights(tmp_path):
         native = net(d1, d2)
         graph = chk(d1.to(DEV), d2.to(DEV))
     assert torch.allclose(native, graph, rtol=2e-2, atol=5e-3), float((native - graph).abs().max())
+
+
+def test_missing_checkpoint_raises_like_the_reference(tmp_path):
+    """test() / color() of the reference torch.load the checkpoint (solver/mainsolver.py:95-98, 159): without one they raise
+    instead of reporting the metrics of an untrained network."""
+    from solver.mainsolver import Solver
+    ms, pan, label = orc.synthetic_scene(64, 64, 7, seed=4, label_seed=5, blocky=True)
+    cfg = c1_cfg(tmp_path, ms, pan, label, train=0, color=0)
+    cfg['DATA_DICT']['c1']['size'] = [64, 64, 4]
+    cfg['test']['allow_random_init'] = False
+    s = Solver(cfg)
+    s.dataloader()
+    with pytest.raises(FileNotFoundError):
+        s.test()
+    cfg2 = dict(cfg, DATA_DICT={'c1': {'size': [60, 64, 4], 'color': cfg['DATA_DICT']['c1']['color']}})
+    with pytest.raises(ValueError):                       # cfg size, label map and rasters must describe the same grid
+        Solver(cfg2)
+
+
+def test_validation_loss_and_best_epoch_match_the_reference_loop(tmp_path, monkeypatch):
+    """f3: the validation / best-checkpoint logic of Solver.train() (solver/mainsolver.py:62-84).  Three epochs through the mirror
+    Solver; the weights at the end of every epoch are then pushed through an oracle loop that restates the reference text
+    (fp32 oracle Net in eval mode, ``val_loss += loss.item() * data1.size(0)`` with the early ``break`` once the running sum
+    exceeds the best loss, ``if val_loss < best_loss`` -> new best): same best epoch, per-epoch validation loss within 2e-3
+    relative (bf16 tensor-core logits vs fp32), `<time>_weights.pth` = the weights of the best epoch, `<time>_curweights.pth`
+    = {state_dict, optimizer} of the last one (utils/utils.py:82-88)."""
+    import copy
+    import solver.mainsolver as sm
+    from oracle.gmfnet_ref import Net as RefNet
+    ms, pan, label = orc.synthetic_scene_structured(72, 72, 7, seed=4, label_seed=5)
+    cfg = c1_cfg(tmp_path, ms, pan, label, train=1, color=0)
+    cfg['DATA_DICT']['c1']['size'] = [72, 72, 4]
+    cfg['train_rate'], cfg['verify_rate'], cfg['epoch'] = 0.25, 0.1, 3
+    cfg['schedule']['lr'] = 3e-3
+    states = []
+    real_save = sm.save_checkpoint
+
+    def spy(model, optimizer, path):
+        states.append(copy.deepcopy({k: v.detach().cpu() for k, v in model.state_dict().items()}))
+        return real_save(model, optimizer, path)
+    monkeypatch.setattr(sm, 'save_checkpoint', spy)
+    torch.manual_seed(0)
+    s = sm.Solver(cfg)
+    s.dataloader()
+    s.train()
+    assert len(states) == 3 and len(s.val_losses) == 3
+    # oracle loop (reference text) on the same weights, fp32 torch on the GPU, TF32 off
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    crit = torch.nn.CrossEntropyLoss()
+    ref = RefNet(cfg).to(DEV)
+    best_loss, best_epoch, full = float('inf'), 0, []
+    for epoch, sd in enumerate(states):
+        ref.load_state_dict(sd)
+        ref.eval()
+        with torch.no_grad():
+            val_loss, total, broke = 0.0, 0.0, False
+            for data1, data2, target, _, _ in s.valid_loader:
+                loss = crit(ref(data1, data2), target.long())
+                total += loss.item() * data1.size(0)
+                if not broke:
+                    val_loss += loss.item() * data1.size(0)
+                    if val_loss > best_loss:
+                        broke = True                      # the reference stops summing here (:73-74); `total` is the full sum
+        full.append(total)
+        if val_loss < best_loss:
+            best_loss, best_epoch = val_loss, epoch
+    assert s.best_epoch == best_epoch, (s.val_losses, full)
+    np.testing.assert_allclose(s.val_losses, full, rtol=2e-3)
+    assert abs(s.best_loss - best_loss) <= 2e-3 * best_loss
+    saved = torch.load(str(tmp_path / 'out' / '0_weights.pth'), map_location='cpu')
+    for k, v in states[best_epoch].items():
+        assert torch.equal(saved[k], v), k
+    cur = torch.load(str(tmp_path / 'out' / '0_curweights.pth'), map_location='cpu')
+    assert set(cur.keys()) >= {'state_dict', 'optimizer'}
+    for k, v in states[-1].items():
+        assert torch.equal(cur['state_dict'][k], v), k
+    assert len(set(np.round(s.val_losses, 6))) == 3                      # the epochs really differ

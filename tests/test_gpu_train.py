@@ -368,3 +368,17 @@ def test_errors_are_loud(dmf):
         h.step_patches(ms, pan, tgt)
     with pytest.raises(RuntimeError, match='no CPU'):
         net.cpu()(ms.cpu(), pan.cpu())
+
+
+def test_data_parallel_gradient_parity_nccl():
+    """2 ranks over NCCL: averaged flat gradient == single-rank gradient of the same two sub-batches (tools/dp_grad_check.py).
+    Skipped on a box with fewer than 2 GPUs (the driver's GPU-test box has one; run under `gpurun --gpus 2`)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29611', os.path.join(repo, 'tools', 'dp_grad_check.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

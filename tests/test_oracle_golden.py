@@ -114,3 +114,27 @@ def test_c1_whole_scene_through_oracle(golden):
     assert np.array_equal(orc.argmax_first(logits), g['label_map'].reshape(-1)[:512])
     aa, oa, k, _ = orc.aa_oa(g['M'])
     eq(np.array([aa, oa, k]), g['aa_oa_k'])
+
+
+def test_fitted_net_reproduces_the_reference_run(golden):
+    """The fitted (non-degenerate) net of oracle/fitted_net.py on the structured C1 scene: same logits and predictions as the
+    run through the reference's Solver objects (tests/golden/solver_c1_fitted.npz), and that run predicts many classes."""
+    import torch
+    from oracle import fitted_net
+    g = golden('solver_c1_fitted')
+    H = W = 128
+    ms, pan, label = orc.synthetic_scene_structured(H, W, 7, seed=0, label_seed=1)
+    MS, PAN = orc.data_padding(ms, 16), orc.data_padding(pan, 16)
+    net = fitted_net.fitted_net('c1')
+    flat = np.arange(512)
+    with torch.no_grad():
+        a, b = orc.gather_dual(MS, PAN, flat // W, flat % W, 16)
+        logits = net(torch.from_numpy(a), torch.from_numpy(b)).numpy()
+    np.testing.assert_allclose(logits, g['logits_first512'], rtol=0, atol=2e-5)
+    assert np.array_equal(orc.argmax_first(logits), g['label_map'].reshape(-1)[:512])
+    eq(orc.confusion(g['label_map'].reshape(-1), label.reshape(-1), 8), g['M'])
+    aa, oa, k, _ = orc.aa_oa(g['M'])
+    eq(np.array([aa, oa, k]), g['aa_oa_k'])
+    assert len(np.unique(g['label_map'])) >= 5 and k > 0.1
+    for tag in fitted_net.WORKLOADS:
+        assert set(fitted_net.fitted_state(tag)) == set(fitted_net.base_net(tag).state_dict())
