@@ -43,7 +43,7 @@ def make_config(wl_key):
     """The `config` object: identical in both arms (--impl b200 / reference) and at every N."""
     wl = WORKLOADS[wl_key]
     return {'workload': wl['name'], 'patch_size': P, 'classes_with_background': wl['classes'] + 1, 'pixels': wl['H'] * wl['W'],
-            'scene': 'structured synthetic rasters, uint16 11-bit, labels depend on the rasters (oracle.synthetic_scene_structured, seeds 0 / 1)',
+            'scene': 'structured synthetic rasters, uint16 11-bit, labels depend on the rasters (oracle/fitted_net.scene: regions of 64 MS pixels, seeds 0 / 1)',
             'net': 'GMFNet, seed-3407 convolutions + calibrated BatchNorm + fitted head (oracle/fitted_net.py): predictions vary, Kappa > 0',
             'sharding': 'row bands over the ranks, scene replicated per rank, one int64 CxC all-reduce per step',
             'l2': 'explicit 256 MiB L2 flush between timed steps; the per-step intermediates (GBs) exceed L2 too'}
@@ -97,9 +97,8 @@ class ClockSampler:
 
 
 def workload_scene(wl_key):
-    from oracle import dmf_oracle as orc
-    wl = WORKLOADS[wl_key]
-    return orc.synthetic_scene_structured(wl['H'], wl['W'], wl['classes'], seed=0, label_seed=1)
+    from oracle import fitted_net
+    return fitted_net.scene(wl_key)
 
 
 def cpu_reference_run(wl_key, budget_s, steps=1, warmup=0, scene=None):
@@ -501,8 +500,17 @@ def main():
                                                         Cc.c_void_p(torch.cuda.current_stream().cuda_stream)))
             g_ms = best_ms(call)
             gbs = 8192 * 20 * p_ * p_ * 4 / g_ms / 1e6
-            entry = {'patch_size': p_, 'batch': 8192, 'bytes_per_patch': 20 * p_ * p_ * 4, 'gather_GBs_written': gbs,
-                     'frac_of_write_ceiling': gbs / write_ceiling, 'frac_of_hbm_copy_peak': gbs / pk['hbm_gbs']}
+            ridx = gidx
+            gidx = torch.arange(300 * sc_p.W + 17, 300 * sc_p.W + 17 + 8192, device=dev)       # loader order (test / colour loaders): consecutive pixels
+            s_ms = best_ms(call)
+            sgbs = 8192 * 20 * p_ * p_ * 4 / s_ms / 1e6
+            gidx = ridx
+            entry = {'patch_size': p_, 'batch': 8192, 'bytes_per_patch': 20 * p_ * p_ * 4,
+                     'gather_GBs_written': sgbs, 'frac_of_write_ceiling': sgbs / write_ceiling, 'frac_of_hbm_copy_peak': sgbs / pk['hbm_gbs'],
+                     'order': 'sequential pixels (the reference test / colour loaders: overlapping windows, source reads served by L2)',
+                     'random_batch': {'gather_GBs_written': gbs, 'frac_of_write_ceiling': gbs / write_ceiling,
+                                      'note': 'RandomSampler-style indices after an L2 flush: every window is first read from DRAM '
+                                              '(compulsory reads ~ the bytes written), so the kernel is bound by read + write traffic'}}
             # conv tensor-pipe utilisation of the per-patch kernels at this patch size, batch 8192 (default-initialised weights)
             torch.manual_seed(0)
             net_p = Net({'Categories_Number': C, 'patch_size': p_, 'schedule': {'activate': 'Relu'}, 'b200': {'max_batch': 8192}}).to(dev).eval()
@@ -526,6 +534,7 @@ def main():
         p16 = sweep[1]
         secondary['patch_gather'] = {'GBs_written': p16['gather_GBs_written'], 'frac_of_write_ceiling': p16['frac_of_write_ceiling'],
                                      'frac_of_hbm_copy_peak': p16['frac_of_hbm_copy_peak'], 'batch': 8192, 'bytes_per_patch': p16['bytes_per_patch'],
+                                     'order': p16['order'], 'random_batch': p16['random_batch'],
                                      'write_ceiling_GBs': write_ceiling,
                                      'note': 'write-only kernel (TMA load -> bulk store): ceiling = a 1 GiB memset measured in this run; the copy peak counts read + write'}
         secondary['c5_patch_size_sweep'] = {'workload': 'BASELINE.json configs[4]: p = 8 / 16 / 32 at batch 8192: K1 gather GB/s and conv tensor throughput of the per-patch kernels',

@@ -2,9 +2,11 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <atomic>
 #include <map>
@@ -68,10 +70,12 @@ int num_sms();
 #ifdef __CUDACC__
 __device__ __forceinline__ double run_mean4(double a0, double a1, double a2, double a3) {
     // I = a0; I = (I*i + a_i) / (i+1) for i = 1..3   (image_convert/IHS.py:42-46, 49-53)
+    // x / 2 and x / 4 are computed as x * 0.5 and x * 0.25: the same real number rounded once, hence the same double for every
+    // input (IEEE 754); only the division by 3 needs a true (and, on the FP64 pipe, ~25-instruction) divide
     double I = a0;
-    I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 1.0), a1), 2.0);
+    I = __dmul_rn(__dadd_rn(__dmul_rn(I, 1.0), a1), 0.5);
     I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 2.0), a2), 3.0);
-    I = __ddiv_rn(__dadd_rn(__dmul_rn(I, 3.0), a3), 4.0);
+    I = __dmul_rn(__dadd_rn(__dmul_rn(I, 3.0), a3), 0.25);
     return I;
 }
 #endif

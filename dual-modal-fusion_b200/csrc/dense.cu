@@ -32,7 +32,7 @@ struct DenseWs {
     __nv_bfloat16 *A = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr;
     float* S = nullptr;                              // row sums of F for the separable average pool [3][16][R][W][8]
     float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
-    // conv + pool layers (ms2, pan2, pan3): tap-major bf16 weights with sign(BN scale) folded into every output channel, |scale|,
+    // conv + pool layers (ms2, pan2, pan3): bf16 weights [C_in/8][tap][C_out][8] with sign(BN scale) folded into every output channel, |scale|,
     // shift — conv_pool4_kernel takes the max over the pooling window BEFORE the affine
     __nv_bfloat16* w_cp[3] = {nullptr, nullptr, nullptr};
     float *sc_cp[3] = {nullptr, nullptr, nullptr}, *sh_cp[3] = {nullptr, nullptr, nullptr};
@@ -512,7 +512,7 @@ int dense_pack(dmf_net* n) {
             for (int ci = 0; ci < cin[l]; ++ci)
                 for (int co = 0; co < cout[l]; ++co) {
                     const float v = (*w)[((size_t)co * cin[l] + ci) * 9 + tap];
-                    pk[(((size_t)tap * (cin[l] / 8) + ci / 8) * cout[l] + co) * 8 + ci % 8] = __float2bfloat16_rn(sc[co] < 0.f ? -v : v);
+                    pk[(((size_t)(ci / 8) * 9 + tap) * cout[l] + co) * 8 + ci % 8] = tc::w16(sc[co] < 0.f ? -v : v);   // [ci/8][tap][co][8], fp16
                 }
         for (auto& v : sc) v = fabsf(v);
         DMF_TRY(to_device(&d->w_cp[l], pk));

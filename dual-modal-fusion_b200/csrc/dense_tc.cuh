@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(128, C_OUT);
+        constexpr uint32_t idesc = umma_idesc_bf16_wf16(128, C_OUT);          // weights are fp16 (tc::w16), activations bf16
         const bool leader = elect_one();
         mbar_wait(w_bar, 0);
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
@@ -292,7 +292,7 @@ struct Pool4Params {
     int dbg;
     // rows / columns of each border class (first, interior, last) that some anchor of the band actually uses: [lo, lo + n)
     int row_lo[3], row_n[3], col_lo[3], col_n[3];
-    const __nv_bfloat16* w;               // packed [tap][C_in/8][C_out][8], output channel co multiplied by sign(BN scale[co])
+    const __nv_bfloat16* w;               // packed [C_in/8][tap][C_out][8], output channel co multiplied by sign(BN scale[co])
     const float* scale;                   // |BN scale| (its sign is folded into w)
     const float* shift;
     __nv_bfloat16* out;                   // [9][out_chunks][rows][cols][8]
@@ -408,10 +408,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(128, C_OUT);
+        // The packed weights are [C_in/8][tap][C_out][8]: for one channel chunk the 9 taps are consecutive C_out-row blocks, so a
+        // B descriptor that starts at tap t and spans N = 2 * C_out rows covers taps t and t + 1 = (dy, dx) and (dy, dx + 1).
+        constexpr uint32_t idesc1 = umma_idesc_bf16_wf16(128, C_OUT), idesc2 = umma_idesc_bf16_wf16(128, 2 * C_OUT);      // fp16 weights, bf16 activations
         const bool leader = elect_one();
         mbar_wait(w_bar, 0);
-        const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
+        const uint64_t w_desc0 = umma_desc(smem_u32(w_s), 9 * C_OUT * 16, 128);
         int st = 0;
         uint32_t ph = 0;
         int it = 0;                                    // tiles actually processed
@@ -423,53 +425,60 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
             mbar_wait(tempty_bar(buf), (use & 1) ^ 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 4 * C_OUT);
             const int16_t* win = cls_s[c].win;
-            uint32_t started = 0;
+            uint32_t started = 0;                          // bit s: the accumulator pair of sub-position row s has been written
             for (int kq = 0; kq < NSTEP; ++kq) {
                 mbar_wait(full_bar(st), ph);
                 tc_fence_after();
                 const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * Cfg::STAGE, Cfg::PLANE, SBO_A);
                 if (leader) {
-                    // Window-major issue order: the A window at offset (orow, ocol) from the cell origin feeds every (sub-position
-                    // (s, t), tap (dy, dx)) with s + dy = orow, t + dx = ocol — up to 4 instructions with 4 different accumulators
-                    // and 4 different weight taps.  They are issued back to back with the A operand kept in the collector
-                    // (measured: bare MMA time of the 64->128 layer 3.38 -> 2.49 ms per 1M-pixel scene).
+                    // Window-major issue order with PAIRED sub-positions.  The A window at offset (orow, ocol) from the cell origin
+                    // feeds every (sub-position (s, t), tap (dy, dx)) with s + dy = orow, t + dx = ocol.  For ocol in {0, 1} both
+                    // column sub-positions take part, with the horizontally adjacent taps dx = ocol - 1 (t = 1) and dx = ocol
+                    // (t = 0): ONE instruction with N = 2 * C_out whose B operand spans the two tap blocks and whose accumulator
+                    // spans the column blocks of (s, 1) and (s, 0) — TMEM block of (s, t) = 2 s + (1 - t).  Twice the math per A
+                    // fetch and per instruction issue (an M128 x N128 x K16 instruction is bound by its shared-memory operand
+                    // reads, ~94 clk against a 64-clk math floor; at N = 256 the math takes 128 clk and hides them).  ocol = -1 / 2
+                    // feed one column sub-position each (N = C_out).  Within a row offset the pairs are issued first, so that the
+                    // first write of a tile into both halves of a pair is the same (overwriting) instruction.  Instructions that
+                    // share an A window are issued back to back with A kept in the collector (UTCHMMA ...A_KEEP / A_REUSE).
 #pragma unroll
-                    for (int wi = 0; wi < 16; ++wi) {
-                        const int o = win[wi];
-                        if (o >= 0) {
-                            constexpr int kLo[4] = {0, 0, 0, 1}, kHi[4] = {0, 1, 1, 1};      // sub-position range of offsets -1, 0, 1, 2
-                            const int orow = wi / 4 - 1, ocol = wi % 4 - 1;
-                            const int nu = (kHi[wi / 4] - kLo[wi / 4] + 1) * (kHi[wi % 4] - kLo[wi % 4] + 1);
+                    for (int orow = -1; orow <= 2; ++orow) {
+                        const int s_lo = orow <= 0 ? 0 : (orow == 2 ? 1 : 0), s_hi = orow == -1 ? 0 : 1;      // sub-position rows with a tap dy = orow - s
+                        const int nu = (orow == -1 || orow == 2) ? 1 : 2;
 #pragma unroll
-                            for (int j = 0; j < KQ / 2; ++j) {
-                                const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)o + (uint64_t)(((uint32_t)(2 * j) * Cfg::PLANE) >> 4);
-                                int ui = 0;
+                        for (int oi = 0; oi < 4; ++oi) {
+                            constexpr int kOcol[4] = {0, 1, -1, 2};
+                            const int ocol = kOcol[oi];
+                            const int o = win[(orow + 1) * 4 + ocol + 1];
+                            if (o >= 0) {
 #pragma unroll
-                                for (int s2 = 0; s2 < 2; ++s2)
+                                for (int j = 0; j < KQ / 2; ++j) {
+                                    const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)o + (uint64_t)(((uint32_t)(2 * j) * Cfg::PLANE) >> 4);
+                                    int ui = 0;
 #pragma unroll
-                                    for (int t2 = 0; t2 < 2; ++t2) {
-                                        const int dy = orow - s2, dx = ocol - t2;        // tap offsets in {-1, 0, 1} or no such tap
-                                        if (dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1) {
-                                            const int tap = (dy + 1) * 3 + dx + 1, sub = s2 * 2 + t2;
-                                            const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((tap * KCH + kq * KQ + 2 * j) * C_OUT * 16) >> 4);
-                                            const uint32_t accf = ((started >> sub) & 1u) | (uint32_t)j;
-                                            const uint32_t dt = d_tmem + (uint32_t)(sub * C_OUT);
-                                            if (nu == 1) umma_bf16_a<0>(dt, ad, bd, idesc, accf);
-                                            else if (ui == 0) umma_bf16_a<1>(dt, ad, bd, idesc, accf);
-                                            else if (ui == nu - 1) umma_bf16_a<3>(dt, ad, bd, idesc, accf);
-                                            else umma_bf16_a<2>(dt, ad, bd, idesc, accf);
+                                    for (int s2 = 0; s2 < 2; ++s2) {
+                                        if (s2 >= s_lo && s2 <= s_hi && orow - s2 >= -1 && orow - s2 <= 1) {
+                                            const int dy = orow - s2;
+                                            const bool pair = ocol == 0 || ocol == 1;
+                                            const int t2 = ocol == -1 ? 0 : 1;                               // single: the one column sub-position
+                                            const int tap = pair ? (dy + 1) * 3 + ocol : (dy + 1) * 3 + (ocol - t2) + 1;
+                                            const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(((kq * KQ + 2 * j) * 9 + tap) * C_OUT * 16) >> 4);
+                                            const uint32_t dt = d_tmem + (uint32_t)((pair ? 2 * s2 : 2 * s2 + (1 - t2)) * C_OUT);
+                                            const uint32_t accf = pair ? (((started >> s2) & 1u) | (uint32_t)j) : 1u;
+                                            const uint32_t id = pair ? idesc2 : idesc1;
+                                            if (nu == 1) umma_bf16_a<0>(dt, ad, bd, id, accf);
+                                            else if (ui == 0) umma_bf16_a<1>(dt, ad, bd, id, accf);
+                                            else umma_bf16_a<3>(dt, ad, bd, id, accf);
                                             ++ui;
                                         }
                                     }
-                            }
-                            // every sub-position this window feeds has now been started
-#pragma unroll
-                            for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
-                                for (int t2 = 0; t2 < 2; ++t2) {
-                                    const int dy = orow - s2, dx = ocol - t2;
-                                    if (dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1) started |= 1u << (s2 * 2 + t2);
                                 }
+                                if (ocol == 0 || ocol == 1) {
+#pragma unroll
+                                    for (int s2 = 0; s2 < 2; ++s2)
+                                        if (s2 >= s_lo && s2 <= s_hi) started |= 1u << s2;
+                                }
+                            }
                         }
                     }
                     umma_commit(empty_bar(st));

@@ -16,7 +16,8 @@ constexpr int kHeadWarps = 8;
 
 struct ConvLayer {
     LayerGeom g;
-    __nv_bfloat16* w = nullptr;   // packed [tap][cin/8][cout][8]
+    __nv_bfloat16* w = nullptr;   // packed [tap][cin/8][cout][8]; fp16 bit patterns when w_f16 (tc::w16)
+    bool w_f16 = false;
     float* scale = nullptr;
     float* shift = nullptr;
     CUtensorMap map;              // over the workspace input buffer

@@ -8,17 +8,15 @@
 // (4 p^2 + 16 p^2 floats per pixel); the source windows overlap and stay L2-resident, so outputs
 // are written with streaming stores.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "net_geom.cuh"
 
-// K1 extras of a scene: the MS raster once more in PLANAR layout [4][Hp][pitch] (a patch's CHW tensor is then one 3-D TMA box)
-// and the tensor maps of the three rasters.
+// K1 extras of a scene: the TMA tensor maps of the PAN-grid rasters.
 struct dmf_scene_k1 {
-    float* ms_pl = nullptr;
-    int pitch = 0;                                   // floats per planar MS row (multiple of 4)
-    alignas(64) CUtensorMap tm_ms, tm_pan, tm_mspan;
-    int p_maps = 0, rc = 0;                          // patch size / PAN rows per chunk the maps were encoded for (0 = none: p % 4 != 0)
+    alignas(64) CUtensorMap tm_pan, tm_mspan;
+    int p_maps = 0, rc = 0;                          // patch size / PAN rows per chunk the maps were encoded for (0 = none: gather_scalar_kernel)
     bool has_mspan_map = false;
 };
 
@@ -203,7 +201,8 @@ __global__ void __launch_bounds__(256) ihs_scene_kernel(const TM* __restrict__ m
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const char2 o = __ldg(reinterpret_cast<const char2*>(offs) + i * HW + px);
-                up[i] = (o.x == rr && o.y == cc) ? Norm<TM>::q(ms[px * 4 + i], mlo, mhi) : 0.0;
+                up[i] = 0.0;
+                if (o.x == rr && o.y == cc) up[i] = Norm<TM>::q(ms[px * 4 + i], mlo, mhi);      // 1 element in 16: a branch, not a select (FP64 divide)
             }
             const double pv = Norm<TP>::q(pan[(int64_t)r * (4 * W) + c], plo, phi);
             const double I = run_mean4(up[0], up[1], up[2], up[3]);
@@ -281,32 +280,36 @@ static int scene_alloc(dmf_scene* s, int H, int W, int p) {
 // ---------------------------------------------------------------- K1 gather
 // dataset_dual / dataset_tri + default_collate + .to(device) (train/dataset.py:168-185, 259-279; solver/mainsolver.py:50) is pure
 // data movement: per pixel a p x p x 4 MS window (HWC -> CHW) and one or two 4p x 4p windows of the PAN grid, 20 KB (28 KB tri) of
-// fp32 at p = 16, bounded by the HBM WRITE of the batch (the windows overlap and are served by L2).  No register ever touches
-// the data: a window is one TMA tensor load (cp.async.bulk.tensor: 2-D box of the pitched PAN / MSPAN raster, 3-D box
-// {p, p, 4 bands} of the planar MS copy) into shared memory, and because the box lands densely packed it IS the output tensor's
-// layout, so it leaves again as one bulk copy shared -> global (cp.async.bulk, L2 evict-first so that the batch does not push the
-// scene out of L2).  Unit of work = (patch, part): part 0 = the MS window, then the PAN window in chunks of <= 16 KB, then the
-// MSPAN chunks.  One warp = one shared-memory stage driven by its elected lane: wait until the stage's previous store has read
-// it, arm the mbarrier, load, wait, store.  CTAs are persistent (2 per SM, ~96 KB of stages each).
-constexpr int kK1StageMax = 16384;
+// fp32 at p = 16, bounded by the HBM WRITE of the batch (the windows overlap and are served by L2).
+//   * PAN / MSPAN windows (80 - 89 % of the bytes): no register ever touches the data.  A window (or a <= 16 KB chunk of its rows)
+//     is one TMA tensor load (cp.async.bulk.tensor, 2-D box of the pitched raster; the window starts at column 4y, so the box is
+//     16-byte aligned as TMA requires) into shared memory; the box lands densely packed = the output tensor's layout, and leaves
+//     again as one bulk copy shared -> global (cp.async.bulk, L2 evict-first so that the batch does not push the scene out of L2).
+//     One warp = one shared-memory stage driven by its elected lane: wait until the stage's previous store has read it, arm the
+//     mbarrier, load, wait, store.
+//   * MS windows start at an arbitrary column y (4-byte granularity: a TMA box cannot start there — measured: illegal instruction)
+//     and need the HWC -> CHW transposition: kMsWarps ordinary warps per CTA, a lane takes 4 neighbouring pixels (4 x 16-byte
+//     loads) and writes one float4 per band plane (the 32 lanes of a store cover 512 contiguous bytes), all loads of a patch in
+//     flight before its first store.  They also write the targets.
+// CTAs are persistent (2 per SM, ~96 KB of stages each).
+constexpr int kK1StageMax = 16384, kMsWarps = 4;
 
 struct GatherParams {
     const int64_t* idx;
     int64_t N, HW;
-    int W, p, rc, n_chunks, upp;          // PAN rows per chunk, chunks per window, units per patch
+    int W, p, rc, n_chunks, upp;          // PAN rows per chunk, chunks per window, TMA units per patch
+    int n_tma_warps;
     uint32_t stage_bytes;
+    int dbg;                              // diagnostics (DMF_K1_DBG): 1 = no loads, 2 = no stores, 4 = stores without the L2 hint, 8 = MS only, 16 = PAN only
+    const float4* ms;                     // scene MS [Hp][Wp] float4 (HWC)
+    int Wp;
     float *ms_out, *pan_out, *mspan_out, *target_out;
     const uint8_t* label;
 };
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_store_evict_first(void* dst, uint32_t src, uint32_t bytes, uint64_t policy) {
@@ -315,58 +318,96 @@ __device__ __forceinline__ void bulk_store_evict_first(void* dst, uint32_t src, 
                  : "memory");
 }
 
-__global__ void __launch_bounds__(768) gather_tma_kernel(const __grid_constant__ CUtensorMap tm_ms, const __grid_constant__ CUtensorMap tm_pan,
-                                                         const __grid_constant__ CUtensorMap tm_mspan, const GatherParams P) {
+__global__ void __launch_bounds__(896) gather_tma_kernel(const __grid_constant__ CUtensorMap tm_pan, const __grid_constant__ CUtensorMap tm_mspan,
+                                                         const GatherParams P) {
     extern __shared__ __align__(1024) uint8_t k1_smem[];
     __shared__ uint64_t bars[32];
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (!tc::elect_one()) return;                                            // one driving lane per warp / stage
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = P.p, P4 = 4 * p;
+    if (warp >= P.n_tma_warps) {
+        // ------------------------------------------------ MS windows + targets: ordinary loads / stores
+        if (P.dbg & 16) return;
+        const int items = p * p / 4, pq = p / 4;                 // work items (4 pixels of one row) per patch
+        const int ppw = items >= 32 ? 1 : 32 / items;            // patches a warp handles at once (p < 12)
+        const int sub = items >= 32 ? 0 : lane / items;
+        const int mw = (int)blockIdx.x * kMsWarps + (warp - P.n_tma_warps);
+        const int64_t stride = (int64_t)gridDim.x * kMsWarps * ppw;
+        for (int64_t n0 = (int64_t)mw * ppw; n0 < P.N; n0 += stride) {
+            const int64_t n = n0 + sub;
+            if (n >= P.N || sub >= ppw) continue;
+            int64_t k = __ldg(P.idx + n);
+            k = k < 0 ? 0 : (k >= P.HW ? P.HW - 1 : k);         // never address outside the scene
+            const int x = (int)((uint32_t)k / (uint32_t)P.W), y = (int)((uint32_t)k - (uint32_t)x * (uint32_t)P.W);
+            float* mo = P.ms_out + n * (int64_t)(4 * p * p);
+            const int first = items >= 32 ? lane : lane - sub * items, step = items >= 32 ? 32 : items;
+            for (int i0 = first; i0 < items; i0 += 2 * step) {
+                float4 a[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = i0 + h * step;
+                    if (i < items) {
+                        const int r = i / pq, c = (i - r * pq) * 4;
+                        const float4* src = P.ms + (int64_t)(x + r) * P.Wp + y + c;
+                        a[h][0] = __ldg(src); a[h][1] = __ldg(src + 1); a[h][2] = __ldg(src + 2); a[h][3] = __ldg(src + 3);
+                    }
+                }
+                if (P.dbg & 2) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = i0 + h * step;
+                    if (i < items) {
+                        const int r = i / pq, c = (i - r * pq) * 4;
+                        float* o = mo + r * p + c;
+                        __stcs(reinterpret_cast<float4*>(o), make_float4(a[h][0].x, a[h][1].x, a[h][2].x, a[h][3].x));
+                        __stcs(reinterpret_cast<float4*>(o + p * p), make_float4(a[h][0].y, a[h][1].y, a[h][2].y, a[h][3].y));
+                        __stcs(reinterpret_cast<float4*>(o + 2 * p * p), make_float4(a[h][0].z, a[h][1].z, a[h][2].z, a[h][3].z));
+                        __stcs(reinterpret_cast<float4*>(o + 3 * p * p), make_float4(a[h][0].w, a[h][1].w, a[h][2].w, a[h][3].w));
+                    }
+                }
+            }
+            if (P.target_out && first == 0) P.target_out[n] = (float)__ldg(P.label + k);
+        }
+        return;
+    }
+    // ---------------------------------------------------- PAN / MSPAN windows: TMA load -> bulk store, one lane per warp
+    if ((P.dbg & 8) || !tc::elect_one()) return;
     const uint32_t bar = tc::smem_u32(&bars[warp]);
     const uint32_t stage = tc::smem_u32(k1_smem) + (uint32_t)warp * P.stage_bytes;
     tc::mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    uint64_t policy;
+    uint64_t policy, keep;                  // the batch streams through L2 (evict-first); the scene windows should stay (evict-last)
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    if (warp == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_ms) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_pan) : "memory");
-    }
-    const int64_t total = P.N * P.upp, stride = (int64_t)gridDim.x * nwarps;
-    const int p = P.p, P4 = 4 * p;
-    const uint32_t ms_bytes = 16u * p * p, chunk_bytes = (uint32_t)P.rc * P4 * 4u;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    if (warp == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_pan) : "memory");
+    const int64_t total = P.N * P.upp, stride = (int64_t)gridDim.x * P.n_tma_warps;
+    const uint32_t bytes = (uint32_t)P.rc * P4 * 4u;
     uint32_t phase = 0;
-    int64_t g = (int64_t)blockIdx.x * nwarps + warp;
+    int64_t g = (int64_t)blockIdx.x * P.n_tma_warps + warp;
     int64_t k_next = g < total ? __ldg(P.idx + g / P.upp) : 0;
     for (; g < total; g += stride) {
         const int64_t n = g / P.upp;
-        const int u = (int)(g - n * P.upp);
+        const int c = (int)(g - n * P.upp);
         int64_t k = k_next;
         if (g + stride < total) k_next = __ldg(P.idx + (g + stride) / P.upp);      // in flight while this unit moves
-        k = k < 0 ? 0 : (k >= P.HW ? P.HW - 1 : k);                                // never address outside the scene
+        k = k < 0 ? 0 : (k >= P.HW ? P.HW - 1 : k);
         const int x = (int)((uint32_t)k / (uint32_t)P.W), y = (int)((uint32_t)k - (uint32_t)x * (uint32_t)P.W);
+        const bool third = c >= P.n_chunks;
+        const int ck = third ? c - P.n_chunks : c;
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");             // the stage's previous store has read it
-        void* dst;
-        uint32_t bytes;
-        if (u == 0) {
-            bytes = ms_bytes;
+        if (P.dbg & 1) tc::mbar_arrive(bar);
+        else {
             tc::mbar_expect_tx(bar, bytes);
-            tma_load_3d(stage, &tm_ms, bar, y, x, 0);
-            dst = P.ms_out + n * (int64_t)(4 * p * p);
-            if (P.target_out) P.target_out[n] = (float)__ldg(P.label + k);
-        } else {
-            const int c = u - 1;
-            const bool third = c >= P.n_chunks;
-            const int ck = third ? c - P.n_chunks : c;
-            bytes = chunk_bytes;
-            tc::mbar_expect_tx(bar, bytes);
-            tma_load_2d(stage, third ? &tm_mspan : &tm_pan, bar, 4 * y, 4 * x + ck * P.rc);
-            dst = (third ? P.mspan_out : P.pan_out) + n * (int64_t)(P4 * P4) + (int64_t)ck * P.rc * P4;
+            tma_load_2d(stage, third ? &tm_mspan : &tm_pan, bar, 4 * y, 4 * x + ck * P.rc, keep);
         }
+        float* dst = (third ? P.mspan_out : P.pan_out) + n * (int64_t)(P4 * P4) + (int64_t)ck * P.rc * P4;
         tc::mbar_wait(bar, phase);
         phase ^= 1;
-        bulk_store_evict_first(dst, stage, bytes, policy);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (!(P.dbg & 2)) {
+            if (P.dbg & 4) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"((uint64_t)dst), "r"(stage), "r"(bytes) : "memory");
+            else bulk_store_evict_first(dst, stage, bytes, policy);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -395,17 +436,6 @@ __global__ void __launch_bounds__(256) gather_scalar_kernel(dmf_scene s, const i
     if (threadIdx.x == 0 && target_out) target_out[n] = (float)s.label[k];
 }
 
-// MS [Hp][Wp] float4 (HWC) -> planar [4][Hp][pitch]
-__global__ void __launch_bounds__(256) ms_planar_kernel(const float4* __restrict__ ms, int Hp, int Wp, int pitch, float* __restrict__ out) {
-    const int64_t total = (int64_t)Hp * Wp, plane = (int64_t)Hp * pitch;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / Wp, c = i - r * Wp;
-        const float4 v = __ldg(ms + i);
-        float* o = out + r * pitch + c;
-        o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
-    }
-}
-
 static int encode_f32_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DMF_ERR_CUDA; }
@@ -416,35 +446,18 @@ static int encode_f32_map(CUtensorMap* m, const void* base, int rank, const cuui
     return DMF_OK;
 }
 
-// (re)build the planar MS copy and the tensor maps after the rasters changed
-static int scene_k1_refresh(dmf_scene* s, cudaStream_t st, bool ms_changed) {
+// (re)build the tensor maps of the PAN-grid rasters (their device buffers never move once allocated)
+static int scene_k1_refresh(dmf_scene* s) {
     if (!s->k1) s->k1 = new dmf_scene_k1();
     dmf_scene_k1* k = s->k1;
     const int p = s->p;
-    if (p % 4 != 0 || p > 64) { k->p_maps = 0; return DMF_OK; }   // TMA boxes need 16-byte rows of <= 256 elements: gather_scalar_kernel
-    if (!k->ms_pl) {
-        k->pitch = (s->Wp + 3) & ~3;
-        DMF_CUDA(cudaMalloc(&k->ms_pl, sizeof(float) * 4 * (size_t)s->Hp * k->pitch));
-        ms_changed = true;
-    }
-    if (ms_changed) {
-        const int64_t total = (int64_t)s->Hp * s->Wp;
-        ms_planar_kernel<<<(int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16), 256, 0, st>>>(
-            reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, k->pitch, k->ms_pl);
-        DMF_LAUNCHED();
-    }
+    if (p % 4 != 0 || p > 64) { k->p_maps = 0; return DMF_OK; }   // TMA boxes: rows of <= 256 elements, MS float4 groups: gather_scalar_kernel
+    const int P4 = 4 * p;
+    const cuuint64_t dims[2] = {(cuuint64_t)s->W4p, (cuuint64_t)s->H4p};
+    const cuuint64_t strides[1] = {(cuuint64_t)s->pan_pitch * 4};
     if (k->p_maps != p) {
-        const int P4 = 4 * p;
         k->rc = std::min(P4, kK1StageMax / (P4 * 4));
         while (P4 % k->rc) --k->rc;                                  // chunks tile the window
-        {
-            const cuuint64_t dims[3] = {(cuuint64_t)s->Wp, (cuuint64_t)s->Hp, 4};
-            const cuuint64_t strides[2] = {(cuuint64_t)k->pitch * 4, (cuuint64_t)k->pitch * 4 * s->Hp};
-            const cuuint32_t box[3] = {(cuuint32_t)p, (cuuint32_t)p, 4};
-            DMF_TRY(encode_f32_map(&k->tm_ms, k->ms_pl, 3, dims, strides, box));
-        }
-        const cuuint64_t dims[2] = {(cuuint64_t)s->W4p, (cuuint64_t)s->H4p};
-        const cuuint64_t strides[1] = {(cuuint64_t)s->pan_pitch * 4};
         const cuuint32_t box[2] = {(cuuint32_t)P4, (cuuint32_t)k->rc};
         DMF_TRY(encode_f32_map(&k->tm_pan, s->pan, 2, dims, strides, box));
         k->tm_mspan = k->tm_pan;
@@ -452,9 +465,6 @@ static int scene_k1_refresh(dmf_scene* s, cudaStream_t st, bool ms_changed) {
         k->p_maps = p;
     }
     if (s->mspan && !k->has_mspan_map) {
-        const int P4 = 4 * p;
-        const cuuint64_t dims[2] = {(cuuint64_t)s->W4p, (cuuint64_t)s->H4p};
-        const cuuint64_t strides[1] = {(cuuint64_t)s->pan_pitch * 4};
         const cuuint32_t box[2] = {(cuuint32_t)P4, (cuuint32_t)k->rc};
         DMF_TRY(encode_f32_map(&k->tm_mspan, s->mspan, 2, dims, strides, box));
         k->has_mspan_map = true;
@@ -495,7 +505,7 @@ static int scene_fill_raw(dmf_scene* s, const void* ms, int ms_dtype, const void
     if (rc == DMF_OK) rc = upload(pan, dtype_size(pan_dtype) * 16 * (size_t)H * W, on_device, st, &t2, &dpan);
     if (rc == DMF_OK) rc = normalize_pad_any(dms, ms_dtype, H, W, 4, p, s->ms, DMF_F32, (int64_t)s->Wp * 4, st, ms_lohi);
     if (rc == DMF_OK) rc = normalize_pad_any(dpan, pan_dtype, 4 * H, 4 * W, 1, 4 * p, s->pan, DMF_F32, s->pan_pitch, st, pan_lohi);
-    if (rc == DMF_OK) rc = scene_k1_refresh(s, st, true);
+    if (rc == DMF_OK) rc = scene_k1_refresh(s);
     if (t1) cudaFreeAsync(t1, st);
     if (t2) cudaFreeAsync(t2, st);
     return rc;
@@ -562,7 +572,7 @@ int dmf_scene_create_padded(dmf_scene** out, const void* ms_pad, const void* pan
     int rc = scene_alloc(s, H, W, p);
     if (rc == DMF_OK) rc = copy_padded(ms_pad, dtype, s->Hp, (int64_t)s->Wp * 4, (int64_t)s->Wp * 4, s->ms, on_device, st);
     if (rc == DMF_OK) rc = copy_padded(pan_pad, dtype, s->H4p, s->W4p, s->pan_pitch, s->pan, on_device, st);
-    if (rc == DMF_OK) rc = scene_k1_refresh(s, st, true);
+    if (rc == DMF_OK) rc = scene_k1_refresh(s);
     if (rc != DMF_OK) { dmf_scene_destroy(s); return rc; }
     *out = s;
     return DMF_OK;
@@ -572,7 +582,7 @@ int dmf_scene_set_mspan(dmf_scene* s, const void* mspan_pad, int dtype, int on_d
     DMF_REQUIRE(s && mspan_pad, "scene_set_mspan: null");
     if (!s->mspan) DMF_CUDA(cudaMalloc(&s->mspan, sizeof(float) * (size_t)s->H4p * s->pan_pitch));
     DMF_TRY(copy_padded(mspan_pad, dtype, s->H4p, s->W4p, s->pan_pitch, s->mspan, on_device, (cudaStream_t)stream));
-    return scene_k1_refresh(s, (cudaStream_t)stream, false);
+    return scene_k1_refresh(s);
 }
 
 int dmf_scene_set_mspan_ihs(dmf_scene* s, const void* ms, int ms_dtype, const void* pan, int pan_dtype, int on_device,
@@ -611,7 +621,7 @@ int dmf_scene_set_mspan_ihs(dmf_scene* s, const void* ms, int ms_dtype, const vo
     if (lohi) cudaFreeAsync(lohi, st);
     if (t1) cudaFreeAsync(t1, st);
     if (t2) cudaFreeAsync(t2, st);
-    if (rc == DMF_OK) rc = scene_k1_refresh(s, st, false);
+    if (rc == DMF_OK) rc = scene_k1_refresh(s);
     return rc;
 }
 
@@ -629,7 +639,7 @@ int dmf_scene_destroy(dmf_scene* s) {
     cudaFree(s->pan);
     cudaFree(s->mspan);
     cudaFree(s->label);
-    if (s->k1) { cudaFree(s->k1->ms_pl); delete s->k1; }
+    delete s->k1;
     delete s;
     return DMF_OK;
 }
@@ -667,17 +677,21 @@ int dmf_gather(const dmf_scene* s, const int64_t* flat_idx_dev, int64_t N, float
     DMF_REQUIRE(N < (int64_t)1 << 31, "gather: N too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     const dmf_scene_k1* k = s->k1;
-    if (k && k->p_maps == s->p) {
+    static const bool force_scalar = getenv("DMF_K1_SCALAR") != nullptr;        // debugging aid: the generic kernel for every patch size
+    if (k && k->p_maps == s->p && !force_scalar) {
         const int p = s->p, P4 = 4 * p;
         DMF_REQUIRE((int64_t)s->H * s->W < ((int64_t)1 << 31), "gather: scene too large for 32-bit pixel indices");
         DMF_REQUIRE(!mspan_out_dev || k->has_mspan_map, "gather: tri mode needs dmf_scene_set_mspan");
         GatherParams P{};
         P.idx = flat_idx_dev; P.N = N; P.HW = (int64_t)s->H * s->W; P.W = s->W; P.p = p; P.rc = k->rc; P.n_chunks = P4 / k->rc;
-        P.upp = 1 + P.n_chunks * (mspan_out_dev ? 2 : 1);
-        P.stage_bytes = (uint32_t)std::max(16 * p * p, k->rc * P4 * 4);
-        P.stage_bytes = (P.stage_bytes + 1023u) & ~1023u;
+        P.upp = P.n_chunks * (mspan_out_dev ? 2 : 1);
+        P.stage_bytes = ((uint32_t)(k->rc * P4 * 4) + 1023u) & ~1023u;
+        static const int dbg = getenv("DMF_K1_DBG") ? atoi(getenv("DMF_K1_DBG")) : 0;
+        P.dbg = dbg;
+        P.ms = reinterpret_cast<const float4*>(s->ms); P.Wp = s->Wp;
         P.ms_out = ms_out_dev; P.pan_out = pan_out_dev; P.mspan_out = mspan_out_dev; P.target_out = target_out_dev; P.label = s->label;
         const int warps = (int)std::max<uint32_t>(1, std::min<uint32_t>(24, (96u * 1024u) / P.stage_bytes));
+        P.n_tma_warps = warps;
         const size_t smem = (size_t)warps * P.stage_bytes;
         static bool attr_set = false;
         if (!attr_set) {
@@ -686,7 +700,7 @@ int dmf_gather(const dmf_scene* s, const int64_t* flat_idx_dev, int64_t N, float
         }
         const int64_t units = N * P.upp;
         const int grid = (int)std::min<int64_t>((units + warps - 1) / warps, (int64_t)2 * num_sms());
-        gather_tma_kernel<<<grid, warps * 32, smem, st>>>(k->tm_ms, k->tm_pan, k->tm_mspan, P);
+        gather_tma_kernel<<<grid, (warps + kMsWarps) * 32, smem, st>>>(k->tm_pan, k->tm_mspan, P);
     } else {
         gather_scalar_kernel<<<(unsigned)N, 256, 0, st>>>(*s, flat_idx_dev, N, ms_out_dev, pan_out_dev, mspan_out_dev, target_out_dev);
     }

@@ -20,8 +20,18 @@ from .gmfnet_ref import Net
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'fitted_nets.npz')
 
-# workload tag -> (H, W, classes without background, patch size); scene = synthetic_scene_structured(H, W, classes, seed=0, label_seed=1)
+# workload tag -> (H, W, classes without background, patch size)
 WORKLOADS = {'c1': (128, 128, 7, 16), 'c2': (1000, 1000, 12, 16), 'c3': (2001, 2101, 11, 16), 'smoke': (40, 36, 7, 16)}
+# (scene seed, label seed, region size in MS pixels): land-cover regions a few patches wide, so that most patches are not mixtures
+SCENES = {'c1': (0, 1, 32), 'c2': (0, 1, 64), 'c3': (0, 1, 64), 'smoke': (2, 3, 20)}
+
+
+def scene(tag):
+    """(ms uint16 [H,W,4], pan uint16 [4H,4W], label uint8 [H,W]) of a workload: the structured synthetic scene."""
+    from . import dmf_oracle as orc
+    H, W, ncls, _ = WORKLOADS[tag]
+    seed, label_seed, cell = SCENES[tag]
+    return orc.synthetic_scene_structured(H, W, ncls, seed=seed, label_seed=label_seed, cell=cell)
 
 
 def cfg_for(tag):

@@ -19,8 +19,6 @@ sys.path.insert(0, REPO)
 from oracle import dmf_oracle as orc            # noqa: E402
 from oracle import fitted_net as fn             # noqa: E402
 
-SCENE_SEEDS = {'c1': (0, 1), 'c2': (0, 1), 'c3': (0, 1), 'smoke': (2, 3)}
-
 
 def patches(MS, PAN, W, idx, p):
     a, b = orc.gather_dual(MS, PAN, idx // W, idx % W, p)
@@ -30,7 +28,7 @@ def patches(MS, PAN, W, idx, p):
 def fit(tag):
     H, W, ncls, p = fn.WORKLOADS[tag]
     C = ncls + 1
-    ms, pan, label = orc.synthetic_scene_structured(H, W, ncls, *SCENE_SEEDS[tag])
+    ms, pan, label = fn.scene(tag)
     MS, PAN = orc.data_padding(ms, p), orc.data_padding(pan, p)
     lab = label.reshape(-1)
     labelled = np.flatnonzero(lab != 0)
@@ -62,7 +60,7 @@ def fit(tag):
     ytr, yte = torch.from_numpy(lab[tr].astype(np.int64)), torch.from_numpy(lab[te].astype(np.int64))
     torch.manual_seed(5)
     head = torch.nn.Sequential(torch.nn.Linear(128, 64), torch.nn.ReLU(), torch.nn.Linear(64, C))
-    opt = torch.optim.Adam(head.parameters(), lr=3e-3)
+    opt = torch.optim.AdamW(head.parameters(), lr=3e-3, weight_decay=1e-2)        # an ordinarily regularised head, not a razor-sharp one
     for _ in range(1500):
         opt.zero_grad()
         loss = torch.nn.functional.cross_entropy(head(Ftr), ytr)

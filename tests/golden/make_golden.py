@@ -207,7 +207,7 @@ def golden_solver_c1_fitted():
     from oracle import fitted_net
     H = W = 128
     p, ncls = 16, 7
-    ms, pan, label = orc.synthetic_scene_structured(H, W, ncls, seed=0, label_seed=1)
+    ms, pan, label = fitted_net.scene('c1')
     tmp = tempfile.mkdtemp() + '/'
     np.save(tmp + 'label.npy', label)
     cfg = small_cfg(H, W, p, ncls, city='c1')

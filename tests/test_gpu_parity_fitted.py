@@ -10,8 +10,13 @@ convolutions, calibrated BatchNorm, head fitted on the structured synthetic scen
   * C2 (1000 x 1000) and C3 (2001 x 2101): >= 20 000 sampled pixels against the fp32 oracle Net evaluated by torch on the GPU
     with TF32 off, on patches cut by the (bit-exact) K1 gather.
 
-Asserted: argmax agreement >= 0.999; every disagreeing pixel has an fp32 top-2 margin below the logit tolerance
-(LOGIT_ATOL + LOGIT_RTOL * |logit|, the bf16-operand / fp32-accumulate bound of test_gpu_net.py); the confusion matrix equals
+Logit tolerance: bf16 operands (8-bit mantissa) through five convolution layers with fp32 accumulation leave every pooled
+feature with an error of a few 1e-3 of the FEATURE scale, and a logit is a sum over those features: its error scales with the
+magnitude of the pixel's logit vector, not with the individual logit (a logit near 0 next to one of 35 is off by the same
+~0.3).  So |dlogit| <= LOGIT_ATOL + LOGIT_RTOL * max_c |logit[c]| per pixel (the same constants as test_gpu_net.py, where the
+default-initialised net has logits of one magnitude).  Measured on the fitted nets: max |dlogit| 0.5 at logits up to 35.
+
+Asserted: argmax agreement >= 0.999; every disagreeing pixel has an fp32 top-2 margin below twice that tolerance; the confusion matrix equals
 oracle.confusion(pred_map, label) bit for bit, and the reference run's matrix / OA / AA / Kappa when the predictions agree
 everywhere.
 """
@@ -40,6 +45,11 @@ def product_net(tag, **b200):
     return net.to(DEV).eval()
 
 
+def logit_tol(want, extra_rtol=0.0):
+    """per-pixel tolerance, broadcast over the classes"""
+    return (LOGIT_ATOL + (LOGIT_RTOL + extra_rtol) * np.abs(want).max(axis=1))[:, None]
+
+
 def check_disagreements(pm_flat, want_logits, what):
     """pm_flat: predictions of the product path, want_logits: fp32 logits of the same pixels.  Returns the agreement."""
     want = want_logits.argmax(1)
@@ -47,7 +57,7 @@ def check_disagreements(pm_flat, want_logits, what):
     srt = np.sort(want_logits, axis=1)
     margin = srt[:, -1] - srt[:, -2]
     bad = np.flatnonzero(pm_flat != want)
-    tol = LOGIT_ATOL + LOGIT_RTOL * np.abs(want_logits).max(axis=1)
+    tol = logit_tol(want_logits)[:, 0]
     assert np.all(margin[bad] <= 2 * tol[bad]), '%s: a pixel with a clear fp32 margin (%.4g) was classified differently' % (
         what, float(margin[bad].max()))
     assert agree >= 0.999, '%s: argmax agreement %.5f < 0.999 (%d of %d differ)' % (what, agree, bad.size, want.size)
@@ -59,7 +69,7 @@ def test_c1_fitted_whole_scene_matches_reference_run(golden):
     g = golden('solver_c1_fitted')
     H = W = 128
     C = 8
-    ms, pan, label = orc.synthetic_scene_structured(H, W, 7, seed=0, label_seed=1)
+    ms, pan, label = fitted_net.scene('c1')
     assert len(np.unique(g['label_map'])) >= 5 and g['aa_oa_k'][2] > 0.1          # the reference run itself is non-degenerate
     net = product_net('c1')
     scene = dmf.Scene.from_raw(ms, pan, 16, DEV)
@@ -72,14 +82,15 @@ def test_c1_fitted_whole_scene_matches_reference_run(golden):
         pm, M, lg = pred_map.cpu().numpy(), cm.cpu().numpy().astype(np.float64), logits.cpu().numpy()
         what = 'C1 fitted, %s path' % ('dense' if dense else 'per-patch')
         # logits: exact fp32 goldens for the first 512 pixels, a float16 copy for the rest (2^-11 relative on top of the tolerance)
-        err = np.abs(lg[:512] - g['logits_first512'])
-        assert np.all(err <= LOGIT_ATOL + LOGIT_RTOL * np.abs(g['logits_first512'])), '%s: logits off by %g' % (what, err.max())
-        err = np.abs(lg - want_logits)
-        assert np.all(err <= LOGIT_ATOL + (LOGIT_RTOL + 2.0 ** -10) * np.abs(want_logits)), '%s: logits off by %g' % (what, err.max())
         agree = float((pm == g['label_map']).mean())
         bad = np.flatnonzero(pm.reshape(-1) != g['label_map'].reshape(-1))
+        err = np.abs(lg - want_logits)
+        print('%s: max |dlogit| %.4f at max |logit| %.2f; agreement %.5f (%d px differ)' % (what, err.max(), np.abs(want_logits).max(), agree, bad.size))
+        err512 = np.abs(lg[:512] - g['logits_first512'])
+        assert np.all(err512 <= logit_tol(g['logits_first512'])), '%s: logits off by %g' % (what, err512.max())
+        assert np.all(err <= logit_tol(want_logits, 2.0 ** -10)), '%s: logits off by %g' % (what, err.max())
         assert agree >= 0.999, '%s: argmax agreement with the reference run %.5f' % (what, agree)
-        assert np.all(g['margin_top2'][bad] <= 2 * (LOGIT_ATOL + LOGIT_RTOL * np.abs(want_logits[bad]).max(axis=1))) if bad.size else True
+        assert np.all(g['margin_top2'][bad] <= 2 * logit_tol(want_logits[bad])[:, 0]) if bad.size else True
         assert np.array_equal(pm.reshape(-1), lg.argmax(1)), what + ': label map is not the first-max argmax of the logits'
         assert np.array_equal(M, orc.confusion(pm.reshape(-1), label.reshape(-1), C)), what + ': confusion matrix'
         if bad.size == 0:
@@ -101,7 +112,7 @@ def test_full_scale_fitted_sampled_pixels_vs_fp32_oracle(tag):
     import dmf
     H, W, ncls, p = fitted_net.WORKLOADS[tag]
     C = ncls + 1
-    ms, pan, label = orc.synthetic_scene_structured(H, W, ncls, seed=0, label_seed=1)
+    ms, pan, label = fitted_net.scene(tag)
     net = product_net(tag)
     scene = dmf.Scene.from_raw(ms, pan, p, DEV)
     scene.set_labels(label)
@@ -129,7 +140,7 @@ def test_full_scale_fitted_sampled_pixels_vs_fp32_oracle(tag):
     h = net.native()
     logits, _ = h.forward_scene(scene, flat_idx=torch.from_numpy(idx), want_logits=True)
     err = np.abs(logits.cpu().numpy() - want)
-    assert np.all(err <= LOGIT_ATOL + LOGIT_RTOL * np.abs(want)), '%s: per-patch logits off by %g' % (tag, err.max())
+    assert np.all(err <= logit_tol(want)), '%s: per-patch logits off by %g' % (tag, err.max())
     agree, margin = check_disagreements(pm[idx], want, tag.upper() + ' fitted, dense path')
     hist, edges = np.histogram(margin, bins=[0, 1e-3, 3e-3, 1e-2, 3e-2, 0.1, 0.3, 1, 3, 10, 1e9])
     rec = {'workload': tag, 'sampled_px': int(n), 'argmax_agreement': agree, 'classes_predicted': int(len(np.unique(pm))),

@@ -123,7 +123,7 @@ def test_fitted_net_reproduces_the_reference_run(golden):
     from oracle import fitted_net
     g = golden('solver_c1_fitted')
     H = W = 128
-    ms, pan, label = orc.synthetic_scene_structured(H, W, 7, seed=0, label_seed=1)
+    ms, pan, label = fitted_net.scene('c1')
     MS, PAN = orc.data_padding(ms, 16), orc.data_padding(pan, 16)
     net = fitted_net.fitted_net('c1')
     flat = np.arange(512)

@@ -78,12 +78,15 @@ for p in (8, 16, 32):
     import ctypes as C
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
     ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
-    for tri in (False, True):
-        fn = lambda: dmf.check(dmf.lib.dmf_gather(sc._h, ptr(idx), B, ptr(o_ms), ptr(o_pan), ptr(o_msp if tri else None), ptr(None), st()))
-        t = timed(fn)
-        nbytes = B * (4 * p * p + 16 * p * p * (2 if tri else 1)) * 4
-        extra = {'frac_of_write_ceiling': round(nbytes / t / 1e6 / write_peak, 3)} if t else {}
-        report('gather_tma_kernel', 'p=%d batch %d %s' % (p, B, 'tri' if tri else 'dual'), nbytes, t, **extra)
+    seq = torch.arange(300 * W + 17, 300 * W + 17 + B, device=dev)          # loader order of the test / colour loaders: consecutive pixels
+    for order, ii in (('random (RandomSampler batch; the windows are read from a cold L2: compulsory reads on top of the writes)', idx),
+                      ('sequential (test / colour loader order: overlapping windows, reads served by L2)', seq)):
+        for tri in (False, True):
+            fn = lambda: dmf.check(dmf.lib.dmf_gather(sc._h, ptr(ii), B, ptr(o_ms), ptr(o_pan), ptr(o_msp if tri else None), ptr(None), st()))
+            t = timed(fn)
+            nbytes = B * (4 * p * p + 16 * p * p * (2 if tri else 1)) * 4
+            extra = {'frac_of_write_ceiling': round(nbytes / t / 1e6 / write_peak, 3)} if t else {}
+            report('gather_tma_kernel', 'p=%d batch %d %s, %s' % (p, B, 'tri' if tri else 'dual', order), nbytes, t, **extra)
     sc.close()
 
 # K2 at C3 size
