@@ -600,7 +600,7 @@ def main():
                                'classified); secondary.e2e_single_scene_latency_ms is the un-pipelined submit -> result time'})
         emit(({'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-               'dtype': 'bf16', 'data': 'synthetic', 'config': config, 'clocks': clk.summary(),
+               'dtype': 'fp16', 'data': 'synthetic', 'config': config, 'clocks': clk.summary(),
                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_total, 'd2h_bytes_per_step': d2h_total},
                'gpu_launches': int(launches), 'roofline': roofline, 'secondary': secondary, 'cpu_baseline': cpu_baseline, 'details': details}))
     if world > 1:

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restri
 #pragma unroll
             for (int v = 0; v < 9; ++v) {
                 const float y = fmaxf(fmaf(s[v], sc_s[j], sh_s[j]), 0.f);
-                const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y));
+                const uint32_t b = tc::f16_bits(y);
                 if (j & 1) out[v][j >> 1] |= b << 16;
                 else out[v][j >> 1] = b;
             }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256, 2) pan_stem_map_kernel(const float* __res
                             const int r0e = (er == 0 && pr == 0) ? 0 : 1, r1e = (er == 0 && pr == 1) ? 0 : 1;
                             const int c0e = (ec == 0 && pc == 0) ? 0 : 1, c1e = (ec == 0 && pc == 1) ? 0 : 1;
                             const float m = fmaxf(fmaxf(sv[0][0][r0e][c0e], sv[0][1][r0e][c1e]), fmaxf(sv[1][0][r1e][c0e], sv[1][1][r1e][c1e]));
-                            const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(fmaf(m, sc_s[j], sh_s[j]), 0.f)));
+                            const uint32_t bits = tc::f16_bits(fmaxf(fmaf(m, sc_s[j], sh_s[j]), 0.f));
                             if (j & 1) out[er * 2 + ec][j >> 1] |= bits << 16;
                             else out[er * 2 + ec][j >> 1] = bits;
                         }

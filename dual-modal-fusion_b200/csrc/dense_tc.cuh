@@ -18,7 +18,7 @@ namespace tc {
 // ------------------------------------------------------------------------------------------------
 // 1x1 fusion conv + BN + ReLU fused with the inner sums of the global average pool: F never goes to HBM.
 //
-//     S[a][X][y] = sum_{l < P2} F[a, cls(l)][X][y + 2l],    F[a, b] = bf16(relu(bn(W . CAT[a, b])))    (cls = first / interior / last)
+//     S[a][X][y] = sum_{l < P2} F[a, cls(l)][X][y + 2l],    F[a, b] = fp16(relu(bn(W . CAT[a, b])))    (cls = first / interior / last)
 //
 // One tile = one map row X of one row class a, 128 consecutive columns: three accumulators (column classes b = 0, 1, 2) of
 // M128 x N128, K = 256 in 3 x 4 pipeline steps of 8 channel chunks.  128 columns of one row of one chunk plane are 2 KB contiguous
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16_wf16(128, C_OUT);          // weights are fp16 (tc::w16), activations bf16
+        constexpr uint32_t idesc = umma_idesc_f16(128, C_OUT);          // fp16 activations and weights
         const bool leader = elect_one();
         mbar_wait(w_bar, 0);
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float4 sc = sc4[k], sh = sh4[k];
-                            const float a0 = fmaxf(fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x), 0.f);
-                            const float a1 = fmaxf(fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y), 0.f);
-                            const float a2 = fmaxf(fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z), 0.f);
-                            const float a3 = fmaxf(fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w), 0.f);
-                            pk[2 * k] = pack_bf16x2(a0, a1);
-                            pk[2 * k + 1] = pack_bf16x2(a2, a3);
+                            const float a0 = fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x);
+                            const float a1 = fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y);
+                            const float a2 = fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z);
+                            const float a3 = fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w);
+                            pk[2 * k] = pack_f16x2_relu(a0, a1);
+                            pk[2 * k + 1] = pack_f16x2_relu(a2, a3);
                         }
                         uint4* dst = reinterpret_cast<uint4*>(f_s + (uint32_t)(b * 128 + m) * kFrPitch + (uint32_t)c0 * 2);
 #pragma unroll
@@ -220,8 +220,9 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
                         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            s[2 * h] += __uint_as_float(u[h] << 16);             // bf16 -> fp32 is a shift
-                            s[2 * h + 1] += __uint_as_float(u[h] & 0xFFFF0000u);
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[h]));
+                            s[2 * h] += f.x;
+                            s[2 * h + 1] += f.y;
                         }
                     }
                     o[ch * cstride] = make_float4(s[0], s[1], s[2], s[3]);
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         // ------------------------------------------------ MMA issuer
         // The packed weights are [C_in/8][tap][C_out][8]: for one channel chunk the 9 taps are consecutive C_out-row blocks, so a
         // B descriptor that starts at tap t and spans N = 2 * C_out rows covers taps t and t + 1 = (dy, dx) and (dy, dx + 1).
-        constexpr uint32_t idesc1 = umma_idesc_bf16_wf16(128, C_OUT), idesc2 = umma_idesc_bf16_wf16(128, 2 * C_OUT);      // fp16 weights, bf16 activations
+        constexpr uint32_t idesc1 = umma_idesc_f16(128, C_OUT), idesc2 = umma_idesc_f16(128, 2 * C_OUT);      // fp16 activations and weights
         const bool leader = elect_one();
         mbar_wait(w_bar, 0);
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), 9 * C_OUT * 16, 128);
@@ -549,12 +550,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const float4 sc = sc4[k], sh = sh4[k];
-                        const float a0 = fmaxf(fmaf(__uint_as_float(mx[g][4 * k]), sc.x, sh.x), 0.f);
-                        const float a1 = fmaxf(fmaf(__uint_as_float(mx[g][4 * k + 1]), sc.y, sh.y), 0.f);
-                        const float a2 = fmaxf(fmaf(__uint_as_float(mx[g][4 * k + 2]), sc.z, sh.z), 0.f);
-                        const float a3 = fmaxf(fmaf(__uint_as_float(mx[g][4 * k + 3]), sc.w, sh.w), 0.f);
-                        pk[2 * k] = pack_bf16x2(a0, a1);
-                        pk[2 * k + 1] = pack_bf16x2(a2, a3);
+                        const float a0 = fmaf(__uint_as_float(mx[g][4 * k]), sc.x, sh.x);
+                        const float a1 = fmaf(__uint_as_float(mx[g][4 * k + 1]), sc.y, sh.y);
+                        const float a2 = fmaf(__uint_as_float(mx[g][4 * k + 2]), sc.z, sh.z);
+                        const float a3 = fmaf(__uint_as_float(mx[g][4 * k + 3]), sc.w, sh.w);
+                        pk[2 * k] = pack_f16x2_relu(a0, a1);              // ReLU + saturating fp16 rounding: one F2FP
+                        pk[2 * k + 1] = pack_f16x2_relu(a2, a3);
                     }
                     if (valid) {
 #pragma unroll

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(32 * kHeadWarps) head_kernel(const __nv_bfloat
                 const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[k]));
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
                     s[2 * k] += f.x; s[2 * k + 1] += f.y;
                 }
             }
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(32 * kHeadWarps) head_kernel(const __nv_bfloat
 __global__ void direct_conv_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ w,
                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                    __nv_bfloat16* __restrict__ out, int64_t N, int S, int cin, int cout, int taps,
-                                   int pool, int out_chunks, int out_chunk0, int w_f16) {
+                                   int pool, int out_chunks, int out_chunk0) {
     const int So = pool ? S / 2 : S;
     const int64_t total = N * So * So * cout;
     const int kch = cin / 8;
@@ -239,16 +239,15 @@ __global__ void direct_conv_kernel(const __nv_bfloat16* __restrict__ in, const _
                     const int hh = h + dy, ww = wv + dx;
                     if (hh < 0 || hh >= S || ww < 0 || ww >= S) continue;
                     for (int ci = 0; ci < cin; ++ci) {
-                        const float a = __bfloat162float(in[(((n * kch + ci / 8) * S + hh) * S + ww) * 8 + ci % 8]);
-                        const __nv_bfloat16 wb = w[(((int64_t)tap * kch + ci / 8) * cout + co) * 8 + ci % 8];
-                        const float b = w_f16 ? __half2float(*reinterpret_cast<const __half*>(&wb)) : __bfloat162float(wb);
+                        const float a = __half2float(reinterpret_cast<const __half*>(in)[(((n * kch + ci / 8) * S + hh) * S + ww) * 8 + ci % 8]);
+                        const float b = __half2float(reinterpret_cast<const __half*>(w)[(((int64_t)tap * kch + ci / 8) * cout + co) * 8 + ci % 8]);
                         acc = fmaf(a, b, acc);
                     }
                 }
                 const float yv = fmaxf(fmaf(acc, scale[co], shift[co]), 0.f);
-                best = fmaxf(best, __bfloat162float(__float2bfloat16_rn(yv)));
+                best = fmaxf(best, __half2float(__float2half_rn(fminf(yv, 65504.f))));
             }
-        out[(((n * out_chunks + out_chunk0 + co / 8) * So + oh) * So + ow) * 8 + co % 8] = __float2bfloat16_rn(best);
+        reinterpret_cast<__half*>(out)[(((n * out_chunks + out_chunk0 + co / 8) * So + oh) * So + ow) * 8 + co % 8] = __float2half_rn(best);
     }
 }
 
@@ -285,7 +284,7 @@ static int pack_conv(dmf_net* n, ConvLayer& L, const std::string& blk) {
         for (int ci = 0; ci < cin; ++ci)
             for (int co = 0; co < cout; ++co)
                 pk[(((size_t)tap * kch + ci / 8) * cout + co) * 8 + ci % 8] = tc::w16((*w)[((size_t)co * cin + ci) * taps + tap]);
-    L.w_f16 = true;
+    L.f16 = true;
     std::vector<float> sc, sh;
     DMF_TRY(fold_bn(n, blk, cout, sc, sh));
     DMF_TRY(to_device(&L.w, pk));
@@ -308,7 +307,7 @@ static int pack_conv_rowpair(dmf_net* n, ConvLayer& L, const std::string& blk) {
                         const int tap = (dy + s2) * 3 + dx;
                         pk[(((size_t)tap * kch + ci / 8) * N2 + s2 * cout + co) * 8 + ci % 8] = tc::w16((*w)[((size_t)co * cin + ci) * 9 + dy * 3 + dx]);
                     }
-    L.w_f16 = true;
+    L.f16 = true;
     std::vector<float> sc, sh;
     DMF_TRY(fold_bn(n, blk, cout, sc, sh));
     DMF_TRY(to_device(&L.w, pk));
@@ -350,7 +349,7 @@ static int launch_conv(const ConvLayer& L, const CUtensorMap& map, __nv_bfloat16
     P.N = (int)N;
     P.n_tiles = (int)((N + g.NP - 1) / g.NP) * g.tiles_per_group;
     P.a_plane = g.a_plane; P.a_stage = g.a_stage; P.n_stage = g.n_stage; P.sbo_a = g.sbo_a;
-    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0; P.dbg = dbg; P.w_f16 = L.w_f16 ? 1 : 0;
+    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0; P.dbg = dbg; P.f16_in = L.f16 ? 1 : 0;
     P.stats = nullptr; P.stat_stride = 0;
     P.w = L.w; P.scale = L.scale; P.shift = L.shift; P.out = out; P.gap = gap;
     if (GAPOUT) DMF_CUDA(cudaMemsetAsync(gap, 0, sizeof(float) * (size_t)N * CO, st));
@@ -375,7 +374,7 @@ static int launch_rowpair(const ConvLayer& L, const CUtensorMap& map, __nv_bfloa
     P.S = g.S; P.S_l2 = g.S_l2; P.NP = 1; P.NP_l2 = 0; P.TH = g.TH; P.tiles_x_l2 = g.tiles_x_l2; P.tpg_l2 = g.tpg_l2;
     P.N = (int)N; P.n_tiles = (int)N * g.tiles_per_group;
     P.a_plane = g.a_plane; P.a_stage = g.a_stage; P.n_stage = g.n_stage; P.sbo_a = g.sbo_a;
-    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0; P.w_f16 = L.w_f16 ? 1 : 0;
+    P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0; P.f16_in = L.f16 ? 1 : 0;
     P.w = L.w; P.scale = L.scale; P.shift = L.shift; P.out = out;
     auto kern = tc::conv_rowpair_kernel<CI, G>;
     static bool attr_set = false;
@@ -707,7 +706,7 @@ int dmf_net_debug_layer(dmf_net* n, int layer, int impl, const void* in_dev, voi
         const int64_t total = N * So * So * L.g.cout;
         const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
         direct_conv_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in_dev, L.w, L.scale, L.shift, (__nv_bfloat16*)out_dev, N,
-                                                 L.g.S, L.g.cin, L.g.cout, L.g.taps, L.g.pool, och, oc0, L.w_f16 ? 1 : 0);
+                                                 L.g.S, L.g.cin, L.g.cout, L.g.taps, L.g.pool, och, oc0);
         DMF_LAUNCHED();
         return DMF_OK;
     }

@@ -16,8 +16,8 @@ constexpr int kHeadWarps = 8;
 
 struct ConvLayer {
     LayerGeom g;
-    __nv_bfloat16* w = nullptr;   // packed [tap][cin/8][cout][8]; fp16 bit patterns when w_f16 (tc::w16)
-    bool w_f16 = false;
+    __nv_bfloat16* w = nullptr;   // packed [tap][cin/8][cout][8]; fp16 bit patterns when f16 (tc::w16), in the 16-bit container type
+    bool f16 = false;             // fp16 operands (every inference layer but the hi/lo-split MS stem)
     float* scale = nullptr;
     float* shift = nullptr;
     CUtensorMap map;              // over the workspace input buffer

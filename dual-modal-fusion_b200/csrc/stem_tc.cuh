@@ -245,10 +245,10 @@ __global__ void __launch_bounds__(320 + 128 * G, 1) stem_pan_tc_kernel(const Ste
                         const int k = 4 * k4 + e;
                         const float mx = fmaxf(fmaxf(__uint_as_float(v0[k]), __uint_as_float(v1[k])),
                                                fmaxf(__uint_as_float(v2[k]), __uint_as_float(v3[k])));
-                        r[e] = fmaxf(mx + shv[e], 0.f);
+                        r[e] = mx + shv[e];
                     }
-                    pk[2 * k4] = pack_bf16x2(r[0], r[1]);
-                    pk[2 * k4 + 1] = pack_bf16x2(r[2], r[3]);
+                    pk[2 * k4] = pack_f16x2_relu(r[0], r[1]);            // ReLU + fp16 (the inference activation format)
+                    pk[2 * k4 + 1] = pack_f16x2_relu(r[2], r[3]);
                 }
                 *reinterpret_cast<uint4*>(obase + (int64_t)(2 * hf) * (S * S) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *reinterpret_cast<uint4*>(obase + (int64_t)(2 * hf + 1) * (S * S) * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);

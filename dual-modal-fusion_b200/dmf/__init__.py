@@ -407,12 +407,12 @@ class NetHandle:
         return {k: float(v) for k, v in zip(names, buf) if k != '_'}
 
     def dense_buffer(self, name):
-        """test hook: a dense-path map as a flat tensor aliasing the library's workspace (bf16; the row sums "S" are fp32), and
+        """test hook: a dense-path map as a flat tensor aliasing the library's workspace (fp16; the row sums "S" are fp32), and
         (rows, cols) of the MS grid"""
         ptr, nbytes, dims = C.c_void_p(), C.c_int64(), (C.c_int32 * 2)()
         check(lib.dmf_net_dense_buffer(self._h, name.encode(), C.byref(ptr), C.byref(nbytes), dims))
         t = _from_ptr(ptr.value, nbytes.value, self.device)
-        return t.view(torch.float32 if name == 'S' else torch.bfloat16), (int(dims[0]), int(dims[1]))
+        return t.view(torch.float32 if name == 'S' else torch.float16), (int(dims[0]), int(dims[1]))
 
     def set_timing(self, on):
         check(lib.dmf_net_set_timing(self._h, 1 if on else 0))
@@ -425,13 +425,13 @@ class NetHandle:
 
     def debug_layer(self, layer, impl, x, out_shape, out=None):
         if out is None:
-            out = torch.zeros(out_shape, dtype=torch.bfloat16, device=x.device)
+            out = torch.zeros(out_shape, dtype=torch.float16, device=x.device)
         with torch.cuda.device(x.device):
             check(lib.dmf_net_debug_layer(self._h, layer, impl, _ptr(x.contiguous()), _ptr(out), x.shape[0], _stream()))
         return out
 
     def debug_stem(self, which, patches, out_shape):
-        out = torch.zeros(out_shape, dtype=torch.bfloat16, device=patches.device)
+        out = torch.zeros(out_shape, dtype=torch.float16, device=patches.device)
         with torch.cuda.device(patches.device):
             check(lib.dmf_net_debug_stem(self._h, which, _ptr(patches.contiguous()), _ptr(out), patches.shape[0], _stream()))
         return out
