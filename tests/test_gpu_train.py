@@ -288,7 +288,17 @@ def test_train_step_matches_torch(dmf, p, N):
             assert rel(v, bufs32[k]) <= 5e-3, k
         else:
             assert int(v) == int(bufs32[k]) == 1, k
-    # gradients
+    # gradients: per-tensor table (relative L2 error vs the bf16-emulated torch step and vs pure fp32, cosine vs fp32) -> gpurun_out/
+    import json
+    import os
+    table = {k: {'rel_err_vs_bf16_emulation': rel(gn[k], ge[k]), 'rel_err_vs_fp32': rel(gn[k], g32[k]),
+                 'cosine_vs_fp32': float(F.cosine_similarity(gn[k].reshape(1, -1).double(), g32[k].reshape(1, -1).double())),
+                 'numel': gn[k].numel()} for k in gn if not (k.endswith('.0.bias') and not k.startswith('fc'))}
+    print(json.dumps({'p': p, 'N': N, 'gradients': table}))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(out):
+        json.dump({'test': 'tests/test_gpu_train.py::test_train_step_matches_torch', 'p': p, 'batch': N, 'bounds': {'rel_err_vs_bf16_emulation': GRAD_EMU,
+                   'cosine_vs_fp32': GRAD_COS_FP32}, 'gradients': table}, open(os.path.join(out, 'grad_table_p%d.json' % p), 'w'), indent=1)
     for k in gn:
         if k.endswith('.0.bias') and not k.startswith('fc'):
             # a bias in front of a train-mode BatchNorm has zero gradient (torch returns rounding noise)
