@@ -14,14 +14,13 @@ namespace dmf {
 __global__ void __launch_bounds__(256) ihs_tran_kernel(const double* __restrict__ ms, const double* __restrict__ pan,
                                                        const int8_t* __restrict__ offs, double* __restrict__ out,
                                                        int H, int W) {
-    // work item = (j, r, k): MS row j, sub-row r in 0..3, MS col k; k fastest -> coalesced 32-byte pieces
-    const int64_t total = (int64_t)H * 4 * W;
+    // work item = (j, r, k): MS row j, sub-row r in 0..3 (blockIdx.y = 4j + r), MS col k fastest -> coalesced 32-byte pieces;
+    // no 64-bit division per element
     const int64_t HW = (int64_t)H * W;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(t % W);
-        const int64_t jr = t / W;
-        const int r = (int)(jr & 3);
-        const int j = (int)(jr >> 2);
+    for (int jr = blockIdx.y; jr < 4 * H; jr += gridDim.y)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < W; k += gridDim.x * blockDim.x) {
+        const int r = jr & 3;
+        const int j = jr >> 2;
         const int64_t px = (int64_t)j * W + k;
         const double2* m2 = reinterpret_cast<const double2*>(ms + px * 4);
         const double2 m01 = __ldg(m2), m23 = __ldg(m2 + 1);
@@ -98,8 +97,7 @@ int dmf_ihs_tran(const double* ms_dev, const double* pan_dev, const int8_t* offs
     DMF_REQUIRE(((uintptr_t)ms_dev & 15) == 0 && ((uintptr_t)pan_dev & 15) == 0 && ((uintptr_t)mspan_out_dev & 15) == 0 &&
                     ((uintptr_t)offsets_dev & 1) == 0,
                 "ihs_tran: pointers must be 16-byte aligned");
-    const int64_t total = (int64_t)H * 4 * W;
-    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+    const dim3 grid((unsigned)std::min((W + 255) / 256, 64), (unsigned)std::min(4 * H, 65535));
     ihs_tran_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ms_dev, pan_dev, offsets_dev, mspan_out_dev, H, W);
     DMF_LAUNCHED();
     return DMF_OK;

@@ -45,10 +45,16 @@ __global__ void __launch_bounds__(kK4Warps * 32) argmax_confusion_kernel(const f
         const int total = rows * C;
         int r = lane / C, c = lane - r * C;                      // element e = r * C + c, advanced by 32 per step without a division
         const int dr = 32 / C, dc = 32 - dr * C;
-        for (int e = lane; e < total; e += 32) {
-            tile[r * Cp + c] = __ldg(src + e);
-            r += dr; c += dc;
-            if (c >= C) { c -= C; ++r; }
+        for (int e0 = lane; e0 < total; e0 += 8 * 32) {          // 8 independent 128-byte warp loads in flight, then the 8 tile writes
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = e0 + 32 * u < total ? __ldg(src + e0 + 32 * u) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (e0 + 32 * u < total) tile[r * Cp + c] = v[u];
+                r += dr; c += dc;
+                if (c >= C) { c -= C; ++r; }
+            }
         }
         __syncwarp();
         const bool valid = lane < rows;

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) ihs_scene_kernel(const TM* __restrict__ m
     for (int R = blockIdx.y; R < H4p; R += gridDim.y) {
         const int r = reflect101(R, 4 * H), j = r >> 2, rr = r & 3;
         for (int Cc = blockIdx.x * blockDim.x + threadIdx.x; Cc < W4p; Cc += gridDim.x * blockDim.x) {
-            const int c = reflect101(Cc, 4 * W), k = c >> 2, cc = c & 3;
+            const int c = Cc < 4 * W ? Cc : reflect101(Cc, 4 * W), k = c >> 2, cc = c & 3;      // the modulo only on the padded fringe
             const int64_t px = (int64_t)j * W + k;
             double up[4];
 #pragma unroll

@@ -166,7 +166,12 @@ class Net(nn.Module):
             dist.all_reduce(store)                                # one bucket: the whole model
             h.flat_grad.div_(store[-1])
 
-    def forward(self, ms, pan):
+    def forward(self, ms, pan, mspan=None):
+        """forward(ms, pan) as solver/mainsolver.py:52 calls it; forward(ms, pan, mspan) is the reference's 3-input call
+        (mode '3', train/train.py:44-52, fed by dataset_tri): an IHS-input model reads the IHS product in its PAN branch (the
+        product replaces PAN's intensity: it equals PAN to 2e-16, image_convert/IHS.py:40-54), so `mspan` takes `pan`'s place."""
+        if mspan is not None:
+            pan = mspan
         if not ms.is_cuda:
             raise RuntimeError("gmfnet: tensors must be on a CUDA device (no CPU path)")
         if self.training:
