@@ -482,8 +482,7 @@ class TrainHandle:
         total = sum(q.numel() for _, q in named)
         dev = named[0][1].device
         self.flat = torch.empty(total, dtype=torch.float32, device=dev)
-        self.grad_store = torch.zeros(total + 1, dtype=torch.float32, device=dev)     # + 1: the sample count of a data-parallel all-reduce
-        self.flat_grad = self.grad_store[:total]
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.forward_id = 0
         off = 0
         self._views = []

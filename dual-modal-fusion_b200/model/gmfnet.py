@@ -135,36 +135,36 @@ class Net(nn.Module):
         self._native_key = None
         return self._trainer
 
-    def train_step(self, ms, pan, target, optimizer):
+    def train_step(self, ms, pan, target, optimizer, global_batch=None):
         """One fused step of Solver.train(): zero_grad -> forward -> CrossEntropyLoss(mean) -> backward ->
-        (all-reduce of the flat gradient under torch.distributed) -> optimizer.step().  Returns the loss tensor."""
+        (all-reduce of the flat gradient under torch.distributed) -> optimizer.step().  Returns the loss tensor.
+        global_batch: samples of this step over ALL ranks (PatchLoader.last_global_batch); None = every rank holds ms.shape[0]."""
         h = self.trainer()
         h.reseat_grads()
         loss = h.step_patches(ms, pan, target)
-        self._sync_grads(h, ms.shape[0])
+        self._sync_grads(h, ms.shape[0], global_batch)
         optimizer.step()
         return loss
 
-    def train_step_scene(self, scene, flat_idx, optimizer, use_mspan=False):
+    def train_step_scene(self, scene, flat_idx, optimizer, use_mspan=False, global_batch=None):
         """The same with the batch cropped from the device scene (K1 + IHS-product input fused in front)."""
         h = self.trainer()
         h.reseat_grads()
         loss = h.step_scene(scene, flat_idx, use_mspan)
-        self._sync_grads(h, int(flat_idx.numel() if hasattr(flat_idx, 'numel') else len(flat_idx)))
+        self._sync_grads(h, int(flat_idx.numel() if hasattr(flat_idx, 'numel') else len(flat_idx)), global_batch)
         optimizer.step()
         return loss
 
     @staticmethod
-    def _sync_grads(h, n_local):
+    def _sync_grads(h, n_local, n_global=None):
         """Data-parallel gradient of the GLOBAL batch: each rank's gradient is the mean over its n_local samples, so the global
-        mean is sum_r n_r g_r / sum_r n_r.  One collective: the sample count rides in the spare last element of the flat
-        gradient buffer (the ranks' sub-batches may differ by one sample)."""
+        mean is sum_r (n_r / n_global) g_r — the ranks' sub-batches may differ by one sample.  n_global is known on every rank
+        without communication (all ranks draw the same batch and slice it); one scale kernel + ONE all-reduce of the flat buffer."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            store = h.grad_store                                  # flat_grad + 1 trailing element
-            h.flat_grad.mul_(float(n_local))
-            store[-1] = float(n_local)
-            dist.all_reduce(store)                                # one bucket: the whole model
-            h.flat_grad.div_(store[-1])
+            world = dist.get_world_size()
+            n_global = n_local * world if n_global is None else n_global
+            h.flat_grad.mul_(float(n_local) / float(n_global))
+            dist.all_reduce(h.flat_grad)                          # one bucket: the whole model
 
     def forward(self, ms, pan, mspan=None):
         """forward(ms, pan) as solver/mainsolver.py:52 calls it; forward(ms, pan, mspan) is the reference's 3-input call

@@ -96,7 +96,8 @@ class Solver(BaseSolver):
             for data1, data2, target, _, _ in bar:
                 data1, data2, target = data1.to(self.DEVICE), data2.to(self.DEVICE), target.to(self.DEVICE)
                 if fused:
-                    loss = self.cur_model.train_step(data1, data2, target, self.optimizer)
+                    loss = self.cur_model.train_step(data1, data2, target, self.optimizer,
+                                                     global_batch=getattr(self.train_loader, 'last_global_batch', None))
                 else:
                     self.optimizer.zero_grad()
                     loss = self.loss(self.cur_model(data1, data2), target.long())

@@ -99,11 +99,13 @@ class PatchLoader:
         self.indices = np.asarray(indices, dtype=np.int64)
         self.batch_size = batch_size
         self.rank, self.world = int(rank), int(world)
+        self.last_global_batch = 0
         self._index_loader = DataLoader(_IndexOnly(self.indices), batch_size=batch_size, shuffle=shuffle, num_workers=0)
 
     def __iter__(self):
         for idx in self._index_loader:
             idx = idx.numpy()
+            self.last_global_batch = int(idx.size)      # samples of this step over all ranks (the gradient mean's denominator)
             if self.world > 1:
                 if idx.size < self.world:          # a tail batch that cannot feed every rank is dropped by ALL ranks alike
                     continue

@@ -91,12 +91,11 @@ def _worker_shards(rank, world, port, out):
     class H_:
         pass
     h = H_()
-    h.grad_store = torch.zeros(7, dtype=torch.float32)
-    h.flat_grad = h.grad_store[:6]
+    h.flat_grad = torch.zeros(6, dtype=torch.float32)
     n_local = 3 + rank                                     # unequal sub-batches
     g_local = torch.arange(6, dtype=torch.float32) * (rank + 1)
     h.flat_grad.copy_(g_local)
-    Net._sync_grads(h, n_local)
+    Net._sync_grads(h, n_local, sum(3 + r for r in range(world)))
     want = sum((3 + r) * torch.arange(6, dtype=torch.float32) * (r + 1) for r in range(world)) / sum(3 + r for r in range(world))
     ok_grad = torch.allclose(h.flat_grad, want, rtol=1e-6)
     if rank == 0:

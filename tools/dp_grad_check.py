@@ -45,7 +45,7 @@ class NoStep:                       # the check is on the gradient: no parameter
 
 
 net = fresh()
-net.train_step_scene(scene, torch.from_numpy(subs[rank]).to(dev), NoStep())
+net.train_step_scene(scene, torch.from_numpy(subs[rank]).to(dev), NoStep(), global_batch=len(batch))
 g_dp = net.trainer().flat_grad.clone()
 ok, worst = True, 0.0
 if rank == 0:
