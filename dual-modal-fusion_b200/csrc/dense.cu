@@ -30,7 +30,7 @@ namespace dmf {
 struct DenseWs {
     int W = 0, band = 0, p = 0, R1 = 0, C1 = 0;
     __nv_bfloat16 *A = nullptr, *CAT = nullptr, *B1 = nullptr, *B2 = nullptr;
-    float* S = nullptr;                              // row sums of F for the separable average pool [3][16][R][W][8]
+    __half* S = nullptr;                             // row means of F for the separable average pool [3][16][R][W][8], fp16
     float *w_ms1 = nullptr, *w_pan1 = nullptr;       // fp32 stem conv weights in torch layout
     // conv + pool layers (ms2, pan2, pan3): bf16 weights [C_in/8][tap][C_out][8] with sign(BN scale) folded into every output channel, |scale|,
     // shift — conv_pool4_kernel takes the max over the pooling window BEFORE the affine
@@ -219,7 +219,7 @@ __device__ __forceinline__ void hist_add_warp(unsigned int* hist, int key, bool 
 }
 
 template <int P2>
-__global__ void __launch_bounds__(kDenseHeadThreads, 2) head_dense_kernel(const float4* __restrict__ S, int rows, int nb, int W, int C,
+__global__ void __launch_bounds__(kDenseHeadThreads, 2) head_dense_kernel(const uint4* __restrict__ S, int rows, int nb, int W, int C,
                                                                        const __nv_bfloat16* __restrict__ w1_hilo /* [2][16][64][8] */,
                                                                        const float* __restrict__ fc1b, const float* __restrict__ fc2t,
                                                                        const float* __restrict__ fc2b,
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kDenseHeadThreads, 2) head_dense_kernel(const 
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const float inv = 1.0f / (float)(P2 * P2);
+    const float inv = 1.0f / (float)P2;                 // S holds row means: the column mean over the P2 rows is left
     const int segs = (W + kHeadPx - 1) / kHeadPx;
     const int n_seg = nb * segs;
     uint32_t phase = 0;
@@ -279,18 +279,21 @@ __global__ void __launch_bounds__(kDenseHeadThreads, 2) head_dense_kernel(const 
             if (y < W) {
 #pragma unroll
                 for (int k0 = 0; k0 < P2; k0 += 4) {
-                    float4 v[4][2];
+                    uint4 v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int k = k0 + e, a = k == 0 ? 0 : (k == P2 - 1 ? 2 : 1);
-                        const float4* q = S + ((((int64_t)a * 16 + chunk) * rows + xl + 2 * k) * W + y) * 2;
-                        v[e][0] = __ldg(q);
-                        v[e][1] = __ldg(q + 1);
+                        v[e] = __ldg(S + (((int64_t)a * 16 + chunk) * rows + xl + 2 * k) * W + y);
                     }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        s[0] += v[e][0].x; s[1] += v[e][0].y; s[2] += v[e][0].z; s[3] += v[e][0].w;
-                        s[4] += v[e][1].x; s[5] += v[e][1].y; s[6] += v[e][1].z; s[7] += v[e][1].w;
+                        const uint32_t u[4] = {v[e].x, v[e].y, v[e].z, v[e].w};
+#pragma unroll
+                        for (int h2 = 0; h2 < 4; ++h2) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[h2]));
+                            s[2 * h2] += f.x;
+                            s[2 * h2 + 1] += f.y;
+                        }
                     }
                 }
             }
@@ -569,7 +572,7 @@ static int dense_prepare(dmf_net* n, int W, int band) {
     DMF_CUDA(cudaMalloc(&d->CAT, sCAT));
     DMF_CUDA(cudaMalloc(&d->B1, sB1));
     DMF_CUDA(cudaMalloc(&d->B2, sB2));
-    const size_t sS = R1 * (size_t)W * 3 * C_FUSE * sizeof(float);
+    const size_t sS = R1 * (size_t)W * 3 * C_FUSE * sizeof(__half);
     DMF_CUDA(cudaMalloc(&d->S, sS));
     d->bytes = sA + sCAT + sB1 + sB2 + sS;
     // positions a band never writes are only ever read into don't-care outputs; zero them once so that runs are reproducible
@@ -637,7 +640,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             P.rows = rows; P.W = W; P.tiles_x = cdiv(W, valid); P.n_tiles = rows * 3 * P.tiles_x; P.s_rows = rows;
             static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
             P.dbg = dbg;
-            P.w = n->L[3].w; P.scale = n->L[3].scale; P.shift = n->L[3].shift; P.S = reinterpret_cast<float4*>(d->S);
+            P.w = n->L[3].w; P.scale = n->L[3].scale; P.shift = n->L[3].shift; P.S = reinterpret_cast<uint4*>(d->S);
             P.cat = d->CAT; P.R1 = R1; P.C1 = C1;
             {   // pooled cells k of a patch sit at X = x + 2k: first k = 0, interior 1 .. p/2 - 2, last p/2 - 1
                 const int P2 = p / 2, k_lo[3] = {0, 1, P2 - 1}, k_hi[3] = {0, P2 - 2, P2 - 1};
@@ -654,7 +657,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             const int64_t off = (int64_t)(b0 - row0) * W;
             auto kern = p == 8 ? head_dense_kernel<4> : p == 16 ? head_dense_kernel<8> : head_dense_kernel<16>;
             kern<<<std::min(n_seg, 2 * num_sms()), kDenseHeadThreads, dense_head_smem(n->C), st>>>(      // 2 blocks per SM (~100 KB each)
-                reinterpret_cast<const float4*>(d->S), rows, nb, W, n->C, d->w_fc1, n->fc1b, n->fc2t, n->fc2b, (int64_t)b0 * W, s->label,
+                reinterpret_cast<const uint4*>(d->S), rows, nb, W, n->C, d->w_fc1, n->fc1b, n->fc2t, n->fc2b, (int64_t)b0 * W, s->label,
                 logits_dev ? logits_dev + off * n->C : nullptr, reinterpret_cast<unsigned long long*>(cm_dev), pred_map_dev);
             DMF_LAUNCHED();
         }
@@ -737,7 +740,7 @@ int dmf_net_dense_buffer(dmf_net* n, const char* name, void** ptr_out, int64_t* 
     else if (k == "CAT") { *ptr_out = d->CAT; *bytes_out = px * 9 * C_CAT * 2; }
     else if (k == "B1") { *ptr_out = d->B1; *bytes_out = px * 4 * 9 * C_PAN1 * 2; }
     else if (k == "B2") { *ptr_out = d->B2; *bytes_out = px * 9 * C_PAN2 * 2; }
-    else if (k == "S") { *ptr_out = d->S; *bytes_out = (int64_t)d->R1 * d->W * 3 * C_FUSE * sizeof(float); }
+    else if (k == "S") { *ptr_out = d->S; *bytes_out = (int64_t)d->R1 * d->W * 3 * C_FUSE * sizeof(__half); }
     else { set_error("net_dense_buffer: unknown map '%s'", name); return DMF_ERR_ARG; }
     dims[0] = d->R1; dims[1] = d->C1;
     return DMF_OK;

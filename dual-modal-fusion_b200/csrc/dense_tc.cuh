@@ -31,7 +31,7 @@ namespace tc {
 struct FuseRowsParams {
     int rows, W;                          // map rows of this band, anchor columns
     int tiles_x, n_tiles;
-    int s_rows;                           // row dimension of S ([3][16][s_rows][W][8] fp32)
+    int s_rows;                           // row dimension of S ([3][16][s_rows][W][8] fp16)
     int row_lo[3], row_n[3];              // map rows [lo, lo + n) of each row class that some anchor of the band uses
     int R1, C1;                           // CAT plane geometry: [9][32 chunks][R1][C1][8] bf16 (+ 2 KB of slack behind the tensor)
     const __nv_bfloat16* cat;
@@ -39,7 +39,7 @@ struct FuseRowsParams {
     const __nv_bfloat16* w;               // packed [C_in/8][C_out][8]
     const float* scale;
     const float* shift;
-    float4* S;
+    uint4* S;                              // [3][16][s_rows][W][8] fp16: row means of F (l ascending, fp32 accumulation, one fp16 rounding)
 };
 
 constexpr int kFrKQ = 8, kFrStages = 3, kFrPitch = 272;
@@ -208,8 +208,9 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
             asm volatile("bar.sync 1, 256;" ::: "memory");                // F tile complete
             const int y = tx * VALID + m;
             if (m < VALID && y < P.W && !(P.dbg & 2)) {
-                float4* o = P.S + ((((int64_t)a * 16 + hc * 8) * P.s_rows + X) * P.W + y) * 2;
-                const int64_t cstride = (int64_t)P.s_rows * P.W * 2;
+                uint4* o = P.S + (((int64_t)a * 16 + hc * 8) * P.s_rows + X) * P.W + y;
+                const int64_t cstride = (int64_t)P.s_rows * P.W;
+                constexpr float inv = 1.0f / (float)P2;                    // S holds row MEANS (an exact power-of-two scaling: no fp16 overflow of the sums)
 #pragma unroll 2
                 for (int ch = 0; ch < 8; ++ch) {
                     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
                             s[2 * h + 1] += f.y;
                         }
                     }
-                    o[ch * cstride] = make_float4(s[0], s[1], s[2], s[3]);
-                    o[ch * cstride + 1] = make_float4(s[4], s[5], s[6], s[7]);
+                    o[ch * cstride] = make_uint4(pack_f16x2(s[0] * inv, s[1] * inv), pack_f16x2(s[2] * inv, s[3] * inv),
+                                                 pack_f16x2(s[4] * inv, s[5] * inv), pack_f16x2(s[6] * inv, s[7] * inv));
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");                // F tile free again

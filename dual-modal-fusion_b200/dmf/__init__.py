@@ -407,12 +407,12 @@ class NetHandle:
         return {k: float(v) for k, v in zip(names, buf) if k != '_'}
 
     def dense_buffer(self, name):
-        """test hook: a dense-path map as a flat tensor aliasing the library's workspace (fp16; the row sums "S" are fp32), and
+        """test hook: a dense-path map as a flat tensor aliasing the library's workspace (fp16; "S" holds the row MEANS of F), and
         (rows, cols) of the MS grid"""
         ptr, nbytes, dims = C.c_void_p(), C.c_int64(), (C.c_int32 * 2)()
         check(lib.dmf_net_dense_buffer(self._h, name.encode(), C.byref(ptr), C.byref(nbytes), dims))
         t = _from_ptr(ptr.value, nbytes.value, self.device)
-        return t.view(torch.float32 if name == 'S' else torch.float16), (int(dims[0]), int(dims[1]))
+        return t.view(torch.float16), (int(dims[0]), int(dims[1]))
 
     def set_timing(self, on):
         check(lib.dmf_net_set_timing(self._h, 1 if on else 0))

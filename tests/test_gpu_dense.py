@@ -129,7 +129,7 @@ def test_dense_layers_in_isolation(dmf, p, H, W, row0, nb):
         P2, rows_b = p // 2, nb + p - 1
         S5 = Sm[:3 * 16 * rows_b * W * 8].view(3, 16, rows_b, W, 8)
         for i, (xl, y) in enumerate(anchors):
-            got_sum = sum(S5[c3(k, P2), :, xl + 2 * k, y, :] for k in range(P2)).reshape(128)
+            got_sum = P2 * sum(S5[c3(k, P2), :, xl + 2 * k, y, :].float() for k in range(P2)).reshape(128)      # S holds row MEANS (fp16)
             want_sum = want_f[i].sum(dim=(1, 2))
             tol = (2 * 2.0 ** -8 * want_f[i].abs() + 1e-3).sum(dim=(1, 2))
             assert bool(((got_sum - want_sum).abs() <= tol).all()), 'fuse + row sums: max err %g' % float((got_sum - want_sum).abs().max())
