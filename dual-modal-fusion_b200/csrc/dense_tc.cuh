@@ -42,9 +42,9 @@ struct FuseRowsParams {
     uint4* S;                              // [3][16][s_rows][W][8] fp16: row means of F (l ascending, fp32 accumulation, one fp16 rounding)
 };
 
-constexpr int kFrKQ = 8, kFrStages = 3, kFrPitch = 272;
+constexpr int kFrKQ = 8, kFrStages = 7, kFrPitch = 272;      // 7 x 16 KB of CAT rows in flight per SM (the kernel is bound by memory-level parallelism)
 constexpr uint32_t kFrStage = kFrKQ * 128 * 16;                                        // 16 KB
-constexpr size_t kFrSmem = (size_t)256 * 128 * 2 + kFrStages * kFrStage + 3 * 128 * kFrPitch + 2 * 128 * 4 + 16 * 8;
+constexpr size_t kFrSmem = (size_t)256 * 128 * 2 + kFrStages * kFrStage + 128 * kFrPitch + 2 * 128 * 4 + 24 * 8;
 
 template <int P2>
 __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_constant__ FuseRowsParams P) {
@@ -56,18 +56,18 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;
     uint8_t* a_s = smem + WBYTES;
-    uint8_t* f_s = a_s + kFrStages * kFrStage;                       // [3][128 cols][272 B]
-    float* scale_s = reinterpret_cast<float*>(f_s + 3 * 128 * kFrPitch);
+    uint8_t* f_s = a_s + kFrStages * kFrStage;                       // [128 cols][272 B]: the F tile of ONE column class
+    float* scale_s = reinterpret_cast<float*>(f_s + 128 * kFrPitch);
     float* shift_s = scale_s + C_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
-    // bars: [0,3) full, [3,6) empty, 6 weights, 7 tmem_full, 8 tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    // bars: [0,S) full, [S,2S) empty, 2S weights, 2S+1 tmem_full, 2S+2 tmem_empty   (S = kFrStages)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFrStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (3 + s); };
-    const uint32_t w_bar = bar0 + 8u * 6, tfull_bar = bar0 + 8u * 7, tempty_bar = bar0 + 8u * 8;
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kFrStages + s); };
+    const uint32_t w_bar = bar0 + 8u * (2 * kFrStages), tfull_bar = bar0 + 8u * (2 * kFrStages + 1), tempty_bar = bar0 + 8u * (2 * kFrStages + 2);
 
     for (int i = threadIdx.x; i < C_OUT; i += 320) {
         scale_s[i] = P.scale[i];
@@ -176,59 +176,84 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
             mbar_wait(tfull_bar, it & 1);
             ++it;
             tc_fence_after();
-            if (!(P.dbg & 2)) {
-#pragma unroll 1
-                for (int b = 0; b < 3; ++b) {
-#pragma unroll 1
-                    for (int c0 = hc * 64; c0 < hc * 64 + 64; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(t_row + (uint32_t)(b * C_OUT + c0), v);
-                        const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
-                        const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
-                        uint32_t pk[16];
+            // One F tile (one column class) in shared memory at a time; the row sums live in 64 fp32 registers per thread
+            // (thread = anchor column m, channel half hc).  Class 0 contributes F[a,0][X][y] = the thread's OWN TMEM lane: no
+            // exchange; class 1 contributes the columns y + 2l, l = 1 .. P2-2, class 2 the column y + 2(P2-1): through the tile.
+            // Same fp16 rounding points and the same fp32 summation order (l ascending) as a materialised F tensor.
+            float acc[64];
+            const bool act = !(P.dbg & 2);
+            auto drain = [&](int b, bool to_regs) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const float4 sc = sc4[k], sh = sh4[k];
-                            const float a0 = fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x);
-                            const float a1 = fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y);
-                            const float a2 = fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z);
-                            const float a3 = fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w);
-                            pk[2 * k] = pack_f16x2_relu(a0, a1);
-                            pk[2 * k + 1] = pack_f16x2_relu(a2, a3);
+                for (int cg = 0; cg < 2; ++cg) {
+                    const int c0 = hc * 64 + cg * 32;
+                    uint32_t v[32];
+                    tmem_ld32(t_row + (uint32_t)(b * C_OUT + c0), v);
+                    const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
+                    const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 sc = sc4[k], sh = sh4[k];
+                        const float a0 = fmaf(__uint_as_float(v[4 * k]), sc.x, sh.x);
+                        const float a1 = fmaf(__uint_as_float(v[4 * k + 1]), sc.y, sh.y);
+                        const float a2 = fmaf(__uint_as_float(v[4 * k + 2]), sc.z, sh.z);
+                        const float a3 = fmaf(__uint_as_float(v[4 * k + 3]), sc.w, sh.w);
+                        pk[2 * k] = pack_f16x2_relu(a0, a1);
+                        pk[2 * k + 1] = pack_f16x2_relu(a2, a3);
+                    }
+                    if (to_regs) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk[k]));
+                            acc[cg * 32 + 2 * k] = f.x;
+                            acc[cg * 32 + 2 * k + 1] = f.y;
                         }
-                        uint4* dst = reinterpret_cast<uint4*>(f_s + (uint32_t)(b * 128 + m) * kFrPitch + (uint32_t)c0 * 2);
+                    } else {
+                        uint4* dst = reinterpret_cast<uint4*>(f_s + (uint32_t)m * kFrPitch + (uint32_t)c0 * 2);
 #pragma unroll
                         for (int s4 = 0; s4 < 4; ++s4) dst[s4] = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
                     }
                 }
+            };
+            auto add_col = [&](int col) {                              // acc += F tile row `col`, this thread's 64 channels
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(f_s + (uint32_t)col * kFrPitch + (uint32_t)(hc * 8 + ch) * 16);
+                    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[h]));
+                        acc[ch * 8 + 2 * h] += f.x;
+                        acc[ch * 8 + 2 * h + 1] += f.y;
+                    }
+                }
+            };
+            const int y = tx * VALID + m;
+            const bool mine = m < VALID && y < P.W && act;
+            if (act) {
+                drain(0, true);                                           // l = 0
+                drain(1, false);
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");                // class-1 tile complete
+            if (mine) {
+#pragma unroll
+                for (int l = 1; l < P2 - 1; ++l) add_col(m + 2 * l);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");                // class-1 tile consumed
+            if (act) drain(2, false);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar);                       // accumulators drained: the next tile's MMAs may start
-            asm volatile("bar.sync 1, 256;" ::: "memory");                // F tile complete
-            const int y = tx * VALID + m;
-            if (m < VALID && y < P.W && !(P.dbg & 2)) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");                // class-2 tile complete
+            if (mine) {
+                add_col(m + 2 * (P2 - 1));
                 uint4* o = P.S + (((int64_t)a * 16 + hc * 8) * P.s_rows + X) * P.W + y;
                 const int64_t cstride = (int64_t)P.s_rows * P.W;
                 constexpr float inv = 1.0f / (float)P2;                    // S holds row MEANS (an exact power-of-two scaling: no fp16 overflow of the sums)
-#pragma unroll 2
-                for (int ch = 0; ch < 8; ++ch) {
-                    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int l = 0; l < P2; ++l) {
-                        const int b = l == 0 ? 0 : (l == P2 - 1 ? 2 : 1);
-                        const uint4 v = *reinterpret_cast<const uint4*>(f_s + (uint32_t)(b * 128 + m + 2 * l) * kFrPitch + (uint32_t)(hc * 8 + ch) * 16);
-                        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[h]));
-                            s[2 * h] += f.x;
-                            s[2 * h + 1] += f.y;
-                        }
-                    }
-                    o[ch * cstride] = make_uint4(pack_f16x2(s[0] * inv, s[1] * inv), pack_f16x2(s[2] * inv, s[3] * inv),
-                                                 pack_f16x2(s[4] * inv, s[5] * inv), pack_f16x2(s[6] * inv, s[7] * inv));
-                }
+                for (int ch = 0; ch < 8; ++ch)
+                    o[ch * cstride] = make_uint4(pack_f16x2(acc[ch * 8] * inv, acc[ch * 8 + 1] * inv), pack_f16x2(acc[ch * 8 + 2] * inv, acc[ch * 8 + 3] * inv),
+                                                 pack_f16x2(acc[ch * 8 + 4] * inv, acc[ch * 8 + 5] * inv), pack_f16x2(acc[ch * 8 + 6] * inv, acc[ch * 8 + 7] * inv));
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");                // F tile free again
         }
