@@ -299,7 +299,13 @@ def confusion_at(pred_map, label_map, flat_idx, C_, cm=None):
     pred_map, label_map = pred_map.contiguous(), label_map.contiguous()
     if cm is None:
         cm = torch.zeros((C_, C_), dtype=torch.int64, device=pred_map.device)
-    idx = None if flat_idx is None else torch.as_tensor(flat_idx, dtype=torch.int64).to(pred_map.device).contiguous()
+    idx = None if flat_idx is None else torch.as_tensor(flat_idx, dtype=torch.int64)
+    if idx is not None and not idx.is_cuda and idx.numel():          # host index lists are range-checked (the kernel does not)
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo < 0 or hi >= pred_map.numel():
+            raise IndexError('confusion_at: flat pixel index %d outside a map of %d pixels' % (lo if lo < 0 else hi, pred_map.numel()))
+    assert label_map.numel() == pred_map.numel(), 'prediction and label maps differ in size'
+    idx = None if idx is None else idx.to(pred_map.device).contiguous()
     n = pred_map.numel() if idx is None else idx.numel()
     with torch.cuda.device(pred_map.device):
         check(lib.dmf_confusion_at(_ptr(pred_map), _ptr(label_map), _ptr(idx), n, C_, _ptr(cm), _stream()))

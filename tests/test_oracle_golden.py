@@ -138,3 +138,29 @@ def test_fitted_net_reproduces_the_reference_run(golden):
     assert len(np.unique(g['label_map'])) >= 5 and k > 0.1
     for tag in fitted_net.WORKLOADS:
         assert set(fitted_net.fitted_state(tag)) == set(fitted_net.base_net(tag).state_dict())
+
+
+def test_vendored_reference_runner_agrees_with_the_oracle():
+    """oracle/ref_runner.py (the UNMODIFIED reference copied to oracle/_ref by __graft_entry__.build(), bench.py's CPU arm) on the smoke
+    scene: its confusion matrix and label map are those of the oracle restatement for the pixels it classified.  Skipped where the
+    copy does not exist (no /root/reference at build time)."""
+    import pytest
+    import torch
+    from oracle import fitted_net, ref_runner
+    if not ref_runner.available():
+        pytest.skip('oracle/_ref not built')
+    H, W, ncls, p = fitted_net.WORKLOADS['smoke']
+    ms, pan, label = fitted_net.scene('smoke')
+    run = ref_runner.RefRun(ms, pan, label, p, ncls, lambda args: fitted_net.fitted_net('smoke'))
+    M, label_map, done, secs = run.classify(budget_s=0.0)            # one DataLoader batch of 300 labelled pixels
+    assert done == 300 and M.sum() == 300
+    lab_idx = np.asarray(orc.split_data_old(label, [H, W, 4])[1][1])[:300]      # color_loader1 = the labelled pixels in index order
+    MS, PAN = orc.data_padding(ms, p), orc.data_padding(pan, p)
+    a, b = orc.gather_dual(MS, PAN, lab_idx // W, lab_idx % W, p)
+    with torch.no_grad():
+        pred = orc.argmax_first(fitted_net.fitted_net('smoke')(torch.from_numpy(a), torch.from_numpy(b)).numpy())
+    eq(M, orc.confusion(pred, label.reshape(-1)[lab_idx], ncls + 1))
+    assert np.array_equal(label_map.reshape(-1)[lab_idx], pred.astype(np.float64))
+    # the product mirror's modules are importable again afterwards (the runner swaps sys.modules / sys.path only while importing)
+    import solver.mainsolver as mirror
+    assert hasattr(mirror, 'row_band')
