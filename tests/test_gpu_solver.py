@@ -175,3 +175,66 @@ def test_validation_loss_and_best_epoch_match_the_reference_loop(tmp_path, monke
     for k, v in states[-1].items():
         assert torch.equal(cur['state_dict'][k], v), k
     assert len(set(np.round(s.val_losses, 6))) == 3                      # the epochs really differ
+
+
+def test_scene_pipeline_matches_resident_scene_path():
+    """dmf.ScenePipeline (the e2e public API: pinned host rasters -> upload on a copy stream -> range -> normalise/pad -> dense
+    inference -> D2H, software-pipelined over a stream of scenes) returns, for every scene of the stream, exactly the label band
+    and confusion matrix of the resident-scene path."""
+    import dmf
+    from oracle import fitted_net
+    from model.gmfnet import Net
+    H, W, ncls, p = 72, 60, 7, 16
+    net = Net(dict(fitted_net.cfg_for('c1'), b200={}))
+    net.load_state_dict(fitted_net.fitted_state('c1'))
+    net = net.to(DEV).eval()
+    h = net.native()
+    scenes = [orc.synthetic_scene_structured(H, W, ncls, seed=s, label_seed=s + 1, cell=24) for s in (11, 12, 13, 14, 15)]
+    r0, r1 = 8, 61                                              # a band in the middle: halo rows above the scene's end
+    pipe = dmf.ScenePipeline(h, H, W, p, r0, r1)
+    pins = [(torch.from_numpy(ms.view(np.int16)).pin_memory(), torch.from_numpy(pan.view(np.int16)).pin_memory(),
+             torch.from_numpy(lab).pin_memory()) for ms, pan, lab in scenes]
+    tickets = []
+    results = []
+    for i, (a, b, c) in enumerate(pins):                         # 2-deep pipeline: read result i-1 after submitting i
+        tickets.append(pipe.submit(a, b, c))
+        if i:
+            pm, cm = pipe.result(tickets[i - 1])
+            results.append((pm.clone(), cm.clone()))
+    pm, cm = pipe.result(tickets[-1])
+    results.append((pm.clone(), cm.clone()))
+    for (ms, pan, lab), (pm, cm) in zip(scenes, results):
+        sc = dmf.Scene.from_raw(ms, pan, p, DEV)
+        sc.set_labels(lab)
+        want_pm, want_cm = h.infer_scene(sc, r0, r1)
+        assert torch.equal(pm, want_pm[r0:r1].cpu()) and torch.equal(cm, want_cm.cpu())
+        assert int(cm.sum()) == (r1 - r0) * W and len(np.unique(pm.numpy())) >= 3
+
+
+def test_three_input_forward_and_gradient_accumulation():
+    """forward(ms, pan, mspan) feeds the IHS product to the PAN branch (the 3-input contract); the autograd path
+    accumulates over several backward calls like any torch module and refuses a backward through overwritten activations."""
+    from model.gmfnet import Net
+    p, C, N = 16, 6, 32
+    torch.manual_seed(1)
+    net = Net({'Categories_Number': C, 'patch_size': p, 'schedule': {'activate': 'Relu'}, 'b200': {'max_train_batch': N}}).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    ms = torch.rand((N, 4, p, p), device=DEV, generator=g)
+    pan = torch.rand((N, 1, 4 * p, 4 * p), device=DEV, generator=g)
+    mspan = torch.rand((N, 1, 4 * p, 4 * p), device=DEV, generator=g)
+    tgt = torch.randint(0, C, (N,), device=DEV, generator=g)
+    net.eval()
+    with torch.no_grad():
+        assert torch.equal(net(ms, pan, mspan), net(ms, mspan)) and not torch.equal(net(ms, pan, mspan), net(ms, pan))
+    net.train()
+    crit = torch.nn.CrossEntropyLoss()
+    net.zero_grad()
+    crit(net(ms, pan), tgt).backward()
+    g1 = {k: q.grad.clone() for k, q in net.named_parameters()}
+    crit(net(ms, pan), tgt).backward()                            # second backward without zero_grad: gradients add up
+    for k, q in net.named_parameters():
+        assert torch.allclose(q.grad, 2 * g1[k], rtol=1e-4, atol=1e-6), k
+    out1 = net(ms, pan)
+    net(ms, mspan)                                                # overwrites the handle's activation workspace
+    with pytest.raises(RuntimeError):
+        crit(out1, tgt).backward()
