@@ -627,12 +627,18 @@ class ScenePipeline:
                 s.cm_host = torch.empty((C_, C_), dtype=torch.int64).pin_memory()
                 s.uploaded, s.consumed, s.done = (torch.cuda.Event() for _ in range(3))
                 s.rng = None
+                s.ranges = None
                 s.consumed.record()
                 self.slots.append(s)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.slots[0].ms, self.slots[0].pan, self.slots[0].lab))
         self.d2h_bytes = (r1 - r0) * W + C_ * C_ * 8
 
-    def submit(self, ms_pin, pan_pin, lab_pin):
+    def submit(self, ms_pin, pan_pin, lab_pin, ms_range=None, pan_range=None):
+        """Queue one scene.  to_tensor (function/function.py:120-124) normalises with the range of the WHOLE raster: under
+        torch.distributed the ranks' bands cover the scene and their ranges are all-reduced; a single process that classifies only a
+        part of the scene (r0 > 0 or r1 < H) uploads only that part and must be GIVEN the ranges (ms_range / pan_range = (min, max))."""
+        if self.world == 1 and (self.r0 != 0 or self.r1 != self.H) and (ms_range is None or pan_range is None):
+            raise ValueError('ScenePipeline: a partial band in a single process needs ms_range / pan_range of the whole rasters')
         s = self.slots[self.n % len(self.slots)]
         self.n += 1
         s0, s1, r0, r1 = self.s0, self.s1, self.r0, self.r1
@@ -648,10 +654,15 @@ class ScenePipeline:
                     s.rng = torch.stack([a[0], -a[1], b[0], -b[1]])
                     self.dist.all_reduce(s.rng, op=self.dist.ReduceOp.MIN, group=self.group)
                     s.ranges = (torch.stack([s.rng[0], -s.rng[1]]), torch.stack([s.rng[2], -s.rng[3]]))
+                elif ms_range is not None:
+                    s.ranges = (torch.tensor([float(ms_range[0]), float(ms_range[1])], dtype=torch.float64).to(self.device, non_blocking=True),
+                                torch.tensor([float(pan_range[0]), float(pan_range[1])], dtype=torch.float64).to(self.device, non_blocking=True))
+                else:
+                    s.ranges = None
                 s.uploaded.record()
             cur = torch.cuda.current_stream()
             cur.wait_event(s.uploaded)
-            if self.world > 1:
+            if s.ranges is not None:
                 s.scene.update_raw(s.ms, s.pan, *s.ranges)
             else:
                 s.scene.update_raw(s.ms, s.pan)
