@@ -12,7 +12,10 @@ import dmf
 
 
 def read_tif(cfg, mode):
-    """reference: function/function.py:34-43 (libtiff).  Falls back to OpenCV / PIL readers."""
+    """reference: function/function.py:34-43 (libtiff: bands in FILE order).  Without libtiff the raster is read with OpenCV, whose
+    TIFF decoder hands 3- / 4-sample images back as BGR(A): the first three bands are swapped back so that the array is in file
+    order like libtiff's.  That restoration is announced once (band order matters to trained weights) and can be overridden with
+    cfg['b200']['tif_band_order'] = [i0, i1, i2, i3] (indices into what OpenCV returned)."""
     if mode not in ('ms', 'pan'):
         raise ValueError("mode")
     filename = cfg['data_address'] + ('ms4.tif' if mode == 'ms' else 'pan.tif')
@@ -21,12 +24,17 @@ def read_tif(cfg, mode):
         return TIFF.open(filename, mode='r').read_image()
     except ImportError:
         pass
+    import warnings
     import cv2
     image = cv2.imread(filename, cv2.IMREAD_UNCHANGED)
     if image is None:
         raise FileNotFoundError(filename)
     if image.ndim == 3:
-        image = image[:, :, ::-1] if image.shape[2] == 3 else image[:, :, [2, 1, 0, 3]]   # cv2 reads BGR(A)
+        b200 = cfg.get('b200') if isinstance(cfg.get('b200'), dict) else {}
+        order = b200.get('tif_band_order') or ([2, 1, 0] + list(range(3, image.shape[2])) if image.shape[2] >= 3 else list(range(image.shape[2])))
+        warnings.warn('read_tif: libtiff is not installed; %s read with OpenCV and its bands taken in the order %s '
+                      '(OpenCV decodes multi-sample TIFFs as BGR[A]; set b200.tif_band_order to override)' % (filename, order), stacklevel=2)
+        image = image[:, :, list(order)]
     return np.ascontiguousarray(image)
 
 
