@@ -415,9 +415,11 @@ def main():
 
     def dense_roofline(h, sc, rows0, rows1, Wd, tag_wl):
         """FLOPs the dense kernels execute.  A fused conv + pool layer evaluates, per map position and pooled border class
-        (first / interior / last per axis), the 4 conv outputs of the pooling window with 2,3 / 3,3 / 3,2 live tap rows
-        (columns): (5 + 6 + 5)^2 = 256 tap evaluations of 2*Cin*Cout FLOPs per position (no credit for tile padding, skipped
-        taps or don't-care rows)."""
+        (first / interior / last per axis), the conv outputs of the pooling window with 2,3 / 3,3 / 3,2 live tap rows
+        (columns): (5 + 6 + 5)^2 = 256 tap evaluations of 2*Cin*Cout FLOPs per position on the aligned grid (pan2).  On the
+        stride-1 grids (ms2, pan3) the second sub-position of an interior cell is the first one of its neighbour and is
+        evaluated once (dense_tc.cuh, SHARE): (5 + 3 + 5)^2 = 169.  No credit for tile padding (16/15, 8/7 on the shared
+        axes), skipped taps or don't-care rows."""
         h.set_timing(True)
         h.get_dense_timing(reset=True)
         h.infer_scene(sc, rows0, rows1)
@@ -426,10 +428,9 @@ def main():
         band = max(1, min(args.band, rows1 - rows0))
         bands = [min(band, rows1 - b) for b in range(rows0, rows1, band)]
         pos = sum((nb + P - 1) * (Wd + P - 1) for nb in bands)                 # MS-resolution map positions of the bands
-        tr = (5, 6, 5)                                                        # live tap rows (columns) of the 2 sub-positions per border class
-
         def taps(nb, cells, step_):
             """tap evaluations of one conv + pool layer over a band: per border class only the rows / columns some anchor uses"""
+            tr = (5, 3, 5) if step_ == 2 else (5, 6, 5)                       # live tap rows (columns) evaluated per border class
             ext = (0, step_ * (cells - 3), 0)
             return sum(t * (nb + e) for t, e in zip(tr, ext)) * sum(t * (Wd + e) for t, e in zip(tr, ext))
 

@@ -445,6 +445,9 @@ static int build_pool4_cls(tc::Pool4Cls& c, int a, int b, bool aligned, int box_
     if (nr * nc > max_boxes) { set_error("pool4 class (%d,%d) needs %d boxes", a, b, nr * nc); return DMF_ERR_STATE; }
     c.out_plane = (int16_t)(a * 3 + b);
     c.n_boxes = (int16_t)(nr * nc);
+    // stride-1 pooling, interior class on an axis: sub-position 1 of a cell IS sub-position 0 of the next cell -> evaluated once (dense_tc.cuh, SHARE)
+    c.ns = (int16_t)(!aligned && a == 1 ? 1 : 2);
+    c.nt = (int16_t)(!aligned && b == 1 ? 1 : 2);
     for (int i = 0; i < nr; ++i)
         for (int j = 0; j < nc; ++j) {
             const int k = i * nc + j;
@@ -467,10 +470,12 @@ static int build_pool4_cls(tc::Pool4Cls& c, int a, int b, bool aligned, int box_
 }
 
 // conv + pool of one layer over the band: in = 9 (x 4 phases) planes, out = 9 pooled planes
-template <int CI, int CO, int KQ, int STAGES, int BR, int BC, int NBUF, int EW>
-static int launch_pool4(const CUtensorMap& map, bool aligned, const __nv_bfloat16* w, const float* scale, const float* shift, __nv_bfloat16* out,
+template <int CI, int CO, int KQ, int STAGES, int BR, int BC, int NBUF, int EW, bool ALIGNED, bool SHARE>
+static int launch_pool4(const CUtensorMap& map, const __nv_bfloat16* w, const float* scale, const float* shift, __nv_bfloat16* out,
                         int out_chunks, int out_chunk0, int nb, int W, int p, int R1, int C1, cudaStream_t st) {
-    using Cfg = tc::Pool4Cfg<CI, CO, KQ, STAGES, BR, BC, NBUF>;
+    constexpr bool aligned = ALIGNED;             // pan2 pools on the aligned (phase-separated) grid; the stride-1 layers can share sub-positions
+    static_assert(!(ALIGNED && SHARE), "sub-positions are shared between the cells of a stride-1 pooling grid only");
+    using Cfg = tc::Pool4Cfg<CI, CO, KQ, STAGES, BR, BC, NBUF, SHARE>;
     static_assert(Cfg::SMEM <= (size_t)kSmemLimit, "conv_pool4_kernel does not fit in shared memory");
     tc::Pool4Params P{};
     P.rows = R1; P.cols = C1;
@@ -478,22 +483,27 @@ static int launch_pool4(const CUtensorMap& map, bool aligned, const __nv_bfloat1
     // class (first / interior / last cell) is only ever read at the rows the band's anchors x in [0, nb) put it on.
     const int cells = aligned ? p : p / 2, step = aligned ? 1 : 2;
     const int k_lo[3] = {0, 1, cells - 1}, k_hi[3] = {0, cells - 2, cells - 1};
-    int max_r = 0, max_c = 0;
+    P.tiles_x = P.tiles_y = 0;
     for (int a = 0; a < 3; ++a) {
         P.row_lo[a] = P.col_lo[a] = step * k_lo[a];
         P.row_n[a] = nb + step * (k_hi[a] - k_lo[a]);
         P.col_n[a] = W + step * (k_hi[a] - k_lo[a]);
-        max_r = std::max(max_r, P.row_n[a]);
-        max_c = std::max(max_c, P.col_n[a]);
+        P.trow[a] = SHARE && a == 1 ? 15 : 16;    // the interior class hands its last tile row / column to the next tile
+        P.tcol[a] = SHARE && a == 1 ? 7 : 8;
+        P.tiles_y = std::max(P.tiles_y, cdiv(P.row_n[a], P.trow[a]));
+        P.tiles_x = std::max(P.tiles_x, cdiv(P.col_n[a], P.tcol[a]));
     }
-    P.tiles_x = cdiv(max_c, 8); P.tiles_y = cdiv(max_r, 16); P.n_tiles = P.tiles_x * P.tiles_y * 9;
+    P.n_tiles = P.tiles_x * P.tiles_y * 9;
     P.out_chunks = out_chunks; P.out_chunk0 = out_chunk0;
     P.w = w; P.scale = scale; P.shift = shift; P.out = out;
     static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
     P.dbg = dbg;
     for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) DMF_TRY(build_pool4_cls(P.cls[a * 3 + b], a, b, aligned, BR, BC, Cfg::MAX_BOXES, Cfg::BOX_SLOT));
-    auto kern = tc::conv_pool4_kernel<CI, CO, KQ, STAGES, BR, BC, NBUF, EW>;
+        for (int b = 0; b < 3; ++b) {
+            DMF_TRY(build_pool4_cls(P.cls[a * 3 + b], a, b, aligned, BR, BC, Cfg::MAX_BOXES, Cfg::BOX_SLOT));
+            if (!SHARE) P.cls[a * 3 + b].ns = P.cls[a * 3 + b].nt = 2;
+        }
+    auto kern = tc::conv_pool4_kernel<CI, CO, KQ, STAGES, BR, BC, NBUF, EW, SHARE>;
     static bool attr_set = false;
     if (!attr_set) {
         DMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -628,7 +638,10 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, b0, rows, R1, C1, d->w_ms1, n->L[4].scale, n->L[4].shift, d->A);
         DMF_LAUNCHED();
         mark();
-        DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1, 8>(d->mapA, false, d->w_cp[0], d->sc_cp[0], d->sh_cp[0], d->CAT, C_CAT / 8, 0, nb, W, p, R1, C1, st)));
+        // DMF_DENSE_SHARE=0 (diagnostics): every cell of the stride-1 layers evaluates all four sub-positions itself, as pan2 must
+        static const bool share = !(getenv("DMF_DENSE_SHARE") && atoi(getenv("DMF_DENSE_SHARE")) == 0);
+        if (share) DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 2, 19, 11, 1, 8, false, true>(d->mapA, d->w_cp[0], d->sc_cp[0], d->sh_cp[0], d->CAT, C_CAT / 8, 0, nb, W, p, R1, C1, st)));
+        else DMF_TRY((launch_pool4<C_MS1, C_MS2, 2, 3, 19, 11, 1, 8, false, false>(d->mapA, d->w_cp[0], d->sc_cp[0], d->sh_cp[0], d->CAT, C_CAT / 8, 0, nb, W, p, R1, C1, st)));
         mark();
         mark();          // (stage slot of the former separate pooling pass)
         // ---- PAN branch
@@ -636,10 +649,11 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
             n->use_mspan ? s->mspan : s->pan, s->H4p, s->W4p, s->pan_pitch, b0, rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
-        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2, 8>(d->mapB1, true, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, nb, W, p, R1, C1, st)));
+        DMF_TRY((launch_pool4<C_PAN1, C_PAN2, 4, 2, 17, 9, 2, 8, true, false>(d->mapB1, d->w_cp[1], d->sc_cp[1], d->sh_cp[1], d->B2, C_PAN2 / 8, 0, nb, W, p, R1, C1, st)));
         mark();
         mark();
-        DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1, 8>(d->mapB2s, false, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, nb, W, p, R1, C1, st)));
+        if (share) DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 2, 19, 11, 1, 8, false, true>(d->mapB2s, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, nb, W, p, R1, C1, st)));
+        else DMF_TRY((launch_pool4<C_PAN2, C_PAN3, 2, 3, 19, 11, 1, 8, false, false>(d->mapB2s, d->w_cp[2], d->sc_cp[2], d->sh_cp[2], d->CAT, C_CAT / 8, C_MS2 / 8, nb, W, p, R1, C1, st)));
         mark();
         mark();
         // ---- fusion conv (1x1) on the 9 pooled planes + row sums of the global average pool
@@ -719,7 +733,7 @@ int dmf_dense_class_table(int a, int b, int aligned, int16_t* win, int16_t* box_
     DMF_REQUIRE(a >= 0 && a < 3 && b >= 0 && b < 3 && win && box_plane && box_drow && box_dcol && n_boxes && slot_bytes, "dense_class_table: bad argument");
     tc::Pool4Cls c;
     using CfgA = tc::Pool4Cfg<C_PAN1, C_PAN2, 4, 2, 17, 9, 2>;
-    using CfgS = tc::Pool4Cfg<C_MS1, C_MS2, 2, 3, 19, 11, 1>;
+    using CfgS = tc::Pool4Cfg<C_MS1, C_MS2, 2, 2, 19, 11, 1, true>;
     DMF_TRY(aligned ? build_pool4_cls(c, a, b, true, 17, 9, CfgA::MAX_BOXES, CfgA::BOX_SLOT) : build_pool4_cls(c, a, b, false, 19, 11, CfgS::MAX_BOXES, CfgS::BOX_SLOT));
     memcpy(win, c.win, sizeof(c.win));
     memcpy(box_plane, c.box_plane, sizeof(c.box_plane));

@@ -286,6 +286,16 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
 // 4 accumulators fill TMEM): 8 epilogue warps split the channels, the next tile's MMAs wait for them.
 // Epilogue: thread-local maximum of the 4 raw accumulators (the weights carry sign(BN scale)), then |scale| * max + shift, ReLU,
 // bf16, 16-byte stores in the C8-planar layout.
+//
+// SHARE (stride-1 pooling only).  With stride-1 pooling the sub-position s = 1 of cell X is the conv output at position X + 1.
+// On an axis whose border class is INTERIOR that is exactly the s = 0 output of the NEXT cell (same input variants, same
+// taps): evaluating both sub-positions in every cell computes each conv output twice (four times in the interior / interior
+// class).  For such an axis the tile evaluates ONE sub-position per cell (cls.ns / cls.nt = 1) and the epilogue takes the
+// maximum with the neighbouring cell's value instead: columns by a lane shuffle (lane + 1), rows by a lane shuffle (lane + 8)
+// and, across the 4-row lane quarters, through a 1 KB shared-memory hand-over between the epilogue warps of a channel slice.
+// The max is taken on the packed fp16 values AFTER the affine + ReLU + rounding, which is exact because all three are monotone
+// (the weights carry sign(scale)).  A tile's last row / column then only feeds its neighbour, so such tiles advance by 15 rows /
+// 7 columns.  Tap evaluations per position over the 9 classes: (5 + 3 + 5)^2 = 169 instead of (5 + 6 + 5)^2 = 256.
 constexpr int kP4MaxBoxes = 9;
 
 // tcgen05.mma with a collector hint for the A operand: USAGE 0 = none, 1 = fill (keep A for the next instruction), 2 = use (A is
@@ -310,11 +320,13 @@ struct Pool4Cls {
     int16_t box_plane[kP4MaxBoxes];
     int8_t box_drow[kP4MaxBoxes], box_dcol[kP4MaxBoxes];
     int16_t win[16];                      // [row offset + 1][col offset + 1]: (byte offset of that A window inside a stage) >> 4, or -1 = outside the patch
+    int16_t ns, nt;                       // sub-position rows / columns the tile evaluates itself: 2, or 1 = shared with the neighbouring cell (see below)
 };
 
 struct Pool4Params {
     int rows, cols;                       // grid of the pooled output = grid of every input plane
     int tiles_x, tiles_y, n_tiles;
+    int trow[3], tcol[3];                 // tile pitch per border class: 16 rows / 8 columns, or 15 / 7 where the tile's last row / column only feeds its neighbour
     int out_chunks, out_chunk0;
     int dbg;
     // rows / columns of each border class (first, interior, last) that some anchor of the band actually uses: [lo, lo + n)
@@ -326,7 +338,7 @@ struct Pool4Params {
     Pool4Cls cls[9];
 };
 
-template <int C_IN, int C_OUT, int KQ, int STAGES, int BR, int BC, int NBUF>
+template <int C_IN, int C_OUT, int KQ, int STAGES, int BR, int BC, int NBUF, bool SHARE = false>
 struct Pool4Cfg {
     static constexpr int KCH = C_IN / 8, NSTEP = KCH / KQ;
     static constexpr uint32_t PLANE = BR * BC * 16;                          // bytes of one channel-chunk plane of a box
@@ -335,13 +347,73 @@ struct Pool4Cfg {
     static constexpr int MAX_BOXES = BC == 9 ? 9 : 4;                        // aligned: 3 x 3 sources, stride-1: 2 x 2
     static constexpr uint32_t STAGE = MAX_BOXES * BOX_SLOT;
     static constexpr uint32_t WBYTES = 9u * C_IN * C_OUT * 2;
-    static constexpr size_t SMEM = WBYTES + (size_t)STAGES * STAGE + 2 * C_OUT * 4 + (2 * STAGES + 8) * 8 + 9 * sizeof(Pool4Cls);
-    static_assert(KCH % KQ == 0 && KQ % 2 == 0 && NBUF * 4 * C_OUT <= 512 && WBYTES % 128 == 0, "pool4 configuration");
+    static constexpr uint32_t CLS_BYTES = (9 * sizeof(Pool4Cls) + 15) / 16 * 16;
+    static constexpr uint32_t XCHG = SHARE ? 2u * 64u * C_OUT : 0u;         // 2 buffers x 8 lanes x C_OUT channels x fp16 x 4 lane quarters
+    static constexpr size_t SMEM = WBYTES + (size_t)STAGES * STAGE + 2 * C_OUT * 4 + (2 * STAGES + 8) * 8 + CLS_BYTES + XCHG;
+    static_assert(KCH % KQ == 0 && KQ % 2 == 0 && NBUF * 4 * C_OUT <= 512 && WBYTES % 128 == 0 && (!SHARE || NBUF == 1), "pool4 configuration");
 };
 
-template <int C_IN, int C_OUT, int KQ, int STAGES, int BR, int BC, int NBUF, int EW>
+
+// The MMAs of one pipeline step of one tile, for NS x NT sub-positions (see conv_pool4_kernel).  Window-major issue order with PAIRED
+// column sub-positions.  The A window at offset (orow, ocol) from the cell origin feeds every (sub-position (s, t), tap (dy, dx)) with
+// s + dy = orow, t + dx = ocol.  NT = 2: for ocol in {0, 1} both column sub-positions take part, with the horizontally adjacent taps
+// dx = ocol - 1 (t = 1) and dx = ocol (t = 0): ONE instruction with N = 2 * C_out whose B operand spans the two tap blocks and whose
+// accumulator spans the column blocks of (s, 1) and (s, 0) — TMEM block of (s, t) = 2 s + (1 - t).  Twice the math per A fetch and per
+// instruction issue (an M128 x N128 x K16 instruction is bound by its shared-memory operand reads, ~94 clk against a 64-clk math
+// floor; at N = 256 the math takes 128 clk and hides them).  ocol = -1 / 2 feed one column sub-position each (N = C_out).  Within a
+// row offset the windows ocol = 0, 1 are issued first, so that the first write of a tile into a block (both halves of a pair) is an
+// overwriting instruction.  Instructions that share an A window are issued back to back with A kept in the collector (UTCHMMA
+// ...A_KEEP / A_REUSE).  NT = 1: t = 0 only, every window feeds one N = C_out instruction; NS = 1: s = 0 only.
+template <int C_OUT, int KQ, uint32_t PLANE, int NS, int NT>
+__device__ __forceinline__ void pool4_issue_step(const int16_t* win, uint64_t a_desc0, uint64_t w_desc0, uint32_t d_tmem, int kq, uint32_t& started) {
+    constexpr uint32_t idesc1 = umma_idesc_f16(128, C_OUT), idesc2 = umma_idesc_f16(128, 2 * C_OUT);      // fp16 activations and weights
+#pragma unroll
+    for (int orow = -1; orow <= NS; ++orow) {
+        int nu = 0;                                    // sub-position rows with a tap dy = orow - s
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) nu += (orow - s2 >= -1 && orow - s2 <= 1) ? 1 : 0;
+#pragma unroll
+        for (int oi = 0; oi < 2 + NT; ++oi) {
+            constexpr int kOcol[4] = {0, 1, -1, 2};
+            const int ocol = kOcol[oi];
+            const int o = win[(orow + 1) * 4 + ocol + 1];
+            if (o >= 0) {
+#pragma unroll
+                for (int j = 0; j < KQ / 2; ++j) {
+                    const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)o + (uint64_t)(((uint32_t)(2 * j) * PLANE) >> 4);
+                    int ui = 0;
+#pragma unroll
+                    for (int s2 = 0; s2 < NS; ++s2) {
+                        if (orow - s2 >= -1 && orow - s2 <= 1) {
+                            const int dy = orow - s2;
+                            const bool lead = ocol == 0 || ocol == 1;                        // the windows that open a block
+                            const bool pair = NT == 2 && lead;
+                            const int t2 = ocol == 2 ? 1 : 0;                                // single: the one column sub-position
+                            const int tap = pair ? (dy + 1) * 3 + ocol : (dy + 1) * 3 + (ocol - t2) + 1;
+                            const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(((kq * KQ + 2 * j) * 9 + tap) * C_OUT * 16) >> 4);
+                            const uint32_t dt = d_tmem + (uint32_t)((pair ? 2 * s2 : 2 * s2 + (1 - t2)) * C_OUT);
+                            const uint32_t accf = lead ? (((started >> s2) & 1u) | (uint32_t)j) : 1u;
+                            const uint32_t id = pair ? idesc2 : idesc1;
+                            if (nu == 1) umma_bf16_a<0>(dt, ad, bd, id, accf);
+                            else if (ui == 0) umma_bf16_a<1>(dt, ad, bd, id, accf);
+                            else umma_bf16_a<3>(dt, ad, bd, id, accf);
+                            ++ui;
+                        }
+                    }
+                }
+                if (ocol == 0 || ocol == 1) {
+#pragma unroll
+                    for (int s2 = 0; s2 < NS; ++s2)
+                        if (orow - s2 >= -1 && orow - s2 <= 1) started |= 1u << s2;
+                }
+            }
+        }
+    }
+}
+
+template <int C_IN, int C_OUT, int KQ, int STAGES, int BR, int BC, int NBUF, int EW, bool SHARE = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ Pool4Params P) {
-    using Cfg = Pool4Cfg<C_IN, C_OUT, KQ, STAGES, BR, BC, NBUF>;
+    using Cfg = Pool4Cfg<C_IN, C_OUT, KQ, STAGES, BR, BC, NBUF, SHARE>;
     constexpr int kThreads = 64 + 32 * EW;             // EW epilogue warps: NBUF = 2 -> two groups of EW / 2; NBUF = 1 -> EW / 4 channel slices
     static_assert(EW % 4 == 0 && (NBUF == 1 || EW == 8), "epilogue warps");
     constexpr int KCH = Cfg::KCH, NSTEP = Cfg::NSTEP;
@@ -397,7 +469,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         }
     };
     // tiles outside the rows / columns that any anchor of the band uses for this border class are skipped by every role alike
-    auto live = [&]() { return ty * 16 < P.row_n[c / 3] && tx * 8 < P.col_n[c % 3]; };
+    auto live = [&]() { return ty * P.trow[c / 3] < P.row_n[c / 3] && tx * P.tcol[c % 3] < P.col_n[c % 3]; };
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer: all boxes of a step land on one barrier
@@ -415,7 +487,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (!live()) continue;
             const int nbx = cls_s[c].n_boxes;
-            const int row0 = P.row_lo[c / 3] + ty * 16, col0 = P.col_lo[c % 3] + tx * 8;
+            const int row0 = P.row_lo[c / 3] + ty * P.trow[c / 3], col0 = P.col_lo[c % 3] + tx * P.tcol[c % 3];
             for (int kq = 0; kq < NSTEP; ++kq) {
                 mbar_wait(empty_bar(st), ph);
                 if (leader) {
@@ -437,7 +509,6 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         // ------------------------------------------------ MMA issuer
         // The packed weights are [C_in/8][tap][C_out][8]: for one channel chunk the 9 taps are consecutive C_out-row blocks, so a
         // B descriptor that starts at tap t and spans N = 2 * C_out rows covers taps t and t + 1 = (dy, dx) and (dy, dx + 1).
-        constexpr uint32_t idesc1 = umma_idesc_f16(128, C_OUT), idesc2 = umma_idesc_f16(128, 2 * C_OUT);      // fp16 activations and weights
         const bool leader = elect_one();
         mbar_wait(w_bar, 0);
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), 9 * C_OUT * 16, 128);
@@ -452,62 +523,17 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
             mbar_wait(tempty_bar(buf), (use & 1) ^ 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 4 * C_OUT);
             const int16_t* win = cls_s[c].win;
-            uint32_t started = 0;                          // bit s: the accumulator pair of sub-position row s has been written
+            const int ns = SHARE ? cls_s[c].ns : 2, nt = SHARE ? cls_s[c].nt : 2;
+            uint32_t started = 0;                          // bit s: the accumulator blocks of sub-position row s have been written
             for (int kq = 0; kq < NSTEP; ++kq) {
                 mbar_wait(full_bar(st), ph);
                 tc_fence_after();
                 const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * Cfg::STAGE, Cfg::PLANE, SBO_A);
                 if (leader) {
-                    // Window-major issue order with PAIRED sub-positions.  The A window at offset (orow, ocol) from the cell origin
-                    // feeds every (sub-position (s, t), tap (dy, dx)) with s + dy = orow, t + dx = ocol.  For ocol in {0, 1} both
-                    // column sub-positions take part, with the horizontally adjacent taps dx = ocol - 1 (t = 1) and dx = ocol
-                    // (t = 0): ONE instruction with N = 2 * C_out whose B operand spans the two tap blocks and whose accumulator
-                    // spans the column blocks of (s, 1) and (s, 0) — TMEM block of (s, t) = 2 s + (1 - t).  Twice the math per A
-                    // fetch and per instruction issue (an M128 x N128 x K16 instruction is bound by its shared-memory operand
-                    // reads, ~94 clk against a 64-clk math floor; at N = 256 the math takes 128 clk and hides them).  ocol = -1 / 2
-                    // feed one column sub-position each (N = C_out).  Within a row offset the pairs are issued first, so that the
-                    // first write of a tile into both halves of a pair is the same (overwriting) instruction.  Instructions that
-                    // share an A window are issued back to back with A kept in the collector (UTCHMMA ...A_KEEP / A_REUSE).
-#pragma unroll
-                    for (int orow = -1; orow <= 2; ++orow) {
-                        const int s_lo = orow <= 0 ? 0 : (orow == 2 ? 1 : 0), s_hi = orow == -1 ? 0 : 1;      // sub-position rows with a tap dy = orow - s
-                        const int nu = (orow == -1 || orow == 2) ? 1 : 2;
-#pragma unroll
-                        for (int oi = 0; oi < 4; ++oi) {
-                            constexpr int kOcol[4] = {0, 1, -1, 2};
-                            const int ocol = kOcol[oi];
-                            const int o = win[(orow + 1) * 4 + ocol + 1];
-                            if (o >= 0) {
-#pragma unroll
-                                for (int j = 0; j < KQ / 2; ++j) {
-                                    const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)o + (uint64_t)(((uint32_t)(2 * j) * Cfg::PLANE) >> 4);
-                                    int ui = 0;
-#pragma unroll
-                                    for (int s2 = 0; s2 < 2; ++s2) {
-                                        if (s2 >= s_lo && s2 <= s_hi && orow - s2 >= -1 && orow - s2 <= 1) {
-                                            const int dy = orow - s2;
-                                            const bool pair = ocol == 0 || ocol == 1;
-                                            const int t2 = ocol == -1 ? 0 : 1;                               // single: the one column sub-position
-                                            const int tap = pair ? (dy + 1) * 3 + ocol : (dy + 1) * 3 + (ocol - t2) + 1;
-                                            const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(((kq * KQ + 2 * j) * 9 + tap) * C_OUT * 16) >> 4);
-                                            const uint32_t dt = d_tmem + (uint32_t)((pair ? 2 * s2 : 2 * s2 + (1 - t2)) * C_OUT);
-                                            const uint32_t accf = pair ? (((started >> s2) & 1u) | (uint32_t)j) : 1u;
-                                            const uint32_t id = pair ? idesc2 : idesc1;
-                                            if (nu == 1) umma_bf16_a<0>(dt, ad, bd, id, accf);
-                                            else if (ui == 0) umma_bf16_a<1>(dt, ad, bd, id, accf);
-                                            else umma_bf16_a<3>(dt, ad, bd, id, accf);
-                                            ++ui;
-                                        }
-                                    }
-                                }
-                                if (ocol == 0 || ocol == 1) {
-#pragma unroll
-                                    for (int s2 = 0; s2 < 2; ++s2)
-                                        if (s2 >= s_lo && s2 <= s_hi) started |= 1u << s2;
-                                }
-                            }
-                        }
-                    }
+                    if (!SHARE || (ns == 2 && nt == 2)) pool4_issue_step<C_OUT, KQ, Cfg::PLANE, 2, 2>(win, a_desc0, w_desc0, d_tmem, kq, started);
+                    else if (ns == 2) pool4_issue_step<C_OUT, KQ, Cfg::PLANE, 2, 1>(win, a_desc0, w_desc0, d_tmem, kq, started);
+                    else if (nt == 2) pool4_issue_step<C_OUT, KQ, Cfg::PLANE, 1, 2>(win, a_desc0, w_desc0, d_tmem, kq, started);
+                    else pool4_issue_step<C_OUT, KQ, Cfg::PLANE, 1, 1>(win, a_desc0, w_desc0, d_tmem, kq, started);
                     umma_commit(empty_bar(st));
                     if (kq == NSTEP - 1) umma_commit(tfull_bar(buf));
                 }
@@ -524,53 +550,60 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         const int c_lo = NBUF == 2 ? 0 : eg * C_SPAN;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(NBUF == 2 ? eg * 4 * C_OUT : 0);
         const int64_t cstride = (int64_t)P.rows * P.cols * 8;
+        constexpr int NG = C_SPAN / 32;                      // 32-channel groups per thread
+        // SHARE: hand-over of the first cell row of every lane quarter to the quarter above it: [buffer][channel slice][quarter][group][lane 0..7][4] x 16 B
+        uint4* const xchg = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(cls_s) + Cfg::CLS_BYTES);
         int it = -1;                                   // tiles actually processed
+        int it_x = 0;                                  // tiles that used the hand-over
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (!live()) continue;
             ++it;
             if (NBUF == 2 && (it & 1) != eg) continue;
             const int buf = NBUF == 2 ? eg : 0;
             const int use = NBUF == 2 ? (it >> 1) : it;
-            const int row = P.row_lo[c / 3] + ty * 16 + (m >> 3), col = P.col_lo[c % 3] + tx * 8 + (m & 7);
-            const bool valid = row < P.rows && col < P.cols;
+            const int ns = SHARE ? cls_s[c].ns : 2, nt = SHARE ? cls_s[c].nt : 2;
+            const int row = P.row_lo[c / 3] + ty * P.trow[c / 3] + (m >> 3), col = P.col_lo[c % 3] + tx * P.tcol[c % 3] + (m & 7);
+            // a tile that shares a sub-position with its neighbours produces 15 rows / 7 columns: its last row / column only feeds them
+            const bool valid = row < P.rows && col < P.cols && (!SHARE || ((ns == 2 || (m >> 3) < 15) && (nt == 2 || (m & 7) < 7)));
             __nv_bfloat16* const obase =
                 P.out + ((((int64_t)cls_s[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
             mbar_wait(tfull_bar(buf), use & 1);
             tc_fence_after();
             // The packed weights carry sign(BN scale) and P.scale holds |scale|, so max_s relu(scale * z_s + shift) =
-            // relu(|scale| * max_s z'_s + shift): one FMNMX per accumulator value, the affine + ReLU + bf16 rounding once.
-            // Phase 1 reduces the 4 accumulators into registers and hands TMEM back to the MMA warp; phase 2 (affine, ReLU, bf16,
-            // stores) then runs under the next tile's MMAs.
-            constexpr int NG = C_SPAN / 32;                      // 32-channel groups per thread
+            // relu(|scale| * max_s z'_s + shift): one FMNMX per accumulator value, the affine + ReLU + fp16 rounding once.
+            // Phase 1 reduces the accumulators of the tile's own sub-positions (TMEM block of (s, t) = 2 s + 1 - t) into registers and
+            // hands TMEM back to the MMA warp; phase 2 (affine, ReLU, fp16, neighbour maxima, stores) then runs under the next tile's MMAs.
             uint32_t mx[NG][32];
             if (!(P.dbg & 2)) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const int c0 = c_lo + 32 * g;
                     uint32_t m1[32];
-                    tmem_ld32_nowait(t_row + (uint32_t)(0 * C_OUT + c0), mx[g]);
-                    tmem_ld32_nowait(t_row + (uint32_t)(1 * C_OUT + c0), m1);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    auto fold = [&](int blk) {
+                        tmem_ld32_nowait(t_row + (uint32_t)(blk * C_OUT + c0), m1);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) mx[g][k] = __float_as_uint(fmaxf(__uint_as_float(mx[g][k]), __uint_as_float(m1[k])));
-                    tmem_ld32_nowait(t_row + (uint32_t)(2 * C_OUT + c0), m1);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) mx[g][k] = __float_as_uint(fmaxf(__uint_as_float(mx[g][k]), __uint_as_float(m1[k])));
-                    tmem_ld32_nowait(t_row + (uint32_t)(3 * C_OUT + c0), m1);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) mx[g][k] = __float_as_uint(fmaxf(__uint_as_float(mx[g][k]), __uint_as_float(m1[k])));
+                        for (int k = 0; k < 32; ++k) mx[g][k] = __float_as_uint(fmaxf(__uint_as_float(mx[g][k]), __uint_as_float(m1[k])));
+                    };
+                    if (!SHARE || nt == 2) {
+                        tmem_ld32_nowait(t_row + (uint32_t)(0 * C_OUT + c0), mx[g]);
+                        fold(1);
+                    } else {
+                        tmem_ld32_nowait(t_row + (uint32_t)(1 * C_OUT + c0), mx[g]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+                    if (!SHARE || (ns == 2 && nt == 2)) fold(2);
+                    if (!SHARE || ns == 2) fold(3);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
             if (!(P.dbg & 2)) {
+                uint32_t pk[NG][16];
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const int c0 = c_lo + 32 * g;
-                    uint32_t pk[16];
                     const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
                     const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
 #pragma unroll
@@ -580,15 +613,51 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
                         const float a1 = fmaf(__uint_as_float(mx[g][4 * k + 1]), sc.y, sh.y);
                         const float a2 = fmaf(__uint_as_float(mx[g][4 * k + 2]), sc.z, sh.z);
                         const float a3 = fmaf(__uint_as_float(mx[g][4 * k + 3]), sc.w, sh.w);
-                        pk[2 * k] = pack_f16x2_relu(a0, a1);              // ReLU + saturating fp16 rounding: one F2FP
-                        pk[2 * k + 1] = pack_f16x2_relu(a2, a3);
+                        pk[g][2 * k] = pack_f16x2_relu(a0, a1);              // ReLU + saturating fp16 rounding: one F2FP
+                        pk[g][2 * k + 1] = pack_f16x2_relu(a2, a3);
                     }
-                    if (valid) {
+                }
+                if (SHARE && nt == 1) {                                      // the next cell's column (lane + 1; column 7 has none: not stored)
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) pk[g][k] = max_f16x2(pk[g][k], __shfl_down_sync(0xffffffffu, pk[g][k], 1));
+                }
+                if (SHARE && ns == 1) {                                      // the next cell's row: lane + 8, or the first row of the quarter above
+                    uint4* const xw = xchg + (size_t)(((it_x & 1) * (EW / 4) + eg) * 4 + q) * (NG * 32);
+                    ++it_x;
+                    if (lane < 8) {
+#pragma unroll
+                        for (int g = 0; g < NG; ++g)
+#pragma unroll
+                            for (int s4 = 0; s4 < 4; ++s4)
+                                xw[(g * 8 + lane) * 4 + s4] = make_uint4(pk[g][4 * s4], pk[g][4 * s4 + 1], pk[g][4 * s4 + 2], pk[g][4 * s4 + 3]);
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+                    const uint4* const xr = xw + NG * 32;                  // quarter q + 1 of the same channel slice
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        uint32_t up[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) up[k] = __shfl_down_sync(0xffffffffu, pk[g][k], 8);
+                        if (lane >= 24 && q < 3) {
+#pragma unroll
+                            for (int s4 = 0; s4 < 4; ++s4) {
+                                const uint4 v = xr[(g * 8 + lane - 24) * 4 + s4];
+                                up[4 * s4] = v.x; up[4 * s4 + 1] = v.y; up[4 * s4 + 2] = v.z; up[4 * s4 + 3] = v.w;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) pk[g][k] = max_f16x2(pk[g][k], up[k]);
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
 #pragma unroll
                         for (int s4 = 0; s4 < 4; ++s4)
-                            *reinterpret_cast<uint4*>(obase + ((c0 >> 3) + s4) * cstride) =
-                                make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
-                    }
+                            *reinterpret_cast<uint4*>(obase + (((c_lo + 32 * g) >> 3) + s4) * cstride) =
+                                make_uint4(pk[g][4 * s4], pk[g][4 * s4 + 1], pk[g][4 * s4 + 2], pk[g][4 * s4 + 3]);
                 }
             }
         }
