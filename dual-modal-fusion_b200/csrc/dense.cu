@@ -448,6 +448,8 @@ static int build_pool4_cls(tc::Pool4Cls& c, int a, int b, bool aligned, int box_
     // stride-1 pooling, interior class on an axis: sub-position 1 of a cell IS sub-position 0 of the next cell -> evaluated once (dense_tc.cuh, SHARE)
     c.ns = (int16_t)(!aligned && a == 1 ? 1 : 2);
     c.nt = (int16_t)(!aligned && b == 1 ? 1 : 2);
+    c.ca = (int16_t)a;
+    c.cb = (int16_t)b;
     for (int i = 0; i < nr; ++i)
         for (int j = 0; j < nc; ++j) {
             const int k = i * nc + j;
@@ -498,11 +500,13 @@ static int launch_pool4(const CUtensorMap& map, const __nv_bfloat16* w, const fl
     P.w = w; P.scale = scale; P.shift = shift; P.out = out;
     static const int dbg = getenv("DMF_DENSE_DBG") ? atoi(getenv("DMF_DENSE_DBG")) : 0;      // timing diagnostics (results are wrong when set)
     P.dbg = dbg;
-    for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) {
-            DMF_TRY(build_pool4_cls(P.cls[a * 3 + b], a, b, aligned, BR, BC, Cfg::MAX_BOXES, Cfg::BOX_SLOT));
-            if (!SHARE) P.cls[a * 3 + b].ns = P.cls[a * 3 + b].nt = 2;
-        }
+    // table order: interior / interior (1 TMEM slot per tile), the four classes with one interior axis (2 slots), the corners (4): tiles
+    // of equal size follow each other, so that the slot ring keeps two or more of the small ones in flight
+    static const int kOrder[9] = {4, 1, 7, 3, 5, 0, 2, 6, 8};
+    for (int i = 0; i < 9; ++i) {
+        DMF_TRY(build_pool4_cls(P.cls[i], kOrder[i] / 3, kOrder[i] % 3, aligned, BR, BC, Cfg::MAX_BOXES, Cfg::BOX_SLOT));
+        if (!SHARE) P.cls[i].ns = P.cls[i].nt = 2;
+    }
     auto kern = tc::conv_pool4_kernel<CI, CO, KQ, STAGES, BR, BC, NBUF, EW, SHARE>;
     static bool attr_set = false;
     if (!attr_set) {

@@ -321,6 +321,7 @@ struct Pool4Cls {
     int8_t box_drow[kP4MaxBoxes], box_dcol[kP4MaxBoxes];
     int16_t win[16];                      // [row offset + 1][col offset + 1]: (byte offset of that A window inside a stage) >> 4, or -1 = outside the patch
     int16_t ns, nt;                       // sub-position rows / columns the tile evaluates itself: 2, or 1 = shared with the neighbouring cell (see below)
+    int16_t ca, cb;                       // row / column border class (the table is walked in an order that keeps equal tile sizes together)
 };
 
 struct Pool4Params {
@@ -349,7 +350,7 @@ struct Pool4Cfg {
     static constexpr uint32_t WBYTES = 9u * C_IN * C_OUT * 2;
     static constexpr uint32_t CLS_BYTES = (9 * sizeof(Pool4Cls) + 15) / 16 * 16;
     static constexpr uint32_t XCHG = SHARE ? 2u * 64u * C_OUT : 0u;         // 2 buffers x 8 lanes x C_OUT channels x fp16 x 4 lane quarters
-    static constexpr size_t SMEM = WBYTES + (size_t)STAGES * STAGE + 2 * C_OUT * 4 + (2 * STAGES + 8) * 8 + CLS_BYTES + XCHG;
+    static constexpr size_t SMEM = WBYTES + (size_t)STAGES * STAGE + 2 * C_OUT * 4 + (2 * STAGES + 12) * 8 + CLS_BYTES + XCHG;
     static_assert(KCH % KQ == 0 && KQ % 2 == 0 && NBUF * 4 * C_OUT <= 512 && WBYTES % 128 == 0 && (!SHARE || NBUF == 1), "pool4 configuration");
 };
 
@@ -358,7 +359,7 @@ struct Pool4Cfg {
 // column sub-positions.  The A window at offset (orow, ocol) from the cell origin feeds every (sub-position (s, t), tap (dy, dx)) with
 // s + dy = orow, t + dx = ocol.  NT = 2: for ocol in {0, 1} both column sub-positions take part, with the horizontally adjacent taps
 // dx = ocol - 1 (t = 1) and dx = ocol (t = 0): ONE instruction with N = 2 * C_out whose B operand spans the two tap blocks and whose
-// accumulator spans the column blocks of (s, 1) and (s, 0) — TMEM block of (s, t) = 2 s + (1 - t).  Twice the math per A fetch and per
+// accumulator spans the column blocks of (s, 1) and (s, 0) — TMEM block of (s, t) = 2 s + (1 - t) (NT = 1: block s).  Twice the math per A fetch and per
 // instruction issue (an M128 x N128 x K16 instruction is bound by its shared-memory operand reads, ~94 clk against a 64-clk math
 // floor; at N = 256 the math takes 128 clk and hides them).  ocol = -1 / 2 feed one column sub-position each (N = C_out).  Within a
 // row offset the windows ocol = 0, 1 are issued first, so that the first write of a tile into a block (both halves of a pair) is an
@@ -391,7 +392,7 @@ __device__ __forceinline__ void pool4_issue_step(const int16_t* win, uint64_t a_
                             const int t2 = ocol == 2 ? 1 : 0;                                // single: the one column sub-position
                             const int tap = pair ? (dy + 1) * 3 + ocol : (dy + 1) * 3 + (ocol - t2) + 1;
                             const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(((kq * KQ + 2 * j) * 9 + tap) * C_OUT * 16) >> 4);
-                            const uint32_t dt = d_tmem + (uint32_t)((pair ? 2 * s2 : 2 * s2 + (1 - t2)) * C_OUT);
+                            const uint32_t dt = d_tmem + (uint32_t)((pair ? 2 * s2 : NT * s2 + (NT == 2 ? 1 - t2 : 0)) * C_OUT);   // block of (s, t) = NT s + (NT - 1)(1 - t)
                             const uint32_t accf = lead ? (((started >> s2) & 1u) | (uint32_t)j) : 1u;
                             const uint32_t id = pair ? idesc2 : idesc1;
                             if (nu == 1) umma_bf16_a<0>(dt, ad, bd, id, accf);
@@ -425,9 +426,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
     float* scale_s = reinterpret_cast<float*>(a_s + (size_t)STAGES * Cfg::STAGE);
     float* shift_s = scale_s + C_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
-    // bars: [0,S) full; [S,2S) empty; 2S weights; 2S+1.. tmem_full[NBUF]; 2S+3.. tmem_empty[NBUF]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
-    Pool4Cls* cls_s = reinterpret_cast<Pool4Cls*>(bars + 2 * STAGES + 8);
+    // bars: [0,S) full; [S,2S) empty; 2S weights; 2S+1.. tmem_full[4]; 2S+5.. tmem_empty[4]   (NBUF = 2 uses two of each)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
+    Pool4Cls* cls_s = reinterpret_cast<Pool4Cls*>(bars + 2 * STAGES + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -435,7 +436,16 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     const uint32_t w_bar = bar0 + 8u * (2 * STAGES);
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 1 + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 3 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 5 + a); };
+    // NBUF = 1: TMEM is a ring of 4 slots of C_OUT columns; a tile takes ns * nt (1, 2 or 4) slots, aligned to its size, so the
+    // tiles that share sub-positions with their neighbours leave room for the next tile's MMAs while they are drained.
+    constexpr int kSlots = NBUF == 1 ? 4 : NBUF;
+    auto take_slots = [](int& ring, int n) {
+        int b = (ring + n - 1) & ~(n - 1);
+        if (b + n > 4) b = 0;
+        ring = (b + n) & 3;
+        return b;
+    };
 
     for (int i = threadIdx.x; i < C_OUT; i += kThreads) {
         scale_s[i] = P.scale[i];
@@ -446,7 +456,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
-        for (int a = 0; a < NBUF; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NBUF == 2 ? 4 : EW); }
+        for (int a = 0; a < kSlots; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NBUF == 2 ? 4 : EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -469,7 +479,10 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         }
     };
     // tiles outside the rows / columns that any anchor of the band uses for this border class are skipped by every role alike
-    auto live = [&]() { return ty * P.trow[c / 3] < P.row_n[c / 3] && tx * P.tcol[c % 3] < P.col_n[c % 3]; };
+    auto live = [&]() {
+        const int a = cls_s[c].ca, b = cls_s[c].cb;
+        return ty * P.trow[a] < P.row_n[a] && tx * P.tcol[b] < P.col_n[b];
+    };
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer: all boxes of a step land on one barrier
@@ -487,7 +500,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (!live()) continue;
             const int nbx = cls_s[c].n_boxes;
-            const int row0 = P.row_lo[c / 3] + ty * P.trow[c / 3], col0 = P.col_lo[c % 3] + tx * P.tcol[c % 3];
+            const int ca = cls_s[c].ca, cb = cls_s[c].cb;
+            const int row0 = P.row_lo[ca] + ty * P.trow[ca], col0 = P.col_lo[cb] + tx * P.tcol[cb];
             for (int kq = 0; kq < NSTEP; ++kq) {
                 mbar_wait(empty_bar(st), ph);
                 if (leader) {
@@ -515,15 +529,26 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         int st = 0;
         uint32_t ph = 0;
         int it = 0;                                    // tiles actually processed
+        int ring = 0;                                  // NBUF = 1: next free TMEM slot
+        uint32_t eph = 0;                              // NBUF = 1: phase bit of every slot's tmem_empty barrier
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (!live()) continue;
-            const int buf = NBUF == 2 ? (it & 1) : 0;
-            const int use = NBUF == 2 ? (it >> 1) : it;
-            ++it;
-            mbar_wait(tempty_bar(buf), (use & 1) ^ 1);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 4 * C_OUT);
-            const int16_t* win = cls_s[c].win;
             const int ns = SHARE ? cls_s[c].ns : 2, nt = SHARE ? cls_s[c].nt : 2;
+            int buf;
+            uint32_t d_tmem;
+            if (NBUF == 2) {
+                buf = it & 1;
+                mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
+                d_tmem = tmem_base + (uint32_t)(buf * 4 * C_OUT);
+            } else {
+                const int n = ns * nt;
+                buf = take_slots(ring, n);
+                for (int k = buf; k < buf + n; ++k) mbar_wait(tempty_bar(k), ((eph >> k) & 1u) ^ 1u);
+                eph ^= ((1u << n) - 1u) << buf;
+                d_tmem = tmem_base + (uint32_t)(buf * C_OUT);
+            }
+            ++it;
+            const int16_t* win = cls_s[c].win;
             uint32_t started = 0;                          // bit s: the accumulator blocks of sub-position row s have been written
             for (int kq = 0; kq < NSTEP; ++kq) {
                 mbar_wait(full_bar(st), ph);
@@ -548,31 +573,40 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         const int m = q * 32 + lane;
         constexpr int C_SPAN = NBUF == 2 ? C_OUT : C_OUT / (EW / 4);
         const int c_lo = NBUF == 2 ? 0 : eg * C_SPAN;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(NBUF == 2 ? eg * 4 * C_OUT : 0);
+        const uint32_t t_row0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(NBUF == 2 ? eg * 4 * C_OUT : 0);
         const int64_t cstride = (int64_t)P.rows * P.cols * 8;
         constexpr int NG = C_SPAN / 32;                      // 32-channel groups per thread
         // SHARE: hand-over of the first cell row of every lane quarter to the quarter above it: [buffer][channel slice][quarter][group][lane 0..7][4] x 16 B
         uint4* const xchg = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(cls_s) + Cfg::CLS_BYTES);
         int it = -1;                                   // tiles actually processed
         int it_x = 0;                                  // tiles that used the hand-over
+        int ring = 0;                                  // NBUF = 1: next free TMEM slot
+        uint32_t fph = 0;                              // NBUF = 1: phase bit of every slot's tmem_full barrier
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (!live()) continue;
             ++it;
             if (NBUF == 2 && (it & 1) != eg) continue;
-            const int buf = NBUF == 2 ? eg : 0;
-            const int use = NBUF == 2 ? (it >> 1) : it;
             const int ns = SHARE ? cls_s[c].ns : 2, nt = SHARE ? cls_s[c].nt : 2;
-            const int row = P.row_lo[c / 3] + ty * P.trow[c / 3] + (m >> 3), col = P.col_lo[c % 3] + tx * P.tcol[c % 3] + (m & 7);
+            const int nblk = ns * nt;                  // accumulator blocks of this tile, consecutive in TMEM
+            const int buf = NBUF == 2 ? eg : take_slots(ring, nblk);
+            const uint32_t t_row = t_row0 + (uint32_t)(NBUF == 2 ? 0 : buf * C_OUT);
+            const int ca = cls_s[c].ca, cb = cls_s[c].cb;
+            const int row = P.row_lo[ca] + ty * P.trow[ca] + (m >> 3), col = P.col_lo[cb] + tx * P.tcol[cb] + (m & 7);
             // a tile that shares a sub-position with its neighbours produces 15 rows / 7 columns: its last row / column only feeds them
             const bool valid = row < P.rows && col < P.cols && (!SHARE || ((ns == 2 || (m >> 3) < 15) && (nt == 2 || (m & 7) < 7)));
             __nv_bfloat16* const obase =
                 P.out + ((((int64_t)cls_s[c].out_plane * P.out_chunks + P.out_chunk0) * P.rows + row) * P.cols + col) * 8;
-            mbar_wait(tfull_bar(buf), use & 1);
+            if (NBUF == 2) {
+                mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+            } else {
+                mbar_wait(tfull_bar(buf), (fph >> buf) & 1u);
+                fph ^= 1u << buf;
+            }
             tc_fence_after();
             // The packed weights carry sign(BN scale) and P.scale holds |scale|, so max_s relu(scale * z_s + shift) =
             // relu(|scale| * max_s z'_s + shift): one FMNMX per accumulator value, the affine + ReLU + fp16 rounding once.
-            // Phase 1 reduces the accumulators of the tile's own sub-positions (TMEM block of (s, t) = 2 s + 1 - t) into registers and
-            // hands TMEM back to the MMA warp; phase 2 (affine, ReLU, fp16, neighbour maxima, stores) then runs under the next tile's MMAs.
+            // Phase 1 reduces the accumulator blocks of the tile's own sub-positions into registers and hands their TMEM slots back
+            // to the MMA warp; phase 2 (affine, ReLU, fp16, neighbour maxima, stores) then runs under the next tiles' MMAs.
             uint32_t mx[NG][32];
             if (!(P.dbg & 2)) {
 #pragma unroll
@@ -585,20 +619,27 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
 #pragma unroll
                         for (int k = 0; k < 32; ++k) mx[g][k] = __float_as_uint(fmaxf(__uint_as_float(mx[g][k]), __uint_as_float(m1[k])));
                     };
-                    if (!SHARE || nt == 2) {
-                        tmem_ld32_nowait(t_row + (uint32_t)(0 * C_OUT + c0), mx[g]);
+                    tmem_ld32_nowait(t_row + (uint32_t)c0, mx[g]);
+                    if (!SHARE || nblk >= 2) {
                         fold(1);
                     } else {
-                        tmem_ld32_nowait(t_row + (uint32_t)(1 * C_OUT + c0), mx[g]);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     }
-                    if (!SHARE || (ns == 2 && nt == 2)) fold(2);
-                    if (!SHARE || ns == 2) fold(3);
+                    if (!SHARE || nblk == 4) {
+                        fold(2);
+                        fold(3);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (lane == 0) {
+                if (NBUF == 2) {
+                    mbar_arrive(tempty_bar(buf));
+                } else {
+                    for (int k = buf; k < buf + nblk; ++k) mbar_arrive(tempty_bar(k));
+                }
+            }
             if (!(P.dbg & 2)) {
                 uint32_t pk[NG][16];
 #pragma unroll
