@@ -428,13 +428,14 @@ def main():
         band = max(1, min(args.band, rows1 - rows0))
         bands = [min(band, rows1 - b) for b in range(rows0, rows1, band)]
         pos = sum((nb + P - 1) * (Wd + P - 1) for nb in bands)                 # MS-resolution map positions of the bands
-        def taps(nb, cells, step_):
+        def taps(nb, cells, step_, shared=True):
             """tap evaluations of one conv + pool layer over a band: per border class only the rows / columns some anchor uses"""
-            tr = (5, 3, 5) if step_ == 2 else (5, 6, 5)                       # live tap rows (columns) evaluated per border class
+            tr = (5, 3, 5) if step_ == 2 and shared else (5, 6, 5)            # live tap rows (columns) evaluated per border class
             ext = (0, step_ * (cells - 3), 0)
             return sum(t * (nb + e) for t, e in zip(tr, ext)) * sum(t * (Wd + e) for t, e in zip(tr, ext))
 
         fl_s1 = sum(taps(nb, P // 2, 2) for nb in bands) * 2 * 64 * 128       # ms2, pan3: p/2 pooled cells at x + 2k
+        fl_s1_unshared = sum(taps(nb, P // 2, 2, shared=False) for nb in bands) * 2 * 64 * 128
         fl_al = sum(taps(nb, P, 1) for nb in bands) * 2 * 32 * 64             # pan2: p pooled cells at x + k
         fl_fu = sum(3 * nb + P - 6 for nb in bands) * 3 * (Wd + P - 1) * 2 * 256 * 128
         kernels = {   # kernel -> (stage keys, FLOPs executed over all bands, launches per band)
@@ -456,6 +457,12 @@ def main():
                 'flops_per_launch': fl_k / (len(bands) * per_band),
                 'stage_ms': {k: round(v, 3) for k, v in stage.items()},
                 'map_positions': pos, 'flops_executed_per_pixel': conv_fl / n_loc,
+                'stride1_layers': {'executed_TFLOPs': 2 * fl_s1 / ((stage['conv_ms2'] + stage['conv_pan3']) / 1e3) / 1e12,
+                                   'unshared_equivalent_TFLOPs': 2 * fl_s1_unshared / ((stage['conv_ms2'] + stage['conv_pan3']) / 1e3) / 1e12,
+                                   'note': 'ms2 + pan3: the cells of an interior border class share sub-positions with their neighbours (169 tap '
+                                           'evaluations per position instead of 256, dense_tc.cuh SHARE).  executed = what the tensor pipe does '
+                                           '(this is `achieved` when these layers dominate); unshared_equivalent = the same results at 256 per '
+                                           'position / the same time, comparable with the lines before the sharing (profiles/r02_bench_before_sharing.json)'},
                 'whole_step_executed_TFLOPs': conv_fl / (stage['total'] / 1e3) / 1e12,
                 'per_patch_equivalent_tflops': h.flops_per_patch * n_loc / (stage['total'] / 1e3) / 1e12,
                 'note': 'achieved = tensor-core FLOPs this kernel executes / its time (one isolated pass with per-stage events); '
