@@ -366,7 +366,7 @@ struct Pool4Cfg {
 // overwriting instruction.  Instructions that share an A window are issued back to back with A kept in the collector (UTCHMMA
 // ...A_KEEP / A_REUSE).  NT = 1: t = 0 only, every window feeds one N = C_out instruction; NS = 1: s = 0 only.
 template <int C_OUT, int KQ, uint32_t PLANE, int NS, int NT>
-__device__ __forceinline__ void pool4_issue_step(const int16_t* win, uint64_t a_desc0, uint64_t w_desc0, uint32_t d_tmem, int kq, uint32_t& started) {
+__device__ __forceinline__ void pool4_issue_step(const int (&win)[16], uint64_t a_desc0, uint64_t w_desc0, uint32_t d_tmem, int kq, uint32_t& started) {
     constexpr uint32_t idesc1 = umma_idesc_f16(128, C_OUT), idesc2 = umma_idesc_f16(128, 2 * C_OUT);      // fp16 activations and weights
 #pragma unroll
     for (int orow = -1; orow <= NS; ++orow) {
@@ -548,7 +548,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
                 d_tmem = tmem_base + (uint32_t)(buf * C_OUT);
             }
             ++it;
-            const int16_t* win = cls_s[c].win;
+            int win[16];                                   // window table of the class in registers: no shared-memory load on the issue path
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t w2 = reinterpret_cast<const uint32_t*>(cls_s[c].win)[k];
+                win[2 * k] = (int)(int16_t)(w2 & 0xffffu);
+                win[2 * k + 1] = (int)(int16_t)(w2 >> 16);
+            }
             uint32_t started = 0;                          // bit s: the accumulator blocks of sub-position row s have been written
             for (int kq = 0; kq < NSTEP; ++kq) {
                 mbar_wait(full_bar(st), ph);
