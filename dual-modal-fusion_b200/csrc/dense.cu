@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restri
             nb[k] = (xx >= 0 && xx < Hp && yy >= 0 && yy < Wp) ? __ldg(ms + (int64_t)xx * Wp + yy) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         uint32_t out[9][4];
+        float even[9];                       // affine results of the even channel of a pair: ReLU + fp16 rounding + packing is ONE F2FP per pair
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float t[9], s[9];
@@ -93,10 +94,9 @@ __global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restri
             masked_sums(t, s);
 #pragma unroll
             for (int v = 0; v < 9; ++v) {
-                const float y = fmaxf(fmaf(s[v], sc_s[j], sh_s[j]), 0.f);
-                const uint32_t b = tc::f16_bits(y);
-                if (j & 1) out[v][j >> 1] |= b << 16;
-                else out[v][j >> 1] = b;
+                const float y = fmaf(s[v], sc_s[j], sh_s[j]);
+                if (j & 1) out[v][j >> 1] = tc::pack_f16x2_relu(even[v], y);
+                else even[v] = y;
             }
         }
         uint4* o = reinterpret_cast<uint4*>(A) + ((int64_t)ch * R1 + Xl) * C1 + Y;
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(256, 2) pan_stem_map_kernel(const float* __res
 #pragma unroll
             for (int pc = 0; pc < 2; ++pc) {
                 uint32_t out[4][4];      // [edge/interior row variant][edge/interior column variant] -> 8 packed channels
+                float even[4];           // affine results of the even channel of a pair: ReLU + fp16 rounding + packing is ONE F2FP per pair
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     // sv[a][b][re][ce]: conv position (a, b) of this pooled cell with its row (column) taps masked as on the patch edge
@@ -171,9 +172,9 @@ __global__ void __launch_bounds__(256, 2) pan_stem_map_kernel(const float* __res
                             const int r0e = (er == 0 && pr == 0) ? 0 : 1, r1e = (er == 0 && pr == 1) ? 0 : 1;
                             const int c0e = (ec == 0 && pc == 0) ? 0 : 1, c1e = (ec == 0 && pc == 1) ? 0 : 1;
                             const float m = fmaxf(fmaxf(sv[0][0][r0e][c0e], sv[0][1][r0e][c1e]), fmaxf(sv[1][0][r1e][c0e], sv[1][1][r1e][c1e]));
-                            const uint32_t bits = tc::f16_bits(fmaxf(fmaf(m, sc_s[j], sh_s[j]), 0.f));
-                            if (j & 1) out[er * 2 + ec][j >> 1] |= bits << 16;
-                            else out[er * 2 + ec][j >> 1] = bits;
+                            const float y = fmaf(m, sc_s[j], sh_s[j]);
+                            if (j & 1) out[er * 2 + ec][j >> 1] = tc::pack_f16x2_relu(even[er * 2 + ec], y);
+                            else even[er * 2 + ec] = y;
                         }
                 }
                 uint4* o = reinterpret_cast<uint4*>(B1) + (((int64_t)(pr * 2 + pc) * 4 + ch) * R1 + Il) * C1 + J;
