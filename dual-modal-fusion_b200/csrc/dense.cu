@@ -63,19 +63,19 @@ __device__ __forceinline__ void masked_sums(const float (&t)[9], float (&s)[9]) 
 }
 
 // MS stem (conv3x3 4->64 + BN + ReLU) at every position of the band: ms = padded scene [Hp][Wp] float4, band-local
-// row Xl <-> scene row r0 + Xl.  w: fp32 [64][4][3][3].  grid.y = channel chunk.  out: A[9][8][R1][C1][8].
-__global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restrict__ ms, int Hp, int Wp, int r0, int rows, int R1, int C1,
+// row Xl <-> scene row r0 + Xl.  w: fp32 [64][4][3][3].  out: A[9][8][R1][C1][8].  One thread = one position, ALL 8 channel chunks: the 3x3
+// neighbourhood (9 float4 loads, bounds tests, index arithmetic: more than half of the instructions of a one-chunk thread) is fetched once.
+__global__ void __launch_bounds__(256, 2) ms_stem_map_kernel(const float4* __restrict__ ms, int Hp, int Wp, int r0, int rows, int R1, int C1,
                                                           const float* __restrict__ w, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ A) {
-    __shared__ float w_s[8][36], sc_s[8], sh_s[8];
-    const int ch = blockIdx.y;
-    for (int i = threadIdx.x; i < 8 * 36; i += blockDim.x) w_s[i / 36][i % 36] = w[ch * 8 * 36 + i];
-    if (threadIdx.x < 8) { sc_s[threadIdx.x] = scale[ch * 8 + threadIdx.x]; sh_s[threadIdx.x] = shift[ch * 8 + threadIdx.x]; }
+    __shared__ float w_s[C_MS1][36], sc_s[C_MS1], sh_s[C_MS1];
+    for (int i = threadIdx.x; i < C_MS1 * 36; i += blockDim.x) w_s[i / 36][i % 36] = w[i];
+    if (threadIdx.x < C_MS1) { sc_s[threadIdx.x] = scale[threadIdx.x]; sh_s[threadIdx.x] = shift[threadIdx.x]; }
     __syncthreads();
-    const int64_t total = (int64_t)rows * C1;
+    const int total = rows * C1;                       // <= 4111 x (W + 31): fits 32 bits
     const int64_t plane = (int64_t)R1 * C1;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int Xl = (int)(i / C1), Y = (int)(i % C1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int Xl = i / C1, Y = i - Xl * C1;
         const int X = r0 + Xl;
         float4 nb[9];
 #pragma unroll
@@ -83,49 +83,53 @@ __global__ void __launch_bounds__(256) ms_stem_map_kernel(const float4* __restri
             const int xx = X + k / 3 - 1, yy = Y + k % 3 - 1;
             nb[k] = (xx >= 0 && xx < Hp && yy >= 0 && yy < Wp) ? __ldg(ms + (int64_t)xx * Wp + yy) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        uint32_t out[9][4];
-        float even[9];                       // affine results of the even channel of a pair: ReLU + fp16 rounding + packing is ONE F2FP per pair
+        uint4* o = reinterpret_cast<uint4*>(A) + (int64_t)Xl * C1 + Y;
+#pragma unroll 1
+        for (int ch = 0; ch < C_MS1 / 8; ++ch, o += plane) {
+            uint32_t out[9][4];
+            float even[9];                   // affine results of the even channel of a pair: ReLU + fp16 rounding + packing is ONE F2FP per pair
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float t[9], s[9];
+            for (int j = 0; j < 8; ++j) {
+                const float* wj = w_s[ch * 8 + j];          // [band][k]
+                const float sc = sc_s[ch * 8 + j], sh = sh_s[ch * 8 + j];
+                float t[9], s[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k)      // weight index [j][band][k]
-                t[k] = fmaf(nb[k].w, w_s[j][27 + k], fmaf(nb[k].z, w_s[j][18 + k], fmaf(nb[k].y, w_s[j][9 + k], nb[k].x * w_s[j][k])));
-            masked_sums(t, s);
+                for (int k = 0; k < 9; ++k)
+                    t[k] = fmaf(nb[k].w, wj[27 + k], fmaf(nb[k].z, wj[18 + k], fmaf(nb[k].y, wj[9 + k], nb[k].x * wj[k])));
+                masked_sums(t, s);
 #pragma unroll
-            for (int v = 0; v < 9; ++v) {
-                const float y = fmaf(s[v], sc_s[j], sh_s[j]);
-                if (j & 1) out[v][j >> 1] = tc::pack_f16x2_relu(even[v], y);
-                else even[v] = y;
+                for (int v = 0; v < 9; ++v) {
+                    const float y = fmaf(s[v], sc, sh);
+                    if (j & 1) out[v][j >> 1] = tc::pack_f16x2_relu(even[v], y);
+                    else even[v] = y;
+                }
             }
-        }
-        uint4* o = reinterpret_cast<uint4*>(A) + ((int64_t)ch * R1 + Xl) * C1 + Y;
 #pragma unroll
-        for (int v = 0; v < 9; ++v) o[(int64_t)v * 8 * plane] = make_uint4(out[v][0], out[v][1], out[v][2], out[v][3]);
+            for (int v = 0; v < 9; ++v) o[(int64_t)v * 8 * plane] = make_uint4(out[v][0], out[v][1], out[v][2], out[v][3]);
+        }
     }
 }
 
 // PAN stem (conv3x3 1->32 + BN + ReLU + maxpool2) on the pooled-once grid (2 cells per pixel and axis; the pooling grid is aligned to
 // every patch origin because 4x is even).  One thread = the 2 x 2 pooled cells of one pixel (I, J) = all four (row, column) parity
-// phases, one 6 x 6 window of PAN, 8 channels.  A cell on an even pooled row can only be the FIRST pooled row of a patch (u = 0) or an
+// phases, one 6 x 6 window of PAN (fetched once), all 4 channel chunks in turn.  A cell on an even pooled row can only be the FIRST pooled row of a patch (u = 0) or an
 // interior one, a cell on an odd row only the LAST (u = 2p-1) or interior; columns likewise: 2 x 2 of the 9 border variants exist per
 // phase, the others are never read (conv_pool4_kernel's class table) and are neither computed nor stored.  "First" masks the dy = -1
 // taps of the cell's upper conv row, "last" the dy = +1 taps of its lower one; everything is static per phase.  BN after the max: the
 // weights carry sign(scale), sc_s holds |scale| (max commutes with a non-negative scale).
-// w: fp32 [32][1][3][3].  grid.y = channel chunk.  out: B1[9][phase 4][4][R1][C1][8], PHASE-SEPARATED: pooled cell (U, V) is stored at
+// w: fp32 [32][1][3][3].  out: B1[9][phase 4][4][R1][C1][8], PHASE-SEPARATED: pooled cell (U, V) is stored at
 // (U >> 1, V >> 1) of phase plane (U & 1) * 2 + (V & 1).  i0 = first pixel row of the band, rows = pixel rows to produce.
 __global__ void __launch_bounds__(256, 2) pan_stem_map_kernel(const float* __restrict__ pan, int H4p, int W4p, int pitch, int i0, int rows,
                                                            int R1, int C1, const float* __restrict__ w, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ B1) {
-    __shared__ float w_s[8][9], sc_s[8], sh_s[8];
-    const int ch = blockIdx.y;
-    for (int i = threadIdx.x; i < 72; i += blockDim.x) w_s[i / 9][i % 9] = scale[ch * 8 + i / 9] < 0.f ? -w[ch * 72 + i] : w[ch * 72 + i];
-    if (threadIdx.x < 8) { sc_s[threadIdx.x] = fabsf(scale[ch * 8 + threadIdx.x]); sh_s[threadIdx.x] = shift[ch * 8 + threadIdx.x]; }
+    __shared__ float w_all[C_PAN1][9], sc_all[C_PAN1], sh_all[C_PAN1];
+    for (int i = threadIdx.x; i < C_PAN1 * 9; i += blockDim.x) w_all[i / 9][i % 9] = scale[i / 9] < 0.f ? -w[i] : w[i];
+    if (threadIdx.x < C_PAN1) { sc_all[threadIdx.x] = fabsf(scale[threadIdx.x]); sh_all[threadIdx.x] = shift[threadIdx.x]; }
     __syncthreads();
-    const int64_t total = (int64_t)rows * C1;
+    const int total = rows * C1;                       // fits 32 bits (see ms_stem_map_kernel)
     const int64_t plane = (int64_t)R1 * C1;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int Il = (int)(i / C1), J = (int)(i % C1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int Il = i / C1, J = i - Il * C1;
         const int I = i0 + Il;
         float xw[6][6];                  // PAN rows 4I-1 .. 4I+4, cols 4J-1 .. 4J+4
 #pragma unroll
@@ -135,6 +139,10 @@ __global__ void __launch_bounds__(256, 2) pan_stem_map_kernel(const float* __res
                 const int xx = 4 * I - 1 + a, yy = 4 * J - 1 + b;
                 xw[a][b] = (xx >= 0 && xx < H4p && yy >= 0 && yy < W4p) ? __ldg(pan + (int64_t)xx * pitch + yy) : 0.f;
             }
+#pragma unroll 1
+        for (int ch = 0; ch < C_PAN1 / 8; ++ch) {
+        const float (*w_s)[9] = w_all + ch * 8;
+        const float *sc_s = sc_all + ch * 8, *sh_s = sh_all + ch * 8;
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
@@ -186,6 +194,7 @@ __global__ void __launch_bounds__(256, 2) pan_stem_map_kernel(const float* __res
                         o[(int64_t)v * 16 * plane] = make_uint4(out[er * 2 + ec][0], out[er * 2 + ec][1], out[er * 2 + ec][2], out[er * 2 + ec][3]);
                     }
             }
+        }
     }
 }
 
@@ -639,7 +648,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
         evi = 0;
         mark();
         // ---- MS branch
-        ms_stem_map_kernel<<<dim3(grid_for((int64_t)rows * C1, 256, 8), C_MS1 / 8), 256, 0, st>>>(
+        ms_stem_map_kernel<<<grid_for((int64_t)rows * C1, 256, 8), 256, 0, st>>>(
             reinterpret_cast<const float4*>(s->ms), s->Hp, s->Wp, b0, rows, R1, C1, d->w_ms1, n->L[4].scale, n->L[4].shift, d->A);
         DMF_LAUNCHED();
         mark();
@@ -650,7 +659,7 @@ int dense_infer(dmf_net* n, const dmf_scene* s, int row0, int row1, float* logit
         mark();
         mark();          // (stage slot of the former separate pooling pass)
         // ---- PAN branch
-        pan_stem_map_kernel<<<dim3(grid_for((int64_t)rows * C1, 256, 8), C_PAN1 / 8), 256, 0, st>>>(
+        pan_stem_map_kernel<<<grid_for((int64_t)rows * C1, 256, 8), 256, 0, st>>>(
             n->use_mspan ? s->mspan : s->pan, s->H4p, s->W4p, s->pan_pitch, b0, rows, R1, C1, d->w_pan1, n->sc_pan1, n->sh_pan1, d->B1);
         DMF_LAUNCHED();
         mark();
