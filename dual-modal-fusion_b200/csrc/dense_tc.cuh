@@ -44,7 +44,7 @@ struct FuseRowsParams {
 
 constexpr int kFrKQ = 8, kFrStages = 7, kFrPitch = 272;      // 7 x 16 KB of CAT rows in flight per SM (the kernel is bound by memory-level parallelism)
 constexpr uint32_t kFrStage = kFrKQ * 128 * 16;                                        // 16 KB
-constexpr size_t kFrSmem = (size_t)256 * 128 * 2 + kFrStages * kFrStage + 128 * kFrPitch + 2 * 128 * 4 + 24 * 8;
+constexpr size_t kFrSmem = (size_t)256 * 128 * 2 + kFrStages * kFrStage + 128 * kFrPitch + 2 * 128 * 4 + 26 * 8;
 
 template <int P2>
 __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_constant__ FuseRowsParams P) {
@@ -60,14 +60,19 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
     float* scale_s = reinterpret_cast<float*>(f_s + 128 * kFrPitch);
     float* shift_s = scale_s + C_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
-    // bars: [0,S) full, [S,2S) empty, 2S weights, 2S+1 tmem_full, 2S+2 tmem_empty   (S = kFrStages)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFrStages + 4);
+    // bars: [0,S) full, [S,2S) empty, 2S weights, 2S+1.. tmem_full[4], 2S+5.. tmem_empty[4]   (S = kFrStages)
+    // TMEM is a ring of four 128-column accumulators, one per (tile, column class): the MMA warp runs up to four classes ahead of the
+    // epilogue, which hands every accumulator back as soon as it has read it (with one barrier pair per TILE the MMA warp waited for the
+    // drain a third of its time and the epilogue warps for the MMAs 39 % of theirs: ncu source view, round 2).
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFrStages + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (kFrStages + s); };
-    const uint32_t w_bar = bar0 + 8u * (2 * kFrStages), tfull_bar = bar0 + 8u * (2 * kFrStages + 1), tempty_bar = bar0 + 8u * (2 * kFrStages + 2);
+    const uint32_t w_bar = bar0 + 8u * (2 * kFrStages);
+    auto tfull_bar = [&](uint32_t slot) { return bar0 + 8u * (2 * kFrStages + 1 + slot); };
+    auto tempty_bar = [&](uint32_t slot) { return bar0 + 8u * (2 * kFrStages + 5 + slot); };
 
     for (int i = threadIdx.x; i < C_OUT; i += 320) {
         scale_s[i] = P.scale[i];
@@ -76,8 +81,7 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < kFrStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
-        mbar_init(tfull_bar, 1);
-        mbar_init(tempty_bar, 8);
+        for (uint32_t k = 0; k < 4; ++k) { mbar_init(tfull_bar(k), 1); mbar_init(tempty_bar(k), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -141,13 +145,13 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), C_OUT * 16, 128);
         int st = 0;
         uint32_t ph = 0;
-        int it = 0;                                    // tiles actually processed
+        uint32_t unit = 0;                             // (tile, class) accumulators started
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (!live()) continue;
-            mbar_wait(tempty_bar, (it & 1) ^ 1);
-            ++it;
             for (int step = 0; step < 3 * NSTEP; ++step) {
-                const int b = step / NSTEP, kq = step % NSTEP;
+                const int kq = step % NSTEP;
+                const uint32_t slot = unit & 3u;
+                if (kq == 0) mbar_wait(tempty_bar(slot), ((unit >> 2) & 1u) ^ 1u);
                 mbar_wait(full_bar(st), ph);
                 tc_fence_after();
                 const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * kFrStage, A_PLANE, 128);
@@ -156,12 +160,13 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
                     for (int j = 0; j < kFrKQ / 2; ++j) {
                         const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(2 * j) * A_PLANE) >> 4);
                         const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)((kq * kFrKQ + 2 * j) * C_OUT * 16) >> 4);
-                        umma_bf16(tmem_base + (uint32_t)(b * C_OUT), ad, bd, idesc, (kq | j) ? 1u : 0u);
+                        umma_bf16(tmem_base + slot * (uint32_t)C_OUT, ad, bd, idesc, (kq | j) ? 1u : 0u);
                     }
                     umma_commit(empty_bar(st));
-                    if (step == 3 * NSTEP - 1) umma_commit(tfull_bar);
+                    if (kq == NSTEP - 1) umma_commit(tfull_bar(slot));
                 }
                 __syncwarp();
+                if (kq == NSTEP - 1) ++unit;
                 if (++st == kFrStages) { st = 0; ph ^= 1; }
             }
         }
@@ -170,24 +175,27 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
         const int q = warp & 3, hc = (warp - 2) >> 2;
         const int m = q * 32 + lane;                      // phase 1: column of the tile; phase 2: anchor column
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-        int it = 0;                                    // tiles actually processed
+        uint32_t unit = 0;                             // (tile, class) accumulators drained
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (!live()) continue;
-            mbar_wait(tfull_bar, it & 1);
-            ++it;
-            tc_fence_after();
             // One F tile (one column class) in shared memory at a time; the row sums live in 64 fp32 registers per thread
             // (thread = anchor column m, channel half hc).  Class 0 contributes F[a,0][X][y] = the thread's OWN TMEM lane: no
             // exchange; class 1 contributes the columns y + 2l, l = 1 .. P2-2, class 2 the column y + 2(P2-1): through the tile.
             // Same fp16 rounding points and the same fp32 summation order (l ascending) as a materialised F tensor.
             float acc[64];
             const bool act = !(P.dbg & 2);
-            auto drain = [&](int b, bool to_regs) {
+            // next accumulator of the ring: wait for its MMAs, read it (when `act`), hand it back
+            auto drain = [&](bool to_regs) {
+                const uint32_t slot = unit & 3u;
+                mbar_wait(tfull_bar(slot), (unit >> 2) & 1u);
+                ++unit;
+                tc_fence_after();
+                if (act) {
 #pragma unroll
                 for (int cg = 0; cg < 2; ++cg) {
                     const int c0 = hc * 64 + cg * 32;
                     uint32_t v[32];
-                    tmem_ld32(t_row + (uint32_t)(b * C_OUT + c0), v);
+                    tmem_ld32(t_row + slot * (uint32_t)C_OUT + (uint32_t)c0, v);
                     const float4* sc4 = reinterpret_cast<const float4*>(scale_s + c0);
                     const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
                     uint32_t pk[16];
@@ -214,6 +222,10 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
                         for (int s4 = 0; s4 < 4; ++s4) dst[s4] = make_uint4(pk[4 * s4], pk[4 * s4 + 1], pk[4 * s4 + 2], pk[4 * s4 + 3]);
                     }
                 }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(slot));
             };
             auto add_col = [&](int col) {                              // acc += F tile row `col`, this thread's 64 channels
 #pragma unroll
@@ -230,20 +242,15 @@ __global__ void __launch_bounds__(320, 1) fuse_rowsum_kernel(const __grid_consta
             };
             const int y = tx * VALID + m;
             const bool mine = m < VALID && y < P.W && act;
-            if (act) {
-                drain(0, true);                                           // l = 0
-                drain(1, false);
-            }
+            drain(true);                                                  // class 0: l = 0
+            drain(false);                                                 // class 1
             asm volatile("bar.sync 1, 256;" ::: "memory");                // class-1 tile complete
             if (mine) {
 #pragma unroll
                 for (int l = 1; l < P2 - 1; ++l) add_col(m + 2 * l);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");                // class-1 tile consumed
-            if (act) drain(2, false);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar);                       // accumulators drained: the next tile's MMAs may start
+            drain(false);                                                 // class 2
             asm volatile("bar.sync 1, 256;" ::: "memory");                // class-2 tile complete
             if (mine) {
                 add_col(m + 2 * (P2 - 1));
