@@ -357,7 +357,10 @@ struct Pool4Cfg {
     static constexpr uint32_t WBYTES = 9u * C_IN * C_OUT * 2;
     static constexpr uint32_t CLS_BYTES = (9 * sizeof(Pool4Cls) + 15) / 16 * 16;
     static constexpr uint32_t XCHG = SHARE ? 2u * 64u * C_OUT : 0u;         // 2 buffers x 8 lanes x C_OUT channels x fp16 x 4 lane quarters
-    static constexpr size_t SMEM = WBYTES + (size_t)STAGES * STAGE + 2 * C_OUT * 4 + (2 * STAGES + 12) * 8 + CLS_BYTES + XCHG;
+    static constexpr int GRAN = SHARE ? 1 : MAX_BOXES;                       // boxes per slot of the A ring: SHARE allocates it box by box (see conv_pool4_kernel)
+    static constexpr int NSLOT = STAGES * MAX_BOXES / GRAN;
+    static constexpr size_t SMEM = WBYTES + (size_t)STAGES * STAGE + 2 * C_OUT * 4 + (2 * NSLOT + 12) * 8 + CLS_BYTES + XCHG;
+    static_assert(NSLOT <= 32, "slot phase bits live in one 32-bit word");
     static_assert(KCH % KQ == 0 && KQ % 2 == 0 && NBUF * 4 * C_OUT <= 512 && WBYTES % 128 == 0 && (!SHARE || NBUF == 1), "pool4 configuration");
 };
 
@@ -433,17 +436,28 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
     float* scale_s = reinterpret_cast<float*>(a_s + (size_t)STAGES * Cfg::STAGE);
     float* shift_s = scale_s + C_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(shift_s + C_OUT);
-    // bars: [0,S) full; [S,2S) empty; 2S weights; 2S+1.. tmem_full[4]; 2S+5.. tmem_empty[4]   (NBUF = 2 uses two of each)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
-    Pool4Cls* cls_s = reinterpret_cast<Pool4Cls*>(bars + 2 * STAGES + 12);
+    // SHARE: the A ring is a ring of NSLOT box slots, not of stages: a pipeline step takes as many consecutive slots as its class has
+    // boxes (1 .. 4 of the 8; it restarts at slot 0 rather than wrap), so the classes with few input sources keep up to 8 steps in
+    // flight instead of 2 — their tiles are short (9 instructions per step in the interior / interior class) and two steps did not
+    // cover the load latency.  Per-slot mbarriers: `full` of a step's FIRST slot, `empty` of every slot it used.  Otherwise (pan2: one
+    // step per tile, 4 .. 9 boxes) a slot is a whole stage: per-box barriers cost more there than the extra depth gives (4.05 -> 4.4 ms).
+    // bars: [0,NS) full; [NS,2NS) empty; 2NS weights; 2NS+1.. tmem_full[4]; 2NS+5.. tmem_empty[4]   (NBUF = 2 uses two of each)
+    constexpr int NSLOT = Cfg::NSLOT;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 10);
+    Pool4Cls* cls_s = reinterpret_cast<Pool4Cls*>(bars + 2 * NSLOT + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    const uint32_t w_bar = bar0 + 8u * (2 * STAGES);
-    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 1 + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 5 + a); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (NSLOT + s); };
+    const uint32_t w_bar = bar0 + 8u * (2 * NSLOT);
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NSLOT + 1 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NSLOT + 5 + a); };
+    auto take_boxes = [](int& head, int n) {           // first slot of a step with n boxes
+        const int h = head + n > NSLOT ? 0 : head;
+        head = h + n == NSLOT ? 0 : h + n;
+        return h;
+    };
     // NBUF = 1: TMEM is a ring of 4 slots of C_OUT columns; a tile takes ns * nt (1, 2 or 4) slots, aligned to its size, so the
     // tiles that share sub-positions with their neighbours leave room for the next tile's MMAs while they are drained.
     constexpr int kSlots = NBUF == 1 ? 4 : NBUF;
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
     for (int i = threadIdx.x; i < 9 * (int)(sizeof(Pool4Cls) / 4); i += kThreads)
         reinterpret_cast<uint32_t*>(cls_s)[i] = reinterpret_cast<const uint32_t*>(P.cls)[i];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(w_bar, 1);
         for (int a = 0; a < kSlots; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NBUF == 2 ? 4 : EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -502,28 +516,30 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
                 bulk_load(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(P.w) + off, min(CH, WBYTES - off), w_bar);
         }
         __syncwarp();
-        int st = 0;
-        uint32_t ph = 1;
+        int head = 0;                                  // next free box slot
+        uint32_t eph = 0;                              // phase bit of every slot's empty barrier
         for (int i = 0; i < n_local; ++i, next_tile()) {
             if (!live()) continue;
             const int nbx = cls_s[c].n_boxes;
             const int ca = cls_s[c].ca, cb = cls_s[c].cb;
             const int row0 = P.row_lo[ca] + ty * P.trow[ca], col0 = P.col_lo[cb] + tx * P.tcol[cb];
+            const int nsl = SHARE ? nbx : 1;               // ring slots of a step
             for (int kq = 0; kq < NSTEP; ++kq) {
-                mbar_wait(empty_bar(st), ph);
+                const int h = take_boxes(head, nsl);
+                for (int k = h; k < h + nsl; ++k) mbar_wait(empty_bar(k), ((eph >> k) & 1u) ^ 1u);
+                eph ^= ((1u << nsl) - 1u) << h;
                 if (leader) {
                     if (P.dbg & 1) {
-                        mbar_arrive(full_bar(st));
+                        mbar_arrive(full_bar(h));
                     } else {
-                        mbar_expect_tx(full_bar(st), (uint32_t)nbx * Cfg::BOX_BYTES);
-                        const uint32_t dst = smem_u32(a_s) + (uint32_t)st * Cfg::STAGE;
+                        mbar_expect_tx(full_bar(h), (uint32_t)nbx * Cfg::BOX_BYTES);
+                        const uint32_t dst = smem_u32(a_s) + (uint32_t)h * (Cfg::GRAN * Cfg::BOX_SLOT);
                         for (int b = 0; b < nbx; ++b)
-                            tma_load_4d(dst + (uint32_t)b * Cfg::BOX_SLOT, &in_map, full_bar(st), (col0 + cls_s[c].box_dcol[b]) * 8,
+                            tma_load_4d(dst + (uint32_t)b * Cfg::BOX_SLOT, &in_map, full_bar(h), (col0 + cls_s[c].box_dcol[b]) * 8,
                                         cls_s[c].box_plane[b], row0 + cls_s[c].box_drow[b], kq * KQ);
                     }
                 }
                 __syncwarp();
-                if (++st == STAGES) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -533,8 +549,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
         const bool leader = elect_one();
         mbar_wait(w_bar, 0);
         const uint64_t w_desc0 = umma_desc(smem_u32(w_s), 9 * C_OUT * 16, 128);
-        int st = 0;
-        uint32_t ph = 0;
+        int head = 0;                                  // next box slot of the A ring
+        uint32_t aph = 0;                              // phase bit of every slot's full barrier
         int it = 0;                                    // tiles actually processed
         int ring = 0;                                  // NBUF = 1: next free TMEM slot
         uint32_t eph = 0;                              // NBUF = 1: phase bit of every slot's tmem_empty barrier
@@ -563,20 +579,22 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_pool4_kernel(const __gri
                 win[2 * k + 1] = (int)(int16_t)(w2 >> 16);
             }
             uint32_t started = 0;                          // bit s: the accumulator blocks of sub-position row s have been written
+            const int nsl = SHARE ? cls_s[c].n_boxes : 1;  // ring slots of a step
             for (int kq = 0; kq < NSTEP; ++kq) {
-                mbar_wait(full_bar(st), ph);
+                const int h = take_boxes(head, nsl);
+                mbar_wait(full_bar(h), (aph >> h) & 1u);
+                aph ^= 1u << h;
                 tc_fence_after();
-                const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)st * Cfg::STAGE, Cfg::PLANE, SBO_A);
+                const uint64_t a_desc0 = umma_desc(smem_u32(a_s) + (uint32_t)h * (Cfg::GRAN * Cfg::BOX_SLOT), Cfg::PLANE, SBO_A);
                 if (leader) {
                     if (!SHARE || (ns == 2 && nt == 2)) pool4_issue_step<C_OUT, KQ, Cfg::PLANE, 2, 2>(win, a_desc0, w_desc0, d_tmem, kq, started);
                     else if (ns == 2) pool4_issue_step<C_OUT, KQ, Cfg::PLANE, 2, 1>(win, a_desc0, w_desc0, d_tmem, kq, started);
                     else if (nt == 2) pool4_issue_step<C_OUT, KQ, Cfg::PLANE, 1, 2>(win, a_desc0, w_desc0, d_tmem, kq, started);
                     else pool4_issue_step<C_OUT, KQ, Cfg::PLANE, 1, 1>(win, a_desc0, w_desc0, d_tmem, kq, started);
-                    umma_commit(empty_bar(st));
+                    for (int k = h; k < h + nsl; ++k) umma_commit(empty_bar(k));
                     if (kq == NSTEP - 1) umma_commit(tfull_bar(buf));
                 }
                 __syncwarp();
-                if (++st == STAGES) { st = 0; ph ^= 1; }
             }
         }
     } else {
