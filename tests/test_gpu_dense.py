@@ -10,6 +10,9 @@ The dense path evaluates every layer once per scene position and border class in
     oracle (|d| <= LOGIT_ATOL + LOGIT_RTOL*|logit|), argmax agreement >= 99.9 %, label map == argmax of the returned
     logits, confusion matrix == oracle.confusion(pred, label) bit for bit.
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -287,3 +290,47 @@ def test_ihs_product_as_pan_input(dmf):
     with pytest.raises(RuntimeError, match='IHS product'):
         h.infer_scene(bare)
     h.close()
+
+
+_SHARE_PROBE = r'''
+import os, sys
+import numpy as np
+import torch
+sys.path[:0] = [%(tests)r, %(repo)r, %(pkg)r]
+import dmf
+import test_gpu_dense as T
+out = {}
+for p, H, W, band in ((16, 45, 61, 24), (8, 40, 33, 64), (32, 20, 37, 9)):
+    ms, pan, label, sc, ref, h = T.scene_and_net(dmf, p, H, W, 8, seed=5)
+    h.set_dense(True, band_rows=band)
+    pm, cm, lg = h.infer_scene(sc, want_logits=True)
+    torch.cuda.synchronize()
+    out['pm%%d' %% p], out['cm%%d' %% p], out['lg%%d' %% p] = pm.cpu().numpy(), cm.cpu().numpy(), lg.cpu().numpy()
+    h.close()
+np.savez(sys.argv[1], **out)
+'''
+
+
+def test_shared_sub_positions_equal_the_unshared_evaluation(dmf, tmp_path):
+    """The stride-1 conv + pool layers let interior-class cells take sub-position 1 from their neighbour (dense_tc.cuh, SHARE);
+    DMF_DENSE_SHARE=0 makes every cell evaluate all four itself.  Both are the same conv outputs (other fp32 summation order of the
+    column taps at most), so the label maps must agree and the logits differ by rounding only.  The switch is read once per process."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    repo = os.path.dirname(here)
+    code = _SHARE_PROBE % {'tests': here, 'repo': repo, 'pkg': os.path.join(repo, 'dual-modal-fusion_b200')}
+    res = {}
+    for tag, val in (('shared', '1'), ('unshared', '0')):
+        path = str(tmp_path / (tag + '.npz'))
+        env = dict(os.environ, DMF_DENSE_SHARE=val)
+        r = subprocess.run([sys.executable, '-c', code, path], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = np.load(path)
+    for p in (16, 8, 32):
+        a, b = res['shared']['lg%d' % p], res['unshared']['lg%d' % p]
+        tol = LOGIT_ATOL + LOGIT_RTOL * np.abs(b).max()
+        assert np.abs(a - b).max() <= 0.1 * tol, 'p=%d: shared vs unshared logits differ by %g (rounding-level bound %g)' % (p, np.abs(a - b).max(), 0.1 * tol)
+        pa, pb = res['shared']['pm%d' % p], res['unshared']['pm%d' % p]
+        assert (pa == pb).mean() >= 0.999, 'p=%d: label maps agree on %.5f' % (p, (pa == pb).mean())
+        if np.array_equal(pa, pb):
+            assert np.array_equal(res['shared']['cm%d' % p], res['unshared']['cm%d' % p])
