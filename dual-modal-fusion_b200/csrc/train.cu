@@ -18,6 +18,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "net_geom.cuh"
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const FinishJobs J) {
 constexpr int kStemRows = 16;
 
 // forward: x [N][S][S] fp32 -> Z [N][4][S][S][8] bf16 (conv3x3 1->32, zero padding, no bias) + sum z, sum z^2
-__global__ void __launch_bounds__(256) pan1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int S, int64_t N,
+__global__ void __launch_bounds__(256, 2) pan1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int S, int64_t N,
                                                        __nv_bfloat16* __restrict__ Z, double* __restrict__ stats) {
     __shared__ float st_s[2][T_PAN1];
     if (threadIdx.x < 2 * T_PAN1) (&st_s[0][0])[threadIdx.x] = 0.f;
@@ -835,10 +837,28 @@ static int wgrad_finish(dmf_train* t, const int* layers, int count, cudaStream_t
     return DMF_OK;
 }
 
+// Blocks of `threads` threads of a kernel that are resident per SM (registers / shared memory), cached per kernel.  The grid-stride
+// kernels below are launched as exactly ONE wave: with 4 blocks per SM requested and 3 resident (79 registers) the statistics pass of
+// the BatchNorm backward ran 1.33 waves and took as long as 2; the PAN stem forward (188 registers, 1 block resident) ran 4.
+template <typename K>
+static int resident_blocks(K kernel, int threads) {
+    static std::map<const void*, int> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    const void* key = reinterpret_cast<const void*>(kernel);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
+    cache[key] = n;
+    return n;
+}
+
 // PAN stem kernels: one warp per (patch, 16-row segment, chunk, 32-column group)
-static int stem_grid(int64_t N, int S) {
+template <typename K>
+static int stem_grid(K kernel, int64_t N, int S) {
     const int64_t tasks = N * (S / kStemRows) * 4 * (S / 32);
-    return (int)std::max<int64_t>(1, std::min<int64_t>((tasks + 7) / 8, (int64_t)num_sms() * 4));
+    return (int)std::max<int64_t>(1, std::min<int64_t>((tasks + 7) / 8, (int64_t)num_sms() * resident_blocks(kernel, 256)));
 }
 
 static int ew_grid(int64_t items) { return (int)std::min<int64_t>((items + 255) / 256, (int64_t)num_sms() * 8); }
@@ -858,10 +878,12 @@ template <int SRC>
 static int bn_backward(dmf_train* t, int layer, const void* dsrc, int dchunks, int dchunk0, int64_t N, cudaStream_t st) {
     const int C = kCout[layer], S = S_of(t, layer), So = SRC == 0 ? S / 2 : S;
     const int64_t items = N * So * So;
-    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((items + 255) / 256, std::max(1, num_sms() * 4 / (C / 8)))), C / 8);
-    bn_bwd_kernel<SRC, false><<<grid, 256, 0, st>>>(t->Z[layer], dsrc, dchunks, dchunk0, t->bn[layer], C, S, N, t->dZ);
+    auto grid_of = [&](int resident) {
+        return dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((items + 255) / 256, std::max(1, num_sms() * resident / (C / 8)))), C / 8);
+    };
+    bn_bwd_kernel<SRC, false><<<grid_of(resident_blocks(bn_bwd_kernel<SRC, false>, 256)), 256, 0, st>>>(t->Z[layer], dsrc, dchunks, dchunk0, t->bn[layer], C, S, N, t->dZ);
     DMF_LAUNCHED();
-    bn_bwd_kernel<SRC, true><<<grid, 256, 0, st>>>(t->Z[layer], dsrc, dchunks, dchunk0, t->bn[layer], C, S, N, t->dZ);
+    bn_bwd_kernel<SRC, true><<<grid_of(resident_blocks(bn_bwd_kernel<SRC, true>, 256)), 256, 0, st>>>(t->Z[layer], dsrc, dchunks, dchunk0, t->bn[layer], C, S, N, t->dZ);
     DMF_LAUNCHED();
     return DMF_OK;
 }
@@ -909,7 +931,7 @@ static int train_forward(dmf_train* t, const float* ms, const float* pan, int64_
     // PAN branch
     {
         const int S = 4 * p;
-        pan1_fwd_kernel<<<stem_grid(N, S), 256, 0, st>>>(pan, t->pan1w, S, N, t->Z[L_PAN1], t->bn[L_PAN1].stats);
+        pan1_fwd_kernel<<<stem_grid(pan1_fwd_kernel, N, S), 256, 0, st>>>(pan, t->pan1w, S, N, t->Z[L_PAN1], t->bn[L_PAN1].stats);
         DMF_LAUNCHED();
     }
     DMF_TRY(bn_forward(t, L_PAN1, true, t->B1, T_PAN1 / 8, 0, N, st));
@@ -960,7 +982,7 @@ static int train_backward(dmf_train* t, const float* dlogits, cudaStream_t st) {
     DMF_TRY(bn_backward<0>(t, L_PAN1, t->dA, T_PAN1 / 8, 0, N, st));
     {
         const int S = 4 * p;
-        pan1_wgrad_kernel<<<stem_grid(N, S), 256, 0, st>>>(t->dZ, t->pan_patches, S, N, t->dpan1w);
+        pan1_wgrad_kernel<<<stem_grid(pan1_wgrad_kernel, N, S), 256, 0, st>>>(t->dZ, t->pan_patches, S, N, t->dpan1w);
         DMF_LAUNCHED();
     }
     const int all[5] = {L_MS1, L_MS2, L_PAN2, L_PAN3, L_FUSE};
@@ -1219,7 +1241,7 @@ int dmf_train_debug_op(dmf_train* t, int op, int layer, int64_t N, void* stream)
     if (op == 1) {
         DMF_CUDA(cudaMemsetAsync(t->bn[layer].stats, 0, sizeof(double) * 4 * kStatStride, st));
         if (layer != L_PAN1) return fwd_conv(t, layer, N, st);
-        pan1_fwd_kernel<<<stem_grid(N, S), 256, 0, st>>>(t->in_pan, t->pan1w, S, N, t->Z[L_PAN1], t->bn[L_PAN1].stats);
+        pan1_fwd_kernel<<<stem_grid(pan1_fwd_kernel, N, S), 256, 0, st>>>(t->in_pan, t->pan1w, S, N, t->Z[L_PAN1], t->bn[L_PAN1].stats);
         DMF_LAUNCHED();
         return DMF_OK;
     }
@@ -1229,7 +1251,7 @@ int dmf_train_debug_op(dmf_train* t, int op, int layer, int64_t N, void* stream)
             DMF_TRY(wgrad_conv(t, layer, N, st));
             return wgrad_finish(t, &layer, 1, st);
         }
-        pan1_wgrad_kernel<<<stem_grid(N, S), 256, 0, st>>>(t->dZ, t->in_pan, S, N, t->dpan1w);
+        pan1_wgrad_kernel<<<stem_grid(pan1_wgrad_kernel, N, S), 256, 0, st>>>(t->dZ, t->in_pan, S, N, t->dpan1w);
         DMF_LAUNCHED();
         return DMF_OK;
     }
