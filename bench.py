@@ -465,7 +465,10 @@ def main():
                                            'position / the same time, comparable with the lines before the sharing (profiles/r02_bench_before_sharing.json)'},
                 'whole_step_executed_TFLOPs': conv_fl / (stage['total'] / 1e3) / 1e12,
                 'per_patch_equivalent_tflops': h.flops_per_patch * n_loc / (stage['total'] / 1e3) / 1e12,
-                'note': 'achieved = tensor-core FLOPs this kernel executes / its time (one isolated pass with per-stage events); '
+                'note': 'achieved = tensor-core FLOPs this kernel EXECUTES / its time (one isolated pass with per-stage events).  The stride-1 '
+                        'layers execute a third fewer FLOPs for the same results since their interior-class cells share conv outputs with '
+                        'their neighbours, so this utilisation figure fell (0.80 -> 0.6 of burst) while the time per scene fell by a fifth: '
+                        'stride1_layers.unshared_equivalent_TFLOPs is the figure comparable with earlier lines; '
                         'per_patch_equivalent_tflops = the per-patch network FLOPs the same result would cost / whole-step time: it '
                         'exceeds the peak because the dense algorithm shares work between overlapping patches'}
         a = conv_fl / (conv_ms / 1e3) / 1e12
