@@ -21,9 +21,10 @@ from .gmfnet_ref import Net
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'fitted_nets.npz')
 
 # workload tag -> (H, W, classes without background, patch size)
-WORKLOADS = {'c1': (128, 128, 7, 16), 'c2': (1000, 1000, 12, 16), 'c3': (2001, 2101, 11, 16), 'smoke': (40, 36, 7, 16)}
+WORKLOADS = {'c1': (128, 128, 7, 16), 'c2': (1000, 1000, 12, 16), 'c3': (2001, 2101, 11, 16), 'smoke': (40, 36, 7, 16),
+             'p8': (96, 100, 7, 8), 'p32': (96, 104, 7, 32)}          # the other patch sizes of BASELINE.json configs[4]
 # (scene seed, label seed, region size in MS pixels): land-cover regions a few patches wide, so that most patches are not mixtures
-SCENES = {'c1': (0, 1, 32), 'c2': (0, 1, 64), 'c3': (0, 1, 64), 'smoke': (2, 3, 20)}
+SCENES = {'c1': (0, 1, 32), 'c2': (0, 1, 64), 'c3': (0, 1, 64), 'smoke': (2, 3, 20), 'p8': (4, 5, 24), 'p32': (6, 7, 32)}
 
 
 def scene(tag):

@@ -106,9 +106,10 @@ def test_c1_fitted_whole_scene_matches_reference_run(golden):
         print('%s: agreement %.5f, %d classes predicted, Kappa %.4f' % (what, agree, len(np.unique(pm)), orc.aa_oa(M)[2]))
 
 
-@pytest.mark.parametrize('tag', ['c2', 'c3'])
+@pytest.mark.parametrize('tag', ['c2', 'c3', 'p8', 'p32'])
 def test_full_scale_fitted_sampled_pixels_vs_fp32_oracle(tag):
-    """>= 20 000 sampled pixels of the C2 / C3 scene: whole-scene dense inference vs the fp32 oracle on the same patches."""
+    """>= 20 000 sampled pixels of the C2 / C3 scene: whole-scene dense inference vs the fp32 oracle on the same patches.
+    p8 / p32: the other patch sizes of BASELINE.json configs[4], small scenes, EVERY pixel."""
     import dmf
     H, W, ncls, p = fitted_net.WORKLOADS[tag]
     C = ncls + 1
@@ -126,10 +127,10 @@ def test_full_scale_fitted_sampled_pixels_vs_fp32_oracle(tag):
     assert len(np.unique(pm)) >= 5 and k > 0.1, 'the fitted net must be non-degenerate: %d classes, Kappa %.3f' % (len(np.unique(pm)), k)
     ref = fitted_net.fitted_net(tag).to(DEV)
     rng = np.random.default_rng(123)
-    n = 24000
+    n = min(24000, H * W)
     idx = np.sort(rng.choice(H * W, size=n, replace=False))
-    # corners and edges too (reflect padding on the bottom / right, the band seams of the dense path every 512 rows)
-    idx[:8] = [0, W - 1, (H - 1) * W, H * W - 1, 511 * W + 5, 512 * W + 5, (H - 1) * W + W // 2, (H // 2) * W + W - 1]
+    if n < H * W:   # corners and edges too (reflect padding on the bottom / right, the band seams of the dense path every 512 rows)
+        idx[:8] = [0, W - 1, (H - 1) * W, H * W - 1, 511 * W + 5, 512 * W + 5, (H - 1) * W + W // 2, (H // 2) * W + W - 1]
     want = []
     with torch.no_grad():
         for i in range(0, n, 2000):
