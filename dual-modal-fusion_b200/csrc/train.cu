@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const FinishJobs J) {
 constexpr int kStemRows = 16;
 
 // forward: x [N][S][S] fp32 -> Z [N][4][S][S][8] bf16 (conv3x3 1->32, zero padding, no bias) + sum z, sum z^2
-__global__ void __launch_bounds__(256, 2) pan1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int S, int64_t N,
+__global__ void __launch_bounds__(256) pan1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int S, int64_t N,
                                                        __nv_bfloat16* __restrict__ Z, double* __restrict__ stats) {
     __shared__ float st_s[2][T_PAN1];
     if (threadIdx.x < 2 * T_PAN1) (&st_s[0][0])[threadIdx.x] = 0.f;
