@@ -49,21 +49,29 @@ net.train_step_scene(scene, torch.from_numpy(subs[rank]).to(dev), NoStep(), glob
 g_dp = net.trainer().flat_grad.clone()
 ok, worst = True, 0.0
 if rank == 0:
-    acc, n = torch.zeros_like(g_dp), 0
-    for r in range(world):
+    def solo_grad(r):
         solo = fresh()
         h = solo.trainer()
         h.reseat_grads()
         h.step_scene(scene, torch.from_numpy(subs[r]).to(dev))          # no collective: the raw local gradient of sub-batch r
-        acc += h.flat_grad * len(subs[r])
-        n += len(subs[r])
-    want = acc / n
-    err = (g_dp - want).abs().max().item()
+        return h.flat_grad.clone()
+    solos = [solo_grad(r) for r in range(world)]
+    n = sum(len(s_) for s_ in subs)
+    want = sum(g * len(s_) for g, s_ in zip(solos, subs)) / n
+    plain = sum(solos) / world                                          # the UNWEIGHTED mean: must explain the result worse
     scale = want.abs().max().item()
+    err = (g_dp - want).abs().max().item()
+    err_plain = (g_dp - plain).abs().max().item()
+    # The step is not bit-reproducible (fp32 / fp64 atomics in the weight-gradient and BatchNorm reductions, bf16 storage of Z / dZ: a
+    # last-bit change of a sum can move a stored value by one bf16 ulp): the same sub-batch twice gives the noise floor of this check.
+    noise = max((solo_grad(r) - solos[r]).abs().max().item() for r in range(world))
     worst = err / scale
-    ok = worst <= 1e-4
+    # Measured over repeated runs: rel is ~4e-5 most of the time and jumps to 5e-4 .. 9e-4 when one stored bf16 value flips (the rerun
+    # noise shows the same two levels); the unweighted mean is off by 7e-3.  So: within 2e-3, and at least 3x closer than the unweighted mean.
+    ok = worst <= 2e-3 and 3.0 * err < err_plain
     print(json.dumps({'check': 'data-parallel flat gradient == sample-weighted mean of the single-rank gradients of the same sub-batches',
-                      'world': world, 'sub_batches': [len(s) for s in subs], 'max_abs_err': err, 'max_abs_grad': scale, 'rel': worst, 'ok': ok}))
+                      'world': world, 'sub_batches': [len(s) for s in subs], 'max_abs_err': err, 'max_abs_grad': scale, 'rel': worst,
+                      'rerun_noise_rel': noise / scale, 'unweighted_mean_rel': err_plain / scale, 'ok': ok}))
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 dist.destroy_process_group()
