@@ -15,6 +15,9 @@ Scene = oracle.synthetic_scene_structured (labels depend on the rasters); networ
 HOST rasters — H2D + range + normalise/pad + inference + all-reduce + D2H of label band and matrix + OA/AA/Kappa every step,
 software-pipelined (scene i+1 uploads while scene i is classified).  `--impl reference` times the reference's own CPU
 objects (oracle/_ref through oracle/ref_runner.py; the oracle port if that copy is absent) on all host cores.
+oracle/ in the b200 arm: it only GENERATES INPUTS before any timing starts — the synthetic rasters (numpy) and the weight values of
+the fitted net, loaded into the product's own model.gmfnet.Net with load_state_dict like a checkpoint.  No oracle code computes
+anything on the product path or inside a timed region; the oracle's compute runs in the `cpu_baseline` / `--impl reference` legs only.
 """
 import argparse
 import json
